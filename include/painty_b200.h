@@ -1,0 +1,183 @@
+/* painty_b200 — C ABI of the B200-native paint-renderer hot path (imprint + Kubelka-Munk compose).
+ *
+ * painty has no plugin / FFI layer: its boundary is the C++ template API in namespace painty
+ * (SURVEY.md §8b). This header is the flat surface the C++ façade in include/painty/ forwards to,
+ * and that any other host (ctypes, cgo, JNI) can bind. Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - Every call returns 0 on success, non-zero on failure; pb_last_error() (thread local) explains.
+ *     The C++ façade rethrows the exception type the reference would have thrown.
+ *   - "host AoS f64" = the reference's own boundary layout: Mat<vec3> = rows*cols*3 doubles,
+ *     Mat<double> = rows*cols doubles, row-major (painty/image/Mat.hxx:40-41, core/Vec.hxx:35).
+ *   - Device storage is SoA planes in HBM: Kr,Kg,Kb,Sr,Sg,Sb,V (+R0r,R0g,R0b,h for a canvas), dense
+ *     row-major, element type float (PB_F32) or double (PB_F64 validation mode) per context.
+ *   - One context per device; a handle is not thread safe; all work is ordered on the context's stream
+ *     (the reference is single-submitter too: GpuTaskQueue = ThreadPool{1}, gpu/GpuTaskQueue.hxx:33-46).
+ *   - Canvas / PaintLayer constructors take (rows, cols) like the reference.
+ *   - There is no CPU fallback: without a CUDA device every entry point fails with an error.
+ */
+#ifndef PAINTY_B200_H
+#define PAINTY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_context pb_context;
+typedef struct pb_canvas pb_canvas; /* painty::Canvas<vec3>           renderer/Canvas.hxx:20-198 */
+typedef struct pb_layer pb_layer;   /* painty::PaintLayer<vec3>       renderer/PaintLayer.hxx:22-145 */
+typedef struct pb_fbrush pb_fbrush; /* painty::FootprintBrush<vec3>   renderer/FootprintBrush.hxx:22-503 */
+typedef struct pb_tbrush pb_tbrush; /* painty::TextureBrush<vec3>     renderer/TextureBrush.hxx:19-237 */
+
+enum { PB_F32 = 0, PB_F64 = 1 };
+
+const char* pb_last_error(void);
+int pb_version(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+int pb_context_create(int device, int precision, pb_context** out);
+int pb_context_destroy(pb_context* ctx);
+int pb_context_synchronize(pb_context* ctx);
+int pb_context_precision(const pb_context* ctx);
+void* pb_context_stream(pb_context* ctx); /* cudaStream_t all work of this context is ordered on */
+/* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t pb_context_launch_count(const pb_context* ctx);
+
+/* ---- host-side scalar calls that stay on the host (bit-exact f64) ---------------------------- */
+/* core/KubelkaMunk.hxx:28-83 ComputeReflectance<double,3>. */
+int pb_compute_reflectance(const double K[3], const double S[3], const double R0[3], double d, double out[3]);
+/* core/KubelkaMunk.hxx:92-124; fails (invalid_argument) unless 0 < Rb < Rw < 1 per channel. */
+int pb_compute_scattering_absorption(const double Rb[3], const double Rw[3], double K[3], double S[3]);
+/* mixer/src/PaintMixer.cxx:536-548 PaintMixer::mixed. */
+int pb_paint_mixed(const double K1[3], const double S1[3], double v1, const double K2[3], const double S2[3], double v2,
+                   double K[3], double S[3]);
+/* mixer/src/PaintMixer.cxx:327-355 PaintMixer::mixSinglePaint; base = n*3 doubles each. */
+int pb_paint_mix_single(int n, const double* baseK, const double* baseS, int n_weights, const double* weights, double K[3],
+                        double S[3]);
+/* Stroke -> imprint expansion (host, f64).
+ * mode 0: library form FootprintBrush::paintStroke (FootprintBrush.hxx:251-267) with p_pre = path[0]
+ *         for the first segment (the reference indexes path[-1] there: UB);
+ * mode 1: GUI form DigitalCanvas::mouseMoveEvent (apps/painty_gui/DigitalCanvas.cxx:107-123), i.e. the
+ *         imprints produced while the points arrive one by one, control = (p[n-3], p[n-2], p[n-1], p[n-1]).
+ * path = n*2 doubles (x,y). Writes up to `capacity` imprints into cx/cy/theta and returns the full
+ * count in *n_imprints (call with capacity 0 to size). theta = atan2(dir.y, dir.x). */
+int pb_expand_stroke(int mode, int n, const double* path_xy, int64_t capacity, double* cx, double* cy, double* theta,
+                     int64_t* n_imprints);
+
+/* ---- PaintLayer ------------------------------------------------------------------------------ */
+int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out);
+int pb_layer_destroy(pb_layer* l);
+int pb_layer_clear(pb_layer* l);                                                    /* PaintLayer.hxx:68-74 */
+int pb_layer_upload(pb_layer* l, const double* K, const double* S, const double* V); /* host AoS f64 -> SoA */
+int pb_layer_download(pb_layer* l, double* K, double* S, double* V);                 /* any may be NULL */
+int pb_layer_copy(const pb_layer* src, pb_layer* dst);                              /* PaintLayer.hxx:103-111 */
+/* PaintLayer::composeOnto (PaintLayer.hxx:81-96), R0 host AoS f64 in/out. */
+int pb_layer_compose_onto(pb_layer* l, double* R0);
+/* Renderer::compose(layer, R0) (Renderer.hxx:26-41): out = KM(layer over R0), host AoS f64. */
+int pb_layer_compose(pb_layer* l, const double* R0, double* out);
+
+/* ---- Canvas ---------------------------------------------------------------------------------- */
+int pb_canvas_create(pb_context* ctx, int rows, int cols, pb_canvas** out);
+/* Row band [row_begin,row_end) (plus `halo` rows on both sides where they exist) of a rows x cols canvas;
+ * coordinates passed to brushes stay global. Used for multi-GPU sharding. */
+int pb_canvas_create_band(pb_context* ctx, int rows, int cols, int row_begin, int row_end, int halo, pb_canvas** out);
+int pb_canvas_destroy(pb_canvas* c);
+int pb_canvas_rows(const pb_canvas* c);
+int pb_canvas_cols(const pb_canvas* c);
+int pb_canvas_clear(pb_canvas* c);                            /* Canvas.hxx:37-58 */
+int pb_canvas_set_background(pb_canvas* c, const double* R0); /* Canvas.hxx:80-87 (clear + copy) */
+int pb_canvas_dry(pb_canvas* c);                              /* Canvas.hxx:105-121, fused compose+zero+h */
+int pb_canvas_upload_layer(pb_canvas* c, const double* K, const double* S, const double* V);
+/* Download stored rows (all rows of a full canvas; band+halo rows of a band canvas). Any may be NULL. */
+int pb_canvas_download(pb_canvas* c, double* K, double* S, double* V, double* R0, double* h);
+/* Renderer::compose(canvas) (Renderer.hxx:48-53) into host AoS f64 (stored rows). */
+int pb_canvas_compose(pb_canvas* c, double* out);
+/* Same, result stays on the device: 3 planes (r,g,b) of stored_rows*cols elements of the context's
+ * element type, written to caller-provided device memory (plane p at d_out + p*plane_stride elements). */
+int pb_canvas_compose_device(pb_canvas* c, void* d_out, int64_t plane_stride);
+/* Compose only the owned band rows [row_begin,row_end) into d_out (3 planes, band_rows*cols each). */
+int pb_canvas_compose_band_device(pb_canvas* c, void* d_out, int64_t plane_stride);
+/* Device plane pointers (element type of the context): 0-2 K, 3-5 S, 6 V, 7-9 R0, 10 h. */
+int pb_canvas_device_planes(pb_canvas* c, void* planes[11], int64_t* elems_per_plane);
+int pb_canvas_stored_rows(const pb_canvas* c, int* first_row, int* n_rows);
+
+/* ---- raw streaming compose on caller-owned device SoA planes (roofline bench, stacked layers) --- */
+/* R = KM(K,S,V over R0) for n pixels; pointers are device pointers of the context's element type.
+ * R may alias R0 (in-place composeOnto). */
+int pb_km_compose_planes(pb_context* ctx, int64_t n, const void* const K[3], const void* const S[3], const void* V,
+                         const void* const R0[3], void* const R[3]);
+/* L stacked layers bottom-up in one pass, R kept in registers: layer l planes at index l. */
+int pb_km_compose_stacked_planes(pb_context* ctx, int64_t n, int n_layers, const void* const* K /*3*L*/,
+                                 const void* const* S /*3*L*/, const void* const* V /*L*/, const void* const R0[3],
+                                 void* const R[3]);
+
+/* ---- FootprintBrush -------------------------------------------------------------------------- */
+int pb_fbrush_create(pb_context* ctx, pb_fbrush** out);
+int pb_fbrush_destroy(pb_fbrush* b);
+/* FootprintBrush::setRadius (FootprintBrush.hxx:46-63). The host (painty's own io::imRead + ScaledMat +
+ * PaddedMat) supplies the padded footprint: side*side doubles. Acts only when |radius - current| >= 0.5
+ * (then the pickup map is reallocated and zeroed); *acted says which. Pass footprint == NULL to ask
+ * whether a call would act (*acted) without changing anything. */
+int pb_fbrush_set_radius(pb_fbrush* b, double radius, int side, const double* footprint, int* acted);
+int pb_fbrush_dip(pb_fbrush* b, const double K[3], const double S[3]); /* :150-154 clean + set paint */
+int pb_fbrush_clean(pb_fbrush* b);                                     /* :160-166 */
+int pb_fbrush_set_pickup_rate(pb_fbrush* b, double rate);
+int pb_fbrush_set_deposition_rate(pb_fbrush* b, double rate);
+double pb_fbrush_get_pickup_rate(const pb_fbrush* b);
+double pb_fbrush_get_deposition_rate(const pb_fbrush* b);
+int pb_fbrush_set_use_snapshot(pb_fbrush* b, int use);
+int pb_fbrush_get_use_snapshot(const pb_fbrush* b);
+int pb_fbrush_size_map(const pb_fbrush* b);
+/* getPickupMap (:174) as host AoS f64 (size_map^2 pixels). */
+int pb_fbrush_pickup_map(pb_fbrush* b, double* K, double* S, double* V);
+/* public updateSnapshot(canvas) (:168-172): full copy canvas wet layer -> snapshot. */
+int pb_fbrush_update_snapshot(pb_fbrush* b, pb_canvas* c);
+int pb_fbrush_snapshot_download(pb_fbrush* b, double* K, double* S, double* V);
+/* FootprintBrush::imprint (:73-143): n imprints applied in order, one dependent chain on the device. */
+int pb_fbrush_imprint_batch(pb_fbrush* b, pb_canvas* c, int64_t n, const double* cx, const double* cy,
+                            const double* theta);
+/* A batch of strokes in submission order, each = dip(K,S) -> setRadius(radius) -> its imprints
+ * (SbrRenderThread.cxx:68-72). Footprints for every distinct ceil(radius) must have been registered with
+ * pb_fbrush_register_footprint. Independent strokes run concurrently; conflicting ones keep their order. */
+typedef struct pb_stroke {
+  double radius;
+  double K[3], S[3];
+  int64_t first_imprint; /* into cx/cy/theta */
+  int64_t n_imprints;
+} pb_stroke;
+int pb_fbrush_register_footprint(pb_fbrush* b, double radius, int side, const double* footprint);
+int pb_fbrush_stroke_batch(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_stroke* strokes, int64_t n_imprints,
+                           const double* cx, const double* cy, const double* theta);
+/* Stroke-pixel counters since creation: visited = the reference's `counter` (:119), cells passing both bounds
+ * checks; active = those with footprint height > 0. `visited` is only maintained while counting is enabled
+ * (it costs a pass over all footprint cells). */
+int pb_fbrush_enable_visited_count(pb_fbrush* b, int enable);
+int pb_fbrush_counters(pb_fbrush* b, uint64_t* visited, uint64_t* active);
+
+/* ---- TextureBrush (smudge off; Smudge is SURVEY.md §8f) ---------------------------------------- */
+/* thickness map: rows*cols host f64 (BrushStrokeSample::getThicknessMap). */
+int pb_tbrush_create(pb_context* ctx, int map_rows, int map_cols, const double* thickness_map, pb_tbrush** out);
+int pb_tbrush_destroy(pb_tbrush* b);
+int pb_tbrush_set_radius(pb_tbrush* b, double radius); /* TextureBrush.hxx:33-41 */
+int pb_tbrush_dip(pb_tbrush* b, const double K[3], const double S[3]);
+int pb_tbrush_set_thickness_scale(pb_tbrush* b, double scale); /* BrushBase.hxx:24-30 */
+/* TextureBrush::paintStroke (TextureBrush.hxx:52-205), path = n*2 doubles. */
+int pb_tbrush_paint_stroke(pb_tbrush* b, pb_canvas* c, int n, const double* path_xy);
+typedef struct pb_tstroke {
+  double radius;
+  double K[3], S[3];
+  double thickness_scale;
+  int64_t first_vertex; /* into path_xy (pairs) */
+  int32_t n_vertices;
+  int32_t reserved;
+} pb_tstroke;
+int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const pb_tstroke* strokes, int64_t n_vertices,
+                           const double* path_xy);
+int pb_tbrush_counters(pb_tbrush* b, uint64_t* pixels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAINTY_B200_H */

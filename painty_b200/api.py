@@ -1,0 +1,417 @@
+"""ctypes binding of libpainty_b200.so — a thin Python mirror of the reference's renderer classes
+(same names and argument meaning as painty::Canvas / PaintLayer / FootprintBrush / TextureBrush /
+Renderer) used by the tests and bench.py. The product is the CUDA library behind the C ABI in
+include/painty_b200.h; the drop-in C++ façade for painty itself lives in include/painty/.
+
+There is no CPU fallback: importing works anywhere (so that symbol checks can run without a GPU), but
+creating a Context without a B200 raises PaintyError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import assets
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpainty_b200.so")
+_PD = C.POINTER(C.c_double)
+_VP = C.c_void_p
+F32, F64 = 0, 1
+
+
+class PaintyError(RuntimeError):
+    pass
+
+
+class pb_stroke(C.Structure):
+    _fields_ = [("radius", C.c_double), ("K", C.c_double * 3), ("S", C.c_double * 3), ("first_imprint", C.c_int64),
+                ("n_imprints", C.c_int64)]
+
+
+class pb_tstroke(C.Structure):
+    _fields_ = [("radius", C.c_double), ("K", C.c_double * 3), ("S", C.c_double * 3), ("thickness_scale", C.c_double),
+                ("first_vertex", C.c_int64), ("n_vertices", C.c_int32), ("reserved", C.c_int32)]
+
+
+STROKE_DTYPE = np.dtype([("radius", "<f8"), ("K", "<f8", 3), ("S", "<f8", 3), ("first_imprint", "<i8"), ("n_imprints", "<i8")])
+TSTROKE_DTYPE = np.dtype([("radius", "<f8"), ("K", "<f8", 3), ("S", "<f8", 3), ("thickness_scale", "<f8"),
+                          ("first_vertex", "<i8"), ("n_vertices", "<i4"), ("reserved", "<i4")])
+assert STROKE_DTYPE.itemsize == C.sizeof(pb_stroke) and TSTROKE_DTYPE.itemsize == C.sizeof(pb_tstroke)
+
+_lib = None
+
+
+def lib():
+    """Load the in-tree CUDA library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PaintyError("%s is missing: run `python -m painty_b200.build` (there is no CPU fallback)" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.pb_last_error.restype = C.c_char_p
+        _lib.pb_context_stream.restype = _VP
+        _lib.pb_context_launch_count.restype = C.c_int64
+        _lib.pb_fbrush_get_pickup_rate.restype = C.c_double
+        _lib.pb_fbrush_get_deposition_rate.restype = C.c_double
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise PaintyError(lib().pb_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_PD)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _d3(a):
+    return (C.c_double * 3)(*[float(x) for x in a])
+
+
+# ---- host-side scalar calls ---------------------------------------------------------------------
+def ComputeReflectance(K, S, R0, d):
+    out = (C.c_double * 3)()
+    _chk(lib().pb_compute_reflectance(_d3(K), _d3(S), _d3(R0), C.c_double(d), out))
+    return np.array(out[:])
+
+
+def ComputeScatteringAndAbsorption(Rb, Rw):
+    K, S = (C.c_double * 3)(), (C.c_double * 3)()
+    rc = lib().pb_compute_scattering_absorption(_d3(Rb), _d3(Rw), K, S)
+    if rc:
+        raise ValueError(lib().pb_last_error().decode())  # std::invalid_argument in the reference
+    return np.array(K[:]), np.array(S[:])
+
+
+def mixed(K1, S1, v1, K2, S2, v2):
+    K, S = (C.c_double * 3)(), (C.c_double * 3)()
+    _chk(lib().pb_paint_mixed(_d3(K1), _d3(S1), C.c_double(v1), _d3(K2), _d3(S2), C.c_double(v2), K, S))
+    return np.array(K[:]), np.array(S[:])
+
+
+def mixSinglePaint(baseK, baseS, weights):
+    baseK, baseS, w = _f64(baseK), _f64(baseS), _f64(weights)
+    K, S = (C.c_double * 3)(), (C.c_double * 3)()
+    rc = lib().pb_paint_mix_single(len(baseK), _p(baseK), _p(baseS), len(w), _p(w), K, S)
+    if rc:
+        raise ValueError(lib().pb_last_error().decode())
+    return np.array(K[:]), np.array(S[:])
+
+
+def expand_stroke(path, mode=0):
+    """Stroke -> (cx, cy, theta) imprints. mode 0 = FootprintBrush::paintStroke, 1 = GUI mouse-move loop."""
+    path = _f64(path).reshape(-1, 2)
+    n = C.c_int64(0)
+    _chk(lib().pb_expand_stroke(mode, len(path), _p(path), C.c_int64(0), None, None, None, C.byref(n)))
+    cx, cy, th = np.empty(n.value), np.empty(n.value), np.empty(n.value)
+    _chk(lib().pb_expand_stroke(mode, len(path), _p(path), n, _p(cx), _p(cy), _p(th), C.byref(n)))
+    return cx, cy, th
+
+
+# ---- device objects -----------------------------------------------------------------------------
+class Context:
+    def __init__(self, device=0, precision=F32):
+        self.h = _VP()
+        _chk(lib().pb_context_create(device, precision, C.byref(self.h)))
+        self.precision = precision
+        self.device = device
+        self.dtype = np.float64 if precision == F64 else np.float32
+
+    def close(self):
+        if self.h:
+            lib().pb_context_destroy(self.h)
+            self.h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _chk(lib().pb_context_synchronize(self.h))
+
+    @property
+    def stream(self):
+        return lib().pb_context_stream(self.h)
+
+    @property
+    def launches(self):
+        return lib().pb_context_launch_count(self.h)
+
+    def km_compose_planes(self, n, K, S, V, R0, R):
+        """Raw streaming compose on device pointers (ints): K,S,R0,R are 3 pointers each, V one."""
+        a3 = lambda x: (_VP * 3)(*[_VP(int(p)) for p in x])
+        _chk(lib().pb_km_compose_planes(self.h, C.c_int64(n), a3(K), a3(S), _VP(int(V)), a3(R0), a3(R)))
+
+    def km_compose_stacked_planes(self, n, K, S, V, R0, R):
+        """K,S: lists (per layer) of 3 pointers; V: list of pointers; R0,R: 3 pointers."""
+        L = len(V)
+        Ka = (_VP * (3 * L))(*[_VP(int(p)) for l in K for p in l])
+        Sa = (_VP * (3 * L))(*[_VP(int(p)) for l in S for p in l])
+        Va = (_VP * L)(*[_VP(int(p)) for p in V])
+        a3 = lambda x: (_VP * 3)(*[_VP(int(p)) for p in x])
+        _chk(lib().pb_km_compose_stacked_planes(self.h, C.c_int64(n), L, Ka, Sa, Va, a3(R0), a3(R)))
+
+
+class PaintLayer:
+    """painty::PaintLayer<vec3> (renderer/PaintLayer.hxx); ctor is (rows, cols)."""
+
+    def __init__(self, ctx, rows, cols):
+        self.ctx, self.rows, self.cols = ctx, rows, cols
+        self.h = _VP()
+        _chk(lib().pb_layer_create(ctx.h, rows, cols, C.byref(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            lib().pb_layer_destroy(self.h)
+            self.h = None
+
+    def getRows(self):
+        return self.rows
+
+    def getCols(self):
+        return self.cols
+
+    def clear(self):
+        _chk(lib().pb_layer_clear(self.h))
+
+    def upload(self, K, S, V):
+        _chk(lib().pb_layer_upload(self.h, _p(_f64(K)), _p(_f64(S)), _p(_f64(V))))
+
+    def download(self):
+        K, S, V = np.empty((self.rows, self.cols, 3)), np.empty((self.rows, self.cols, 3)), np.empty((self.rows, self.cols))
+        _chk(lib().pb_layer_download(self.h, _p(K), _p(S), _p(V)))
+        return K, S, V
+
+    def composeOnto(self, R0):
+        """In place on a host AoS f64 array, reallocated to ones when the size differs (PaintLayer.hxx:81-96)."""
+        if R0 is None or R0.shape[:2] != (self.rows, self.cols):
+            R0 = np.ones((self.rows, self.cols, 3))
+        R0 = _f64(R0)
+        _chk(lib().pb_layer_compose_onto(self.h, _p(R0)))
+        return R0
+
+    def copyTo(self, other):
+        _chk(lib().pb_layer_copy(self.h, other.h))
+        other.rows, other.cols = self.rows, self.cols
+
+
+class Canvas:
+    """painty::Canvas<vec3> (renderer/Canvas.hxx); ctor is (rows, cols). band=(row_begin,row_end,halo)
+    creates one row band of a larger canvas for multi-GPU sharding."""
+
+    def __init__(self, ctx, rows, cols, band=None):
+        self.ctx, self.rows, self.cols = ctx, rows, cols
+        self.h = _VP()
+        if band is None:
+            _chk(lib().pb_canvas_create(ctx.h, rows, cols, C.byref(self.h)))
+        else:
+            _chk(lib().pb_canvas_create_band(ctx.h, rows, cols, band[0], band[1], band[2], C.byref(self.h)))
+        first, n = C.c_int(0), C.c_int(0)
+        lib().pb_canvas_stored_rows(self.h, C.byref(first), C.byref(n))
+        self.store_first, self.store_rows = first.value, n.value
+        self.band = band if band is not None else (0, rows, 0)
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            lib().pb_canvas_destroy(self.h)
+            self.h = None
+
+    def clear(self):
+        _chk(lib().pb_canvas_clear(self.h))
+
+    def setBackground(self, R0):
+        R0 = _f64(R0)
+        assert R0.shape == (self.store_rows, self.cols, 3)
+        _chk(lib().pb_canvas_set_background(self.h, _p(R0)))
+
+    def dryCanvas(self):
+        _chk(lib().pb_canvas_dry(self.h))
+
+    def upload_layer(self, K, S, V):
+        _chk(lib().pb_canvas_upload_layer(self.h, _p(_f64(K)), _p(_f64(S)), _p(_f64(V))))
+
+    def download(self, which="KSVRh"):
+        r, c = self.store_rows, self.cols
+        o = {}
+        if "K" in which:
+            o["K"] = np.empty((r, c, 3))
+        if "S" in which:
+            o["S"] = np.empty((r, c, 3))
+        if "V" in which:
+            o["V"] = np.empty((r, c))
+        if "R" in which:
+            o["R0"] = np.empty((r, c, 3))
+        if "h" in which:
+            o["h"] = np.empty((r, c))
+        _chk(lib().pb_canvas_download(self.h, _p(o.get("K")), _p(o.get("S")), _p(o.get("V")), _p(o.get("R0")), _p(o.get("h"))))
+        return o
+
+    def compose(self, out=None):
+        """Renderer::compose(canvas) -> host AoS f64 [rows, cols, 3]."""
+        if out is None:
+            out = np.empty((self.store_rows, self.cols, 3))
+        _chk(lib().pb_canvas_compose(self.h, _p(out)))
+        return out
+
+    def compose_device(self, d_out_ptr, plane_stride):
+        _chk(lib().pb_canvas_compose_device(self.h, _VP(int(d_out_ptr)), C.c_int64(plane_stride)))
+
+    def compose_band_device(self, d_out_ptr, plane_stride):
+        _chk(lib().pb_canvas_compose_band_device(self.h, _VP(int(d_out_ptr)), C.c_int64(plane_stride)))
+
+    def device_planes(self):
+        planes = (_VP * 11)()
+        n = C.c_int64(0)
+        _chk(lib().pb_canvas_device_planes(self.h, planes, C.byref(n)))
+        return [int(p) for p in planes], n.value
+
+
+class Renderer:
+    """painty::Renderer<vec3>::compose (renderer/Renderer.hxx:26-53)."""
+
+    def compose(self, a, R0=None):
+        if isinstance(a, Canvas):
+            return a.compose()
+        R0 = _f64(R0)
+        out = np.empty_like(R0)
+        _chk(lib().pb_layer_compose(a.h, _p(R0), _p(out)))
+        return out
+
+
+class FootprintBrush:
+    """painty::FootprintBrush<vec3> (renderer/FootprintBrush.hxx). The footprint image is prepared on the
+    host by painty_b200.assets (= painty's own imRead + ScaledMat + PaddedMat)."""
+
+    def __init__(self, ctx, radius):
+        self.ctx = ctx
+        self.h = _VP()
+        _chk(lib().pb_fbrush_create(ctx.h, C.byref(self.h)))
+        self.setRadius(radius)
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            lib().pb_fbrush_destroy(self.h)
+            self.h = None
+
+    def setRadius(self, radius):
+        acted = C.c_int(0)
+        _chk(lib().pb_fbrush_set_radius(self.h, C.c_double(radius), 0, None, C.byref(acted)))
+        if acted.value:
+            fp = assets.baked_footprint(radius)
+            _chk(lib().pb_fbrush_set_radius(self.h, C.c_double(radius), fp.shape[0], _p(fp), C.byref(acted)))
+
+    def register_radius(self, radius):
+        fp = assets.baked_footprint(radius)
+        _chk(lib().pb_fbrush_register_footprint(self.h, C.c_double(radius), fp.shape[0], _p(fp)))
+
+    def dip(self, paint):
+        _chk(lib().pb_fbrush_dip(self.h, _d3(paint[0]), _d3(paint[1])))
+
+    def clean(self):
+        _chk(lib().pb_fbrush_clean(self.h))
+
+    def setPickupRate(self, r):
+        lib().pb_fbrush_set_pickup_rate(self.h, C.c_double(r))
+
+    def setDepositionRate(self, r):
+        lib().pb_fbrush_set_deposition_rate(self.h, C.c_double(r))
+
+    def getPickupRate(self):
+        return lib().pb_fbrush_get_pickup_rate(self.h)
+
+    def getDepositionRate(self):
+        return lib().pb_fbrush_get_deposition_rate(self.h)
+
+    def setUseSnapshotBuffer(self, use):
+        lib().pb_fbrush_set_use_snapshot(self.h, int(bool(use)))
+
+    def getUseSnapshotBuffer(self):
+        return bool(lib().pb_fbrush_get_use_snapshot(self.h))
+
+    def updateSnapshot(self, canvas):
+        _chk(lib().pb_fbrush_update_snapshot(self.h, canvas.h))
+
+    def getPickupMap(self):
+        n = lib().pb_fbrush_size_map(self.h)
+        K, S, V = np.empty((n, n, 3)), np.empty((n, n, 3)), np.empty((n, n))
+        _chk(lib().pb_fbrush_pickup_map(self.h, _p(K), _p(S), _p(V)))
+        return K, S, V
+
+    def getSnapshot(self, canvas):
+        r, c = canvas.store_rows, canvas.cols
+        K, S, V = np.empty((r, c, 3)), np.empty((r, c, 3)), np.empty((r, c))
+        _chk(lib().pb_fbrush_snapshot_download(self.h, _p(K), _p(S), _p(V)))
+        return K, S, V
+
+    def imprint(self, center, theta, canvas):
+        self.imprint_batch(canvas, [center[0]], [center[1]], [theta])
+
+    def imprint_batch(self, canvas, cx, cy, theta):
+        cx, cy, theta = _f64(cx), _f64(cy), _f64(theta)
+        _chk(lib().pb_fbrush_imprint_batch(self.h, canvas.h, C.c_int64(len(cx)), _p(cx), _p(cy), _p(theta)))
+
+    def paintStroke(self, path, canvas, mode=0):
+        cx, cy, th = expand_stroke(path, mode)
+        self.imprint_batch(canvas, cx, cy, th)
+
+    def stroke_batch(self, canvas, strokes, cx, cy, theta):
+        """strokes: numpy structured array of STROKE_DTYPE (submission order)."""
+        strokes = np.ascontiguousarray(strokes, dtype=STROKE_DTYPE)
+        cx, cy, theta = _f64(cx), _f64(cy), _f64(theta)
+        _chk(lib().pb_fbrush_stroke_batch(self.h, canvas.h, C.c_int64(len(strokes)), strokes.ctypes.data_as(_VP),
+                                          C.c_int64(len(cx)), _p(cx), _p(cy), _p(theta)))
+
+    def enable_visited_count(self, enable=True):
+        lib().pb_fbrush_enable_visited_count(self.h, int(enable))
+
+    def counters(self):
+        v, a = C.c_uint64(0), C.c_uint64(0)
+        _chk(lib().pb_fbrush_counters(self.h, C.byref(v), C.byref(a)))
+        return v.value, a.value
+
+
+class TextureBrush:
+    """painty::TextureBrush<vec3> with smudge disabled (renderer/TextureBrush.hxx)."""
+
+    def __init__(self, ctx, thickness_map=None):
+        self.ctx = ctx
+        tm = _f64(assets.thickness_map() if thickness_map is None else thickness_map)
+        self.h = _VP()
+        _chk(lib().pb_tbrush_create(ctx.h, tm.shape[0], tm.shape[1], _p(tm), C.byref(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            lib().pb_tbrush_destroy(self.h)
+            self.h = None
+
+    def setRadius(self, r):
+        lib().pb_tbrush_set_radius(self.h, C.c_double(r))
+
+    def dip(self, paint):
+        lib().pb_tbrush_dip(self.h, _d3(paint[0]), _d3(paint[1]))
+
+    def setThicknessScale(self, s):
+        lib().pb_tbrush_set_thickness_scale(self.h, C.c_double(s))
+
+    def paintStroke(self, path, canvas):
+        path = _f64(path).reshape(-1, 2)
+        _chk(lib().pb_tbrush_paint_stroke(self.h, canvas.h, len(path), _p(path)))
+
+    def stroke_batch(self, canvas, strokes, path_xy):
+        strokes = np.ascontiguousarray(strokes, dtype=TSTROKE_DTYPE)
+        path_xy = _f64(path_xy).reshape(-1, 2)
+        _chk(lib().pb_tbrush_stroke_batch(self.h, canvas.h, C.c_int64(len(strokes)), strokes.ctypes.data_as(_VP),
+                                          C.c_int64(len(path_xy)), _p(path_xy)))
+
+    def counters(self):
+        p = C.c_uint64(0)
+        _chk(lib().pb_tbrush_counters(self.h, C.byref(p)))
+        return p.value

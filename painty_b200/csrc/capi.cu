@@ -1,0 +1,959 @@
+// C ABI of libpainty_b200.so (include/painty_b200.h): contexts, device-resident canvas / layer /
+// brush state, host-side stroke planning, kernel launches. No CPU fallback anywhere: every entry point
+// that computes pixels needs a CUDA device and fails loudly otherwise.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "host_math.hpp"
+#include "imprint.cuh"
+#include "schedule.hpp"
+#include "texture.cuh"
+#include "texture_host.hpp"
+
+namespace pb {
+namespace {
+thread_local std::string g_error;
+}
+void set_error(const std::string& msg) { g_error = msg; }
+}  // namespace pb
+
+#define PB_API_BEGIN try {
+#define PB_API_END                           \
+  return 0;                                  \
+  }                                          \
+  catch (const std::exception& e) {          \
+    pb::set_error(e.what());                 \
+    return 1;                                \
+  }                                          \
+  catch (...) {                              \
+    pb::set_error("unknown C++ exception");  \
+    return 1;                                \
+  }
+
+using namespace pb;
+
+namespace {
+
+struct DeviceGuard {
+  explicit DeviceGuard(const pb_context* ctx) { PB_CUDA(cudaSetDevice(ctx->device)); }
+};
+
+template <typename T>
+struct DevBuf {  // stream-ordered temporary
+  T* p = nullptr;
+  cudaStream_t s;
+  DevBuf(pb_context* ctx, size_t n) : s(ctx->stream) {
+    if (n) PB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), n * sizeof(T), s));
+  }
+  ~DevBuf() {
+    if (p) cudaFreeAsync(p, s);
+  }
+  void upload(const T* h, size_t n) {
+    if (n) PB_CUDA(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void zero(size_t n) {
+    if (n) PB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+};
+
+uint64_t fnv1a(const void* data, size_t bytes) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint64_t h             = 1469598103934665603ull;
+  for (size_t i = 0; i < bytes; ++i) h = (h ^ p[i]) * 1099511628211ull;
+  return h;
+}
+
+void canvas_clear(pb_canvas* c) {  // Canvas.hxx:37-58: wet layer 0, R0 = background (1), h = 0
+  pb_context* ctx = c->pl.ctx;
+  const int64_t n = c->pl.n();
+  for (int p = 0; p < kLayerPlanes; ++p) fill_plane(ctx, c->pl.plane(p), n, 0.0);
+  for (int p = 0; p < 3; ++p) fill_plane(ctx, c->pl.plane(PR + p), n, 1.0);
+  fill_plane(ctx, c->pl.plane(PH), n, 0.0);
+}
+
+ComposeArgs compose_args(const pb_planes& layer, const pb_planes& r0, int r0_first, void* const out[3], int64_t elem_off,
+                         size_t esize) {
+  ComposeArgs a;
+  for (int k = 0; k < 3; ++k) {
+    a.K[k]  = static_cast<char*>(layer.plane(PK + k)) + elem_off * esize;
+    a.S[k]  = static_cast<char*>(layer.plane(PS + k)) + elem_off * esize;
+    a.R0[k] = static_cast<char*>(r0.plane(r0_first + k)) + elem_off * esize;
+    a.R[k]  = out[k];
+  }
+  a.V = static_cast<char*>(layer.plane(PV)) + elem_off * esize;
+  return a;
+}
+
+}  // namespace
+
+struct pb_fbrush {
+  pb_context* ctx = nullptr;
+  double radius   = 0.0;  // FootprintBrush::_radius
+  std::map<std::pair<int, uint64_t>, FootprintGeom> geoms;  // (side, content hash) -> compacted footprint
+  std::map<int, std::pair<int, uint64_t>> by_width;         // width -> key of the footprint registered for it
+  const FootprintGeom* cur = nullptr;
+  pb_planes pick;      // dense pickup map, 7 planes of size_map^2
+  pb_planes snapshot;  // 7 planes, canvas sized, allocated at the first imprint (:281-284)
+  bool use_snapshot = true;
+  double pickup_rate = 0.9, deposition_rate = 0.05, capacity = 1.0;  // :477-495
+  double paintK[3] = {0, 0, 0}, paintS[3] = {0, 0, 0};                // zero-initialised
+  unsigned long long* d_counters = nullptr;                          // [0] active [1] visited
+  bool count_visited             = false;
+};
+
+struct pb_tbrush {
+  pb_context* ctx = nullptr;
+  double radius   = 0.0;
+  double thickness_scale = 1.0;                                        // BrushBase.hxx:45
+  double paintK[3] = {0.1, 0.1, 0.1}, paintS[3] = {0.1, 0.1, 0.1};      // TextureBrush.hxx:29-31
+  int map_rows = 0, map_cols = 0;
+  double* d_map = nullptr;
+  unsigned long long* d_counters = nullptr;
+};
+
+namespace {
+
+const FootprintGeom* register_footprint(pb_fbrush* b, double radius, int side, const double* fp) {
+  pb_context* ctx = b->ctx;
+  const int width = static_cast<int32_t>(2.0 * std::ceil(radius) + 1.0);  // FootprintBrush.hxx:54-55
+  const int size_map = static_cast<int32_t>(std::ceil(std::sqrt(2.0) * width));
+  PB_REQUIRE(side >= 0 && side <= 0xffff, "footprint side out of range");
+  const auto key = std::make_pair(side, fnv1a(fp, sizeof(double) * side * side) ^ static_cast<uint64_t>(size_map));
+  auto it        = b->geoms.find(key);
+  if (it == b->geoms.end()) {
+    FootprintGeom g;
+    g.width    = width;
+    g.size_map = size_map;
+    g.side     = side;
+    std::vector<uint32_t> xy;
+    std::vector<double> fh;
+    // reads at map index >= side are out of range in the reference (B#2) -> height 0; cells whose
+    // index is >= size_map are rejected by the reference's map bounds check
+    const int lim = std::min(side, size_map);
+    for (int my = 0; my < lim; ++my)
+      for (int mx = 0; mx < lim; ++mx) {
+        const double h = fp[static_cast<size_t>(my) * side + mx];
+        if (h > 0.0) {
+          xy.push_back(static_cast<uint32_t>(my) << 16 | static_cast<uint32_t>(mx));
+          fh.push_back(h);
+        }
+      }
+    g.n_active = static_cast<int>(xy.size());
+    if (g.n_active) {
+      PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&g.d_xy), sizeof(uint32_t) * xy.size()));
+      PB_CUDA(cudaMemcpyAsync(g.d_xy, xy.data(), sizeof(uint32_t) * xy.size(), cudaMemcpyHostToDevice, ctx->stream));
+      PB_CUDA(cudaMalloc(&g.d_fh, ctx->esize() * fh.size()));
+      if (ctx->precision == PB_F64) {
+        PB_CUDA(cudaMemcpyAsync(g.d_fh, fh.data(), sizeof(double) * fh.size(), cudaMemcpyHostToDevice, ctx->stream));
+      } else {
+        std::vector<float> f32(fh.begin(), fh.end());
+        PB_CUDA(cudaMemcpyAsync(g.d_fh, f32.data(), sizeof(float) * f32.size(), cudaMemcpyHostToDevice, ctx->stream));
+      }
+      PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    it = b->geoms.emplace(key, g).first;
+  }
+  b->by_width[width] = key;
+  return &it->second;
+}
+
+void brush_set_geometry(pb_fbrush* b, double radius, const FootprintGeom* g) {
+  b->radius = radius;
+  b->cur    = g;
+  if (b->pick.rows != g->size_map) {
+    planes_free(b->pick);
+    planes_alloc(b->ctx, b->pick, g->size_map, g->size_map, kLayerPlanes);
+  }
+  for (int p = 0; p < kLayerPlanes; ++p) fill_plane(b->ctx, b->pick.plane(p), b->pick.n(), 0.0);
+}
+
+void ensure_snapshot(pb_fbrush* b, pb_canvas* c) {  // FootprintBrush.hxx:281-284
+  if (b->snapshot.base == nullptr || b->snapshot.rows != c->pl.rows || b->snapshot.cols != c->pl.cols) {
+    planes_free(b->snapshot);
+    planes_alloc(b->ctx, b->snapshot, c->pl.rows, c->pl.cols, kLayerPlanes);
+    for (int p = 0; p < kLayerPlanes; ++p)
+      PB_CUDA(cudaMemcpyAsync(b->snapshot.plane(p), c->pl.plane(p), static_cast<size_t>(c->pl.n()) * b->ctx->esize(),
+                              cudaMemcpyDeviceToDevice, b->ctx->stream));
+  }
+}
+
+struct HostStroke {
+  const FootprintGeom* g;
+  double radius;
+  double K[3], S[3];
+  int64_t first, n;
+  int flags;
+};
+
+// Uploads the plan and launches the persistent imprint kernel.
+void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs, int64_t n_imprints, const double* cx,
+                  const double* cy, const double* theta) {
+  pb_context* ctx = b->ctx;
+  PB_REQUIRE(c->pl.ctx == ctx, "canvas and brush belong to different contexts");
+  if (hs.empty()) return;
+  if (b->use_snapshot) ensure_snapshot(b, c);
+
+  std::vector<DevImprint> im(static_cast<size_t>(n_imprints));
+  for (int64_t i = 0; i < n_imprints; ++i) {
+    im[i].cx = cx[i];
+    im[i].cy = cy[i];
+    im[i].c  = std::cos(-theta[i]);  // FootprintBrush.hxx:95-96, per-imprint constants
+    im[i].s  = std::sin(-theta[i]);
+  }
+  std::vector<DevStroke> ds(hs.size());
+  std::vector<int32_t> preds;
+  DataflowPlanner planner(c->rows, c->cols);
+  int max_active = 1;
+  for (size_t s = 0; s < hs.size(); ++s) {
+    const HostStroke& h = hs[s];
+    DevStroke& d        = ds[s];
+    d.first_imprint     = h.first;
+    d.n_imprints        = static_cast<int32_t>(h.n);
+    d.n_active          = h.g->n_active;
+    d.xy                = h.g->d_xy;
+    d.fh                = h.g->d_fh;
+    d.size_map          = h.g->size_map;
+    d.side              = h.g->side;
+    d.radius            = h.radius;
+    for (int k = 0; k < 3; ++k) {
+      d.paintK[k] = h.K[k];
+      d.paintS[k] = h.S[k];
+    }
+    d.flags    = h.flags;
+    d.pad      = 0;
+    max_active = std::max(max_active, d.n_active);
+    // region the stroke reads or writes: union of the snapshot "allowed" boxes (:298-305)
+    Region r{1, 1, 0, 0};
+    if (h.n > 0) {
+      double lx = cx[h.first], hx = lx, ly = cy[h.first], hy = ly;
+      for (int64_t i = h.first; i < h.first + h.n; ++i) {
+        lx = std::min(lx, cx[i]);
+        hx = std::max(hx, cx[i]);
+        ly = std::min(ly, cy[i]);
+        hy = std::max(hy, cy[i]);
+      }
+      const double m = (h.g->side - 1) / 2 + h.radius + 2.0;
+      r.x0 = static_cast<int>(std::max(0.0, std::floor(lx - m)));
+      r.y0 = static_cast<int>(std::max(0.0, std::floor(ly - m)));
+      r.x1 = static_cast<int>(std::min<double>(c->cols - 1, std::ceil(hx + m)));
+      r.y1 = static_cast<int>(std::min<double>(c->rows - 1, std::ceil(hy + m)));
+    }
+    planner.add(static_cast<int32_t>(s), r, preds, d.pred_begin, d.pred_end);
+  }
+
+  ImprintLaunch L{};
+  size_t smem = 0;
+  imprint_plan(ctx, max_active, L.block, L.grid, smem, L.smem_cells);
+  L.grid = static_cast<int>(std::min<int64_t>(L.grid, static_cast<int64_t>(hs.size())));
+  for (int p = 0; p < kLayerPlanes; ++p) {
+    L.canvas[p]     = c->pl.plane(p);
+    L.snapshot[p]   = b->use_snapshot ? b->snapshot.plane(p) : c->pl.plane(p);
+    L.pick_dense[p] = b->pick.base ? b->pick.plane(p) : nullptr;
+  }
+  L.use_snapshot    = b->use_snapshot ? 1 : 0;
+  L.rows            = c->rows;
+  L.cols            = c->cols;
+  L.store_first     = c->store_first;
+  L.store_rows      = c->pl.rows;
+  L.pickup_rate     = b->pickup_rate;
+  L.deposition_rate = b->deposition_rate;
+  L.capacity        = b->capacity;
+  L.n_strokes       = static_cast<int64_t>(hs.size());
+
+  DevBuf<DevStroke> d_strokes(ctx, ds.size());
+  DevBuf<DevImprint> d_im(ctx, im.size());
+  DevBuf<int32_t> d_preds(ctx, preds.size());
+  DevBuf<int> d_flags(ctx, ds.size() + 1);
+  d_strokes.upload(ds.data(), ds.size());
+  d_im.upload(im.data(), im.size());
+  d_preds.upload(preds.data(), preds.size());
+  d_flags.zero(ds.size() + 1);
+  const bool need_scratch = max_active > L.smem_cells;
+  L.scratch_stride        = need_scratch ? static_cast<int64_t>(max_active) * kLayerPlanes : 0;
+  DevBuf<char> d_scratch(ctx, need_scratch ? static_cast<size_t>(L.scratch_stride) * L.grid * ctx->esize() : 0);
+  L.scratch  = d_scratch.p;
+  L.strokes  = d_strokes.p;
+  L.imprints = d_im.p;
+  L.preds    = d_preds.p;
+  L.done     = d_flags.p;
+  L.queue    = d_flags.p + ds.size();
+  L.counters = b->d_counters;
+  imprint_launch(ctx, L, smem);
+  if (b->count_visited) imprint_count_visited(ctx, d_strokes.p, L.n_strokes, d_im.p, c->rows, c->cols, b->d_counters + 1);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pb_last_error(void) { return g_error.c_str(); }
+int pb_version(void) { return 100; }
+
+// ---- context -------------------------------------------------------------------------------------
+int pb_context_create(int device, int precision, pb_context** out) {
+  PB_API_BEGIN
+  PB_REQUIRE(out != nullptr, "pb_context_create: out is null");
+  PB_REQUIRE(precision == PB_F32 || precision == PB_F64, "precision must be PB_F32 or PB_F64");
+  int count = 0;
+  PB_CUDA(cudaGetDeviceCount(&count));
+  PB_REQUIRE(device >= 0 && device < count, "no such CUDA device (painty_b200 has no CPU fallback)");
+  PB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PB_CUDA(cudaGetDeviceProperties(&prop, device));
+  PB_REQUIRE(prop.major == 10, std::string("painty_b200 is built for sm_100a only; device is sm_") +
+                                 std::to_string(prop.major) + std::to_string(prop.minor));
+  auto ctx       = std::make_unique<pb_context>();
+  ctx->device    = device;
+  ctx->precision = precision;
+  ctx->sm_count  = prop.multiProcessorCount;
+  PB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  *out = ctx.release();
+  PB_API_END
+}
+int pb_context_destroy(pb_context* ctx) {
+  PB_API_BEGIN
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+  }
+  PB_API_END
+}
+int pb_context_synchronize(pb_context* ctx) {
+  PB_API_BEGIN
+  DeviceGuard g(ctx);
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));
+  PB_API_END
+}
+int pb_context_precision(const pb_context* ctx) { return ctx->precision; }
+void* pb_context_stream(pb_context* ctx) { return ctx->stream; }
+int64_t pb_context_launch_count(const pb_context* ctx) { return ctx->launches; }
+
+// ---- host scalars ----------------------------------------------------------------------------------
+int pb_compute_reflectance(const double K[3], const double S[3], const double R0[3], double d, double out[3]) {
+  PB_API_BEGIN
+  host::compute_reflectance(K, S, R0, d, out);
+  PB_API_END
+}
+int pb_compute_scattering_absorption(const double Rb[3], const double Rw[3], double K[3], double S[3]) {
+  PB_API_BEGIN
+  PB_REQUIRE(host::compute_scattering_absorption(Rb, Rw, K, S),
+             "invalid_argument: on black or white inputs violate one of the following conditions: 0 < black < white < 1");
+  PB_API_END
+}
+int pb_paint_mixed(const double K1[3], const double S1[3], double v1, const double K2[3], const double S2[3], double v2,
+                   double K[3], double S[3]) {
+  PB_API_BEGIN
+  const double inv = 1.0 / (v1 + v2);  // PaintMixer.cxx:539-545
+  for (int i = 0; i < 3; ++i) {
+    K[i] = ((v1 * K1[i]) + (v2 * K2[i])) * inv;
+    S[i] = ((v1 * S1[i]) + (v2 * S2[i])) * inv;
+  }
+  PB_API_END
+}
+int pb_paint_mix_single(int n, const double* baseK, const double* baseS, int n_weights, const double* w, double K[3],
+                        double S[3]) {
+  PB_API_BEGIN
+  PB_REQUIRE(n == n_weights, "invalid_argument: Palette size does not match underlying size.");
+  double norm = 1.0, sum = 0.0;  // PaintMixer.cxx:332-340
+  for (int i = 0; i < n; ++i) sum += w[i];
+  if (!(std::fabs(sum - 1.0) < 0.00001)) norm = 1. / sum;
+  for (int i = 0; i < 3; ++i) K[i] = S[i] = 0.0;
+  for (int l = 0; l < n; ++l)
+    for (int i = 0; i < 3; ++i) {
+      K[i] += norm * w[l] * baseK[3 * l + i];
+      S[i] += norm * w[l] * baseS[3 * l + i];
+    }
+  PB_API_END
+}
+int pb_expand_stroke(int mode, int n, const double* path_xy, int64_t capacity, double* cx, double* cy, double* theta,
+                     int64_t* n_imprints) {
+  PB_API_BEGIN
+  PB_REQUIRE(mode == 0 || mode == 1, "pb_expand_stroke: mode must be 0 (library) or 1 (GUI)");
+  std::vector<host::Imprint> out;
+  host::expand_stroke(mode, reinterpret_cast<const host::V2*>(path_xy), n, out);
+  if (n_imprints) *n_imprints = static_cast<int64_t>(out.size());
+  for (int64_t i = 0; i < std::min<int64_t>(capacity, static_cast<int64_t>(out.size())); ++i) {
+    cx[i]    = out[i].cx;
+    cy[i]    = out[i].cy;
+    theta[i] = out[i].theta;
+  }
+  PB_API_END
+}
+
+// ---- PaintLayer --------------------------------------------------------------------------------------
+int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out) {
+  PB_API_BEGIN
+  DeviceGuard g(ctx);
+  auto l = std::make_unique<pb_layer>();
+  planes_alloc(ctx, l->pl, rows, cols, kLayerPlanes);
+  // the reference leaves a fresh PaintLayer's memory value-initialised by cv::Mat_; we zero it
+  for (int p = 0; p < kLayerPlanes; ++p) fill_plane(ctx, l->pl.plane(p), l->pl.n(), 0.0);
+  *out = l.release();
+  PB_API_END
+}
+int pb_layer_destroy(pb_layer* l) {
+  PB_API_BEGIN
+  if (l) {
+    DeviceGuard g(l->pl.ctx);
+    PB_CUDA(cudaStreamSynchronize(l->pl.ctx->stream));
+    planes_free(l->pl);
+    delete l;
+  }
+  PB_API_END
+}
+int pb_layer_clear(pb_layer* l) {
+  PB_API_BEGIN
+  DeviceGuard g(l->pl.ctx);
+  for (int p = 0; p < kLayerPlanes; ++p) fill_plane(l->pl.ctx, l->pl.plane(p), l->pl.n(), 0.0);
+  PB_API_END
+}
+int pb_layer_upload(pb_layer* l, const double* K, const double* S, const double* V) {
+  PB_API_BEGIN
+  DeviceGuard g(l->pl.ctx);
+  if (K) upload_aos(l->pl.ctx, l->pl, PK, 3, K);
+  if (S) upload_aos(l->pl.ctx, l->pl, PS, 3, S);
+  if (V) upload_aos(l->pl.ctx, l->pl, PV, 1, V);
+  PB_API_END
+}
+int pb_layer_download(pb_layer* l, double* K, double* S, double* V) {
+  PB_API_BEGIN
+  DeviceGuard g(l->pl.ctx);
+  if (K) download_aos(l->pl.ctx, l->pl, PK, 3, K);
+  if (S) download_aos(l->pl.ctx, l->pl, PS, 3, S);
+  if (V) download_aos(l->pl.ctx, l->pl, PV, 1, V);
+  PB_API_END
+}
+int pb_layer_copy(const pb_layer* src, pb_layer* dst) {
+  PB_API_BEGIN
+  DeviceGuard g(src->pl.ctx);
+  if (dst->pl.rows != src->pl.rows || dst->pl.cols != src->pl.cols) {  // PaintLayer.hxx:104-107
+    PB_CUDA(cudaStreamSynchronize(dst->pl.ctx->stream));
+    planes_free(dst->pl);
+    planes_alloc(src->pl.ctx, dst->pl, src->pl.rows, src->pl.cols, kLayerPlanes);
+  }
+  copy_planes(src->pl.ctx, src->pl, dst->pl, kLayerPlanes);
+  PB_API_END
+}
+int pb_layer_compose(pb_layer* l, const double* R0, double* out) {
+  PB_API_BEGIN
+  pb_context* ctx = l->pl.ctx;
+  DeviceGuard g(ctx);
+  pb_planes r;
+  planes_alloc(ctx, r, l->pl.rows, l->pl.cols, 3);
+  try {
+    upload_aos(ctx, r, 0, 3, R0);
+    void* o[3] = {r.plane(0), r.plane(1), r.plane(2)};
+    km_compose(ctx, l->pl.n(), compose_args(l->pl, r, 0, o, 0, ctx->esize()));
+    download_aos(ctx, r, 0, 3, out);
+  } catch (...) {
+    planes_free(r);
+    throw;
+  }
+  planes_free(r);
+  PB_API_END
+}
+int pb_layer_compose_onto(pb_layer* l, double* R0) { return pb_layer_compose(l, R0, R0); }
+
+// ---- Canvas ------------------------------------------------------------------------------------------
+int pb_canvas_create_band(pb_context* ctx, int rows, int cols, int row_begin, int row_end, int halo, pb_canvas** out) {
+  PB_API_BEGIN
+  DeviceGuard g(ctx);
+  PB_REQUIRE(rows >= 0 && cols >= 0, "canvas size must be non-negative");
+  PB_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= rows && halo >= 0, "invalid band");
+  PB_REQUIRE(static_cast<int64_t>(rows) * cols < (int64_t(1) << 31), "canvas too large (int32 pixel index like the reference)");
+  auto c         = std::make_unique<pb_canvas>();
+  c->rows        = rows;
+  c->cols        = cols;
+  c->row_begin   = row_begin;
+  c->row_end     = row_end;
+  c->halo        = halo;
+  c->store_first = std::max(0, row_begin - halo);
+  const int last = std::min(rows, row_end + halo);
+  planes_alloc(ctx, c->pl, last - c->store_first, cols, kCanvasPlanes);
+  canvas_clear(c.get());
+  *out = c.release();
+  PB_API_END
+}
+int pb_canvas_create(pb_context* ctx, int rows, int cols, pb_canvas** out) {
+  return pb_canvas_create_band(ctx, rows, cols, 0, rows, 0, out);
+}
+int pb_canvas_destroy(pb_canvas* c) {
+  PB_API_BEGIN
+  if (c) {
+    DeviceGuard g(c->pl.ctx);
+    PB_CUDA(cudaStreamSynchronize(c->pl.ctx->stream));
+    planes_free(c->pl);
+    delete c;
+  }
+  PB_API_END
+}
+int pb_canvas_rows(const pb_canvas* c) { return c->rows; }
+int pb_canvas_cols(const pb_canvas* c) { return c->cols; }
+int pb_canvas_stored_rows(const pb_canvas* c, int* first_row, int* n_rows) {
+  if (first_row) *first_row = c->store_first;
+  if (n_rows) *n_rows = c->pl.rows;
+  return 0;
+}
+int pb_canvas_clear(pb_canvas* c) {
+  PB_API_BEGIN
+  DeviceGuard g(c->pl.ctx);
+  canvas_clear(c);
+  PB_API_END
+}
+int pb_canvas_set_background(pb_canvas* c, const double* R0) {
+  PB_API_BEGIN
+  DeviceGuard g(c->pl.ctx);
+  canvas_clear(c);
+  upload_aos(c->pl.ctx, c->pl, PR, 3, R0);
+  PB_API_END
+}
+int pb_canvas_dry(pb_canvas* c) {
+  PB_API_BEGIN
+  DeviceGuard g(c->pl.ctx);
+  void* planes[kCanvasPlanes];
+  for (int p = 0; p < kCanvasPlanes; ++p) planes[p] = c->pl.plane(p);
+  km_dry(c->pl.ctx, c->pl.n(), planes);
+  PB_API_END
+}
+int pb_canvas_upload_layer(pb_canvas* c, const double* K, const double* S, const double* V) {
+  PB_API_BEGIN
+  DeviceGuard g(c->pl.ctx);
+  if (K) upload_aos(c->pl.ctx, c->pl, PK, 3, K);
+  if (S) upload_aos(c->pl.ctx, c->pl, PS, 3, S);
+  if (V) upload_aos(c->pl.ctx, c->pl, PV, 1, V);
+  PB_API_END
+}
+int pb_canvas_download(pb_canvas* c, double* K, double* S, double* V, double* R0, double* h) {
+  PB_API_BEGIN
+  DeviceGuard g(c->pl.ctx);
+  if (K) download_aos(c->pl.ctx, c->pl, PK, 3, K);
+  if (S) download_aos(c->pl.ctx, c->pl, PS, 3, S);
+  if (V) download_aos(c->pl.ctx, c->pl, PV, 1, V);
+  if (R0) download_aos(c->pl.ctx, c->pl, PR, 3, R0);
+  if (h) download_aos(c->pl.ctx, c->pl, PH, 1, h);
+  PB_API_END
+}
+int pb_canvas_compose_device(pb_canvas* c, void* d_out, int64_t plane_stride) {
+  PB_API_BEGIN
+  pb_context* ctx = c->pl.ctx;
+  DeviceGuard g(ctx);
+  void* o[3];
+  for (int k = 0; k < 3; ++k) o[k] = static_cast<char*>(d_out) + static_cast<size_t>(k) * plane_stride * ctx->esize();
+  km_compose(ctx, c->pl.n(), compose_args(c->pl, c->pl, PR, o, 0, ctx->esize()));
+  PB_API_END
+}
+int pb_canvas_compose_band_device(pb_canvas* c, void* d_out, int64_t plane_stride) {
+  PB_API_BEGIN
+  pb_context* ctx = c->pl.ctx;
+  DeviceGuard g(ctx);
+  void* o[3];
+  for (int k = 0; k < 3; ++k) o[k] = static_cast<char*>(d_out) + static_cast<size_t>(k) * plane_stride * ctx->esize();
+  const int64_t off = static_cast<int64_t>(c->row_begin - c->store_first) * c->cols;
+  const int64_t n   = static_cast<int64_t>(c->row_end - c->row_begin) * c->cols;
+  km_compose(ctx, n, compose_args(c->pl, c->pl, PR, o, off, ctx->esize()));
+  PB_API_END
+}
+int pb_canvas_compose(pb_canvas* c, double* out) {
+  PB_API_BEGIN
+  pb_context* ctx = c->pl.ctx;
+  DeviceGuard g(ctx);
+  pb_planes r;
+  planes_alloc(ctx, r, c->pl.rows, c->pl.cols, 3);
+  try {
+    void* o[3] = {r.plane(0), r.plane(1), r.plane(2)};
+    km_compose(ctx, c->pl.n(), compose_args(c->pl, c->pl, PR, o, 0, ctx->esize()));
+    download_aos(ctx, r, 0, 3, out);
+  } catch (...) {
+    planes_free(r);
+    throw;
+  }
+  planes_free(r);
+  PB_API_END
+}
+int pb_canvas_device_planes(pb_canvas* c, void* planes[11], int64_t* elems_per_plane) {
+  for (int p = 0; p < kCanvasPlanes; ++p) planes[p] = c->pl.plane(p);
+  if (elems_per_plane) *elems_per_plane = c->pl.n();
+  return 0;
+}
+
+// ---- raw compose ---------------------------------------------------------------------------------------
+int pb_km_compose_planes(pb_context* ctx, int64_t n, const void* const K[3], const void* const S[3], const void* V,
+                         const void* const R0[3], void* const R[3]) {
+  PB_API_BEGIN
+  DeviceGuard g(ctx);
+  ComposeArgs a;
+  for (int k = 0; k < 3; ++k) {
+    a.K[k]  = K[k];
+    a.S[k]  = S[k];
+    a.R0[k] = R0[k];
+    a.R[k]  = R[k];
+  }
+  a.V = V;
+  km_compose(ctx, n, a);
+  PB_API_END
+}
+int pb_km_compose_stacked_planes(pb_context* ctx, int64_t n, int n_layers, const void* const* K, const void* const* S,
+                                 const void* const* V, const void* const R0[3], void* const R[3]) {
+  PB_API_BEGIN
+  DeviceGuard g(ctx);
+  PB_REQUIRE(n_layers >= 1, "compose_stacked: need at least one layer");
+  // more than kMaxStack layers: chain passes of <= kMaxStack, intermediate R stays on the device in R
+  int done = 0;
+  while (done < n_layers) {
+    const int m = std::min(kMaxStack, n_layers - done);
+    StackArgs a;
+    a.n_layers = m;
+    for (int l = 0; l < m; ++l) {
+      for (int k = 0; k < 3; ++k) {
+        a.K[l][k] = K[3 * (done + l) + k];
+        a.S[l][k] = S[3 * (done + l) + k];
+      }
+      a.V[l] = V[done + l];
+    }
+    for (int k = 0; k < 3; ++k) {
+      a.R0[k] = done == 0 ? R0[k] : R[k];
+      a.R[k]  = R[k];
+    }
+    km_compose_stacked(ctx, n, a);
+    done += m;
+  }
+  PB_API_END
+}
+
+// ---- FootprintBrush --------------------------------------------------------------------------------------
+int pb_fbrush_create(pb_context* ctx, pb_fbrush** out) {
+  PB_API_BEGIN
+  DeviceGuard g(ctx);
+  auto b = std::make_unique<pb_fbrush>();
+  b->ctx = ctx;
+  PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_counters), 2 * sizeof(unsigned long long)));
+  PB_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  *out = b.release();
+  PB_API_END
+}
+int pb_fbrush_destroy(pb_fbrush* b) {
+  PB_API_BEGIN
+  if (b) {
+    DeviceGuard g(b->ctx);
+    PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    for (auto& kv : b->geoms) {
+      if (kv.second.d_xy) cudaFree(kv.second.d_xy);
+      if (kv.second.d_fh) cudaFree(kv.second.d_fh);
+    }
+    planes_free(b->pick);
+    planes_free(b->snapshot);
+    cudaFree(b->d_counters);
+    delete b;
+  }
+  PB_API_END
+}
+int pb_fbrush_register_footprint(pb_fbrush* b, double radius, int side, const double* footprint) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  PB_REQUIRE(footprint != nullptr, "footprint is null");
+  register_footprint(b, radius, side, footprint);
+  PB_API_END
+}
+int pb_fbrush_set_radius(pb_fbrush* b, double radius, int side, const double* footprint, int* acted) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  const bool act = !(std::fabs(b->radius - radius) < 0.5);  // fuzzyCompare, FootprintBrush.hxx:47-48
+  if (acted) *acted = act ? 1 : 0;
+  if (act && footprint != nullptr) brush_set_geometry(b, radius, register_footprint(b, radius, side, footprint));
+  PB_API_END
+}
+int pb_fbrush_clean(pb_fbrush* b) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  if (b->pick.base)
+    for (int p = 0; p < kLayerPlanes; ++p) fill_plane(b->ctx, b->pick.plane(p), b->pick.n(), 0.0);
+  PB_API_END
+}
+int pb_fbrush_dip(pb_fbrush* b, const double K[3], const double S[3]) {
+  const int rc = pb_fbrush_clean(b);
+  if (rc) return rc;
+  for (int i = 0; i < 3; ++i) {
+    b->paintK[i] = K[i];
+    b->paintS[i] = S[i];
+  }
+  return 0;
+}
+int pb_fbrush_set_pickup_rate(pb_fbrush* b, double rate) {
+  b->pickup_rate = rate;
+  return 0;
+}
+int pb_fbrush_set_deposition_rate(pb_fbrush* b, double rate) {
+  b->deposition_rate = rate;
+  return 0;
+}
+double pb_fbrush_get_pickup_rate(const pb_fbrush* b) { return b->pickup_rate; }
+double pb_fbrush_get_deposition_rate(const pb_fbrush* b) { return b->deposition_rate; }
+int pb_fbrush_set_use_snapshot(pb_fbrush* b, int use) {
+  b->use_snapshot = use != 0;
+  return 0;
+}
+int pb_fbrush_get_use_snapshot(const pb_fbrush* b) { return b->use_snapshot ? 1 : 0; }
+int pb_fbrush_size_map(const pb_fbrush* b) { return b->cur ? b->cur->size_map : 0; }
+int pb_fbrush_pickup_map(pb_fbrush* b, double* K, double* S, double* V) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  PB_REQUIRE(b->pick.base != nullptr, "brush has no pickup map yet (setRadius was never applied)");
+  if (K) download_aos(b->ctx, b->pick, PK, 3, K);
+  if (S) download_aos(b->ctx, b->pick, PS, 3, S);
+  if (V) download_aos(b->ctx, b->pick, PV, 1, V);
+  PB_API_END
+}
+int pb_fbrush_update_snapshot(pb_fbrush* b, pb_canvas* c) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  if (b->snapshot.base == nullptr || b->snapshot.rows != c->pl.rows || b->snapshot.cols != c->pl.cols) {
+    ensure_snapshot(b, c);
+  } else {
+    for (int p = 0; p < kLayerPlanes; ++p)
+      PB_CUDA(cudaMemcpyAsync(b->snapshot.plane(p), c->pl.plane(p), static_cast<size_t>(c->pl.n()) * b->ctx->esize(),
+                              cudaMemcpyDeviceToDevice, b->ctx->stream));
+  }
+  PB_API_END
+}
+int pb_fbrush_snapshot_download(pb_fbrush* b, double* K, double* S, double* V) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  PB_REQUIRE(b->snapshot.base != nullptr, "brush has no snapshot buffer yet");
+  if (K) download_aos(b->ctx, b->snapshot, PK, 3, K);
+  if (S) download_aos(b->ctx, b->snapshot, PS, 3, S);
+  if (V) download_aos(b->ctx, b->snapshot, PV, 1, V);
+  PB_API_END
+}
+int pb_fbrush_imprint_batch(pb_fbrush* b, pb_canvas* c, int64_t n, const double* cx, const double* cy,
+                            const double* theta) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  PB_REQUIRE(b->cur != nullptr, "imprint before setRadius: the brush has no footprint");
+  if (n <= 0) return 0;
+  PB_REQUIRE(n < (int64_t(1) << 31), "too many imprints in one batch");
+  HostStroke h;
+  h.g      = b->cur;
+  h.radius = b->radius;
+  for (int i = 0; i < 3; ++i) {
+    h.K[i] = b->paintK[i];
+    h.S[i] = b->paintS[i];
+  }
+  h.first = 0;
+  h.n     = n;
+  h.flags = 3;  // continue with, and write back, the brush's persistent pickup map
+  run_imprints(b, c, {h}, n, cx, cy, theta);
+  PB_API_END
+}
+int pb_fbrush_stroke_batch(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_stroke* strokes, int64_t n_imprints,
+                           const double* cx, const double* cy, const double* theta) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  if (n_strokes <= 0) return 0;
+  PB_REQUIRE(n_strokes < (int64_t(1) << 31), "too many strokes in one batch");
+  std::vector<HostStroke> hs(static_cast<size_t>(n_strokes));
+  double radius            = b->radius;
+  const FootprintGeom* cur = b->cur;
+  for (int64_t s = 0; s < n_strokes; ++s) {
+    const pb_stroke& in = strokes[s];
+    PB_REQUIRE(in.first_imprint >= 0 && in.n_imprints >= 0 && in.first_imprint + in.n_imprints <= n_imprints,
+               "stroke imprint range out of bounds");
+    PB_REQUIRE(in.n_imprints < (int64_t(1) << 31), "too many imprints in one stroke");
+    // dip -> setRadius -> paintStroke (SbrRenderThread.cxx:68-72); setRadius only acts on a change >= 0.5
+    if (!(std::fabs(radius - in.radius) < 0.5)) {
+      radius          = in.radius;
+      const int width = static_cast<int32_t>(2.0 * std::ceil(radius) + 1.0);
+      auto it         = b->by_width.find(width);
+      PB_REQUIRE(it != b->by_width.end(), "stroke_batch: no footprint registered for radius " + std::to_string(radius));
+      cur = &b->geoms.at(it->second);
+    }
+    PB_REQUIRE(cur != nullptr, "stroke_batch: the brush has no footprint");
+    HostStroke& h = hs[static_cast<size_t>(s)];
+    h.g           = cur;
+    h.radius      = radius;
+    for (int i = 0; i < 3; ++i) {
+      h.K[i] = in.K[i];
+      h.S[i] = in.S[i];
+    }
+    h.first = in.first_imprint;
+    h.n     = in.n_imprints;
+    h.flags = 0;  // dip(): clean pickup map
+  }
+  // brush state after the batch = state after the last stroke
+  brush_set_geometry(b, radius, cur);
+  for (int i = 0; i < 3; ++i) {
+    b->paintK[i] = strokes[n_strokes - 1].K[i];
+    b->paintS[i] = strokes[n_strokes - 1].S[i];
+  }
+  hs.back().flags = 2;
+  run_imprints(b, c, hs, n_imprints, cx, cy, theta);
+  PB_API_END
+}
+int pb_fbrush_enable_visited_count(pb_fbrush* b, int enable) {
+  b->count_visited = enable != 0;
+  return 0;
+}
+int pb_fbrush_counters(pb_fbrush* b, uint64_t* visited, uint64_t* active) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  unsigned long long h[2];
+  PB_CUDA(cudaMemcpyAsync(h, b->d_counters, sizeof(h), cudaMemcpyDeviceToHost, b->ctx->stream));
+  PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  if (active) *active = h[0];
+  if (visited) *visited = h[1];
+  PB_API_END
+}
+
+// ---- TextureBrush -----------------------------------------------------------------------------------------
+int pb_tbrush_create(pb_context* ctx, int map_rows, int map_cols, const double* thickness_map, pb_tbrush** out) {
+  PB_API_BEGIN
+  DeviceGuard g(ctx);
+  PB_REQUIRE(map_rows > 0 && map_cols > 0 && thickness_map != nullptr, "texture brush needs a thickness map");
+  auto b      = std::make_unique<pb_tbrush>();
+  b->ctx      = ctx;
+  b->map_rows = map_rows;
+  b->map_cols = map_cols;
+  PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_map), sizeof(double) * map_rows * map_cols));
+  PB_CUDA(cudaMemcpyAsync(b->d_map, thickness_map, sizeof(double) * map_rows * map_cols, cudaMemcpyHostToDevice, ctx->stream));
+  PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_counters), sizeof(unsigned long long)));
+  PB_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = b.release();
+  PB_API_END
+}
+int pb_tbrush_destroy(pb_tbrush* b) {
+  PB_API_BEGIN
+  if (b) {
+    DeviceGuard g(b->ctx);
+    PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    cudaFree(b->d_map);
+    cudaFree(b->d_counters);
+    delete b;
+  }
+  PB_API_END
+}
+int pb_tbrush_set_radius(pb_tbrush* b, double radius) {
+  if (!(std::fabs(b->radius - radius) < 0.5)) b->radius = radius;  // TextureBrush.hxx:33-41
+  return 0;
+}
+int pb_tbrush_dip(pb_tbrush* b, const double K[3], const double S[3]) {
+  for (int i = 0; i < 3; ++i) {
+    b->paintK[i] = K[i];
+    b->paintS[i] = S[i];
+  }
+  return 0;
+}
+int pb_tbrush_set_thickness_scale(pb_tbrush* b, double scale) {
+  b->thickness_scale = scale;
+  return 0;
+}
+int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const pb_tstroke* strokes, int64_t n_vertices,
+                           const double* path_xy) {
+  PB_API_BEGIN
+  pb_context* ctx = b->ctx;
+  DeviceGuard g(ctx);
+  PB_REQUIRE(c->pl.ctx == ctx, "canvas and brush belong to different contexts");
+  if (n_strokes <= 0) return 0;
+  std::vector<DevTStroke> ds;
+  ds.reserve(static_cast<size_t>(n_strokes));
+  std::vector<host::V2> poly, uv;
+  std::vector<int32_t> preds;
+  DataflowPlanner planner(c->rows, c->cols);
+  double radius = b->radius;
+  for (int64_t s = 0; s < n_strokes; ++s) {
+    const pb_tstroke& in = strokes[s];
+    PB_REQUIRE(in.first_vertex >= 0 && in.n_vertices >= 0 && in.first_vertex + in.n_vertices <= n_vertices,
+               "stroke vertex range out of bounds");
+    if (!(std::fabs(radius - in.radius) < 0.5)) radius = in.radius;
+    const host::TextureFrame f = host::build_texture_frame(reinterpret_cast<const host::V2*>(path_xy) + in.first_vertex,
+                                                           in.n_vertices, radius, c->rows, c->cols);
+    DevTStroke d{};
+    for (int i = 0; i < 3; ++i) {
+      d.K[i] = in.K[i];
+      d.S[i] = in.S[i];
+    }
+    d.thickness_scale = in.thickness_scale;
+    d.poly_begin      = static_cast<int32_t>(poly.size());
+    Region r{1, 1, 0, 0};
+    if (f.valid) {
+      PB_REQUIRE(f.poly.size() <= static_cast<size_t>(kMaxPoly), "stroke has too many vertices (max 510 per stroke)");
+      d.x0 = f.x0, d.x1 = f.x1, d.y0 = f.y0, d.y1 = f.y1;
+      d.local_rows = f.local_rows;
+      d.local_cols = f.local_cols;
+      d.n_poly     = static_cast<int32_t>(f.poly.size());
+      poly.insert(poly.end(), f.poly.begin(), f.poly.end());
+      uv.insert(uv.end(), f.uv.begin(), f.uv.end());
+      r = Region{std::max(f.x0, 0), std::max(f.y0, 0), std::min(f.x1, c->cols - 1), std::min(f.y1, c->rows - 1)};
+    } else {
+      d.x0 = d.y0 = 0;
+      d.x1 = d.y1 = -1;
+      d.n_poly    = 0;
+    }
+    planner.add(static_cast<int32_t>(s), r, preds, d.pred_begin, d.pred_end);
+    ds.push_back(d);
+  }
+  b->radius = radius;
+  for (int i = 0; i < 3; ++i) {
+    b->paintK[i] = strokes[n_strokes - 1].K[i];
+    b->paintS[i] = strokes[n_strokes - 1].S[i];
+  }
+  static_assert(sizeof(host::V2) == sizeof(double2), "V2 must match double2");
+  DevBuf<DevTStroke> d_strokes(ctx, ds.size());
+  DevBuf<double2> d_poly(ctx, poly.size()), d_uv(ctx, uv.size());
+  DevBuf<int32_t> d_preds(ctx, preds.size());
+  DevBuf<int> d_flags(ctx, ds.size() + 1);
+  d_strokes.upload(ds.data(), ds.size());
+  d_poly.upload(reinterpret_cast<const double2*>(poly.data()), poly.size());
+  d_uv.upload(reinterpret_cast<const double2*>(uv.data()), uv.size());
+  d_preds.upload(preds.data(), preds.size());
+  d_flags.zero(ds.size() + 1);
+  TextureLaunch L{};
+  for (int p = 0; p < kLayerPlanes; ++p) L.canvas[p] = c->pl.plane(p);
+  L.rows        = c->rows;
+  L.cols        = c->cols;
+  L.store_first = c->store_first;
+  L.store_rows  = c->pl.rows;
+  L.map         = b->d_map;
+  L.map_rows    = b->map_rows;
+  L.map_cols    = b->map_cols;
+  L.strokes     = d_strokes.p;
+  L.n_strokes   = n_strokes;
+  L.poly        = d_poly.p;
+  L.uv          = d_uv.p;
+  L.preds       = d_preds.p;
+  L.done        = d_flags.p;
+  L.queue       = d_flags.p + ds.size();
+  L.counters    = b->d_counters;
+  texture_launch(ctx, L);
+  PB_API_END
+}
+int pb_tbrush_paint_stroke(pb_tbrush* b, pb_canvas* c, int n, const double* path_xy) {
+  pb_tstroke s{};
+  s.radius = b->radius;
+  for (int i = 0; i < 3; ++i) {
+    s.K[i] = b->paintK[i];
+    s.S[i] = b->paintS[i];
+  }
+  s.thickness_scale = b->thickness_scale;
+  s.first_vertex    = 0;
+  s.n_vertices      = n;
+  return pb_tbrush_stroke_batch(b, c, 1, &s, n, path_xy);
+}
+int pb_tbrush_counters(pb_tbrush* b, uint64_t* pixels) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  unsigned long long h = 0;
+  PB_CUDA(cudaMemcpyAsync(&h, b->d_counters, sizeof(h), cudaMemcpyDeviceToHost, b->ctx->stream));
+  PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  if (pixels) *pixels = h;
+  PB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Device-side interface of the footprint-brush imprint engine (imprint.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+
+// One footprint geometry (= one ceil(radius)): the compacted list of active cells (height > 0) of the
+// padded footprint. Cell i sits at map position (xy[i] & 0xffff, xy[i] >> 16) and has height fh[i].
+struct FootprintGeom {
+  int width    = 0;  // 2*ceil(r)+1
+  int size_map = 0;  // ceil(sqrt(2)*width)
+  int side     = 0;  // width + 2*pad (footprint rows == cols)
+  int n_active = 0;
+  uint32_t* d_xy = nullptr;  // device
+  void* d_fh     = nullptr;  // device, context element type
+};
+
+struct DevImprint {  // per-imprint constants, computed on the host in f64 (FootprintBrush.hxx:95-96)
+  double cx, cy, c, s;  // c = cos(-theta), s = sin(-theta)
+};
+
+struct DevStroke {
+  int64_t first_imprint;
+  int32_t n_imprints;
+  int32_t n_active;
+  const uint32_t* xy;
+  const void* fh;
+  int32_t size_map, side;
+  double radius;  // FootprintBrush::_radius as used by updateSnapshot (:298-305)
+  double paintK[3], paintS[3];
+  int32_t pred_begin, pred_end;  // into preds[]
+  int32_t flags;                 // bit0: load pick state from the dense map, bit1: store it back
+  int32_t pad;
+};
+
+struct ImprintLaunch {
+  // canvas
+  void* canvas[kLayerPlanes];
+  void* snapshot[kLayerPlanes];  // == canvas planes when the snapshot buffer is disabled
+  int use_snapshot;
+  int rows, cols;               // logical canvas size (bounds checks)
+  int store_first, store_rows;  // stored row window
+  // brush constants
+  double pickup_rate, deposition_rate, capacity;
+  // dense pickup map of the brush (7 planes of size_map^2), used by strokes with flags
+  void* pick_dense[kLayerPlanes];
+  // work
+  const DevStroke* strokes;
+  int64_t n_strokes;
+  const DevImprint* imprints;
+  const int32_t* preds;
+  int* done;                     // per stroke completion flags (zeroed)
+  int* queue;                    // single counter (zeroed)
+  unsigned long long* counters;  // [0] active stroke-pixels
+  // per-CTA pick scratch in global memory for footprints that do not fit shared memory
+  void* scratch;
+  int64_t scratch_stride;  // elements per CTA
+  int smem_cells;          // cells that fit in dynamic shared memory
+  int block;               // threads per CTA
+  int grid;
+};
+
+void imprint_launch(pb_context* ctx, const ImprintLaunch& L, size_t smem_bytes);
+// grid/block/smem plan for a batch whose largest footprint has max_active cells
+void imprint_plan(pb_context* ctx, int max_active, int& block, int& grid, size_t& smem_bytes, int& smem_cells);
+
+// visited stroke-pixel count (the reference's `counter`, FootprintBrush.hxx:119): one pass over all
+// (2hr+1)(2wr+1) cells of every imprint, both bounds checks evaluated exactly in f64.
+void imprint_count_visited(pb_context* ctx, const DevStroke* strokes, int64_t n_strokes, const DevImprint* imprints,
+                           int rows, int cols, unsigned long long* counter);
+
+}  // namespace pb

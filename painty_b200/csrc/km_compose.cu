@@ -1,0 +1,349 @@
+// Kubelka-Munk layer compose — fused, coalesced, 128-bit vectorised streaming kernels for sm_100a.
+//
+// Restates (not copies) painty/core/KubelkaMunk.hxx:28-83 + painty/core/Math.hxx:159-169 per pixel
+// and the whole-image loops painty/renderer/Renderer.hxx:26-41 (compose), PaintLayer.hxx:81-96
+// (composeOnto), Canvas.hxx:105-121 (dryCanvas) over SoA planes in HBM.
+//
+// Roofline: pure streaming map, no reuse -> HBM bound. Algorithmic bytes FP32: 7 layer planes + 3 R0
+// planes read, 3 R planes written = 52 B/px; L stacked layers 28 L + 24; dry 88 B/px; FP64 x2.
+// Each thread owns 4 consecutive pixels (float4 / 2 x double2 per plane): 10 independent 16 B loads
+// in flight per thread, streaming (evict-first) loads and stores, no shared memory, no tensor cores
+// (nothing here is a contraction).
+//
+// FP32 math is a reformulation that avoids the reference's cancellations and its libm calls:
+//   ks = K/S', a = 1+ks, b = sqrt(ks(ks+2))            (= sqrt(a^2-1) without the a^2-1 cancellation)
+//   b coth(x) = b + 2b/expm1(2x),  x = b S' d           (expm1: degree-5 polynomial for |2x|<0.25, else
+//                                                         ex2.approx; K==0 gives 0/0 = NaN like the reference)
+// 5 MUFU ops per channel (rcp, sqrt, ex2, rcp, rcp). The f64 thresholds of the reference are used in
+// both precisions (a float instantiation of the reference would early-out at d < 1.19e-3).
+// FP64 validation mode follows the reference's operation order exactly; the library is compiled with
+// -fmad=false so no FMA contraction happens there, FP32 uses explicit fmaf.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace pb {
+namespace {
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ float km_channel(float K, float S_in, float R0, float d) {
+  const float S  = (fabsf(S_in) > static_cast<float>(kKmEps)) ? S_in : 1e-11f;
+  const float ks = __fdividef(K, S);
+  const float a  = 1.0f + ks;
+  const float b  = sqrt_approx(fmaxf(fmaf(ks, ks, ks + ks), 0.0f));
+  const float y  = 2.0f * b * S * d;
+  // expm1(y)
+  float p = fmaf(y, 1.0f / 120.0f, 1.0f / 24.0f);
+  p       = fmaf(p, y, 1.0f / 6.0f);
+  p       = fmaf(p, y, 0.5f);
+  p       = fmaf(p, y, 1.0f);
+  p       = p * y;
+  const float e   = __expf(y) - 1.0f;
+  const float em1 = (fabsf(y) < 0.25f) ? p : e;
+  const float c   = b + __fdividef(b + b, em1);
+  return __fdividef(fmaf(-R0, a - c, 1.0f), (a - R0) + c);
+}
+
+// reference order of operations, IEEE f64 (KubelkaMunk.hxx:36-80, Math.hxx:159-169)
+__device__ __forceinline__ double km_channel(double K, double S_in, double R0, double d) {
+  const double S = (fabs(S_in) > kKmEps) ? S_in : 0.00000000001;
+  const double a = 1.0 + K / S;
+  const double v = a * a - 1.0;
+  const double b = (v < 0.0) ? 0.0 : sqrt(v);
+  const double x = b * S * d;
+  double coth;
+  if (x > 20.0) {
+    coth = 1.0;
+  } else if (fabs(x) > 0.0) {
+    const double r = cosh(x) / sinh(x);
+    coth           = isnan(r) ? 1.0 : r;
+  } else {
+    coth = CUDART_INF;
+  }
+  const double c = b * coth;
+  return (1.0 - R0 * (a - c)) / (a - R0 + c);
+}
+
+__device__ __forceinline__ bool is_dry(float v) { return fabsf(v) < static_cast<float>(kKmEps); }
+__device__ __forceinline__ bool is_dry(double v) { return fabs(v) < kKmEps; }
+
+template <typename T>
+__device__ __forceinline__ void km_pixel(T k0, T k1, T k2, T s0, T s1, T s2, T v, T& r0, T& r1, T& r2) {
+  if (is_dry(v)) return;  // KubelkaMunk.hxx:31-34: R = R0
+  r0 = km_channel(k0, s0, r0, v);
+  r1 = km_channel(k1, s1, r1, v);
+  r2 = km_channel(k2, s2, r2, v);
+}
+
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+  using type              = float4;
+  static constexpr int kN = 4;
+};
+template <>
+struct Vec<double> {
+  using type              = double2;
+  static constexpr int kN = 2;
+};
+
+template <typename T>
+__device__ __forceinline__ void ld4(const T* p, T (&o)[4]);
+template <>
+__device__ __forceinline__ void ld4<float>(const float* p, float (&o)[4]) {
+  const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+  o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void ld4<double>(const double* p, double (&o)[4]) {
+  const double2 a = __ldcs(reinterpret_cast<const double2*>(p));
+  const double2 b = __ldcs(reinterpret_cast<const double2*>(p) + 1);
+  o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y;
+}
+template <typename T>
+__device__ __forceinline__ void st4(T* p, const T (&o)[4]);
+template <>
+__device__ __forceinline__ void st4<float>(float* p, const float (&o)[4]) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(o[0], o[1], o[2], o[3]));
+}
+template <>
+__device__ __forceinline__ void st4<double>(double* p, const double (&o)[4]) {
+  __stcs(reinterpret_cast<double2*>(p), make_double2(o[0], o[1]));
+  __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(o[2], o[3]));
+}
+
+template <typename T>
+struct ComposePtrs {
+  const T* K[3];
+  const T* S[3];
+  const T* V;
+  const T* R0[3];
+  T* R[3];
+};
+
+// One thread = 4 consecutive pixels. All loads are issued before any math (10 x 16 B in flight).
+template <typename T>
+__global__ void __launch_bounds__(256) km_compose_kernel(ComposePtrs<T> a, int64_t n4, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const int64_t o = i * 4;
+    T k[3][4], s[3][4], v[4], r[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ld4(a.K[c] + o, k[c]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ld4(a.S[c] + o, s[c]);
+    ld4(a.V + o, v);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ld4(a.R0[c] + o, r[c]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) km_pixel(k[0][j], k[1][j], k[2][j], s[0][j], s[1][j], s[2][j], v[j], r[0][j], r[1][j], r[2][j]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st4(a.R[c] + o, r[c]);
+  } else if (i == n4) {  // scalar tail (n % 4 pixels)
+    for (int64_t o = n4 * 4; o < n; ++o) {
+      T r0 = a.R0[0][o], r1 = a.R0[1][o], r2 = a.R0[2][o];
+      km_pixel(a.K[0][o], a.K[1][o], a.K[2][o], a.S[0][o], a.S[1][o], a.S[2][o], a.V[o], r0, r1, r2);
+      a.R[0][o] = r0, a.R[1][o] = r1, a.R[2][o] = r2;
+    }
+  }
+}
+
+// fallback for caller-provided planes that are not 16 B aligned: one pixel per thread
+template <typename T>
+__global__ void __launch_bounds__(256) km_compose_scalar_kernel(ComposePtrs<T> a, int64_t n) {
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (o < n) {
+    T r0 = a.R0[0][o], r1 = a.R0[1][o], r2 = a.R0[2][o];
+    km_pixel(a.K[0][o], a.K[1][o], a.K[2][o], a.S[0][o], a.S[1][o], a.S[2][o], a.V[o], r0, r1, r2);
+    a.R[0][o] = r0, a.R[1][o] = r1, a.R[2][o] = r2;
+  }
+}
+
+template <typename T>
+struct StackPtrs {
+  const T* K[kMaxStack][3];
+  const T* S[kMaxStack][3];
+  const T* V[kMaxStack];
+  const T* R0[3];
+  T* R[3];
+  int n_layers;
+};
+
+// L layers bottom-up, R stays in registers between layers: (28 L + 24) B/px instead of 52 L.
+template <typename T>
+__global__ void __launch_bounds__(256) km_stacked_kernel(StackPtrs<T> a, int64_t n4, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const int64_t o = i * 4;
+    T r[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ld4(a.R0[c] + o, r[c]);
+    for (int l = 0; l < a.n_layers; ++l) {
+      T k[3][4], s[3][4], v[4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ld4(a.K[l][c] + o, k[c]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ld4(a.S[l][c] + o, s[c]);
+      ld4(a.V[l] + o, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        km_pixel(k[0][j], k[1][j], k[2][j], s[0][j], s[1][j], s[2][j], v[j], r[0][j], r[1][j], r[2][j]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st4(a.R[c] + o, r[c]);
+  } else if (i == n4) {
+    for (int64_t o = n4 * 4; o < n; ++o) {
+      T r0 = a.R0[0][o], r1 = a.R0[1][o], r2 = a.R0[2][o];
+      for (int l = 0; l < a.n_layers; ++l)
+        km_pixel(a.K[l][0][o], a.K[l][1][o], a.K[l][2][o], a.S[l][0][o], a.S[l][1][o], a.S[l][2][o], a.V[l][o], r0, r1, r2);
+      a.R[0][o] = r0, a.R[1][o] = r1, a.R[2][o] = r2;
+    }
+  }
+}
+
+template <typename T>
+struct DryPtrs {
+  T* p[kCanvasPlanes];
+};
+
+// Canvas::dryCanvas (Canvas.hxx:105-121): h += V; R0 = KM(K,S,R0,V); K = S = V = 0. 88 B/px FP32.
+template <typename T>
+__global__ void __launch_bounds__(256) km_dry_kernel(DryPtrs<T> a, int64_t n4, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const int64_t o = i * 4;
+    T k[3][4], s[3][4], v[4], r[3][4], h[4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ld4(a.p[PK + c] + o, k[c]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ld4(a.p[PS + c] + o, s[c]);
+    ld4(a.p[PV] + o, v);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ld4(a.p[PR + c] + o, r[c]);
+    ld4(a.p[PH] + o, h);
+    const T z[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] += v[j];
+      km_pixel(k[0][j], k[1][j], k[2][j], s[0][j], s[1][j], s[2][j], v[j], r[0][j], r[1][j], r[2][j]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st4(a.p[PR + c] + o, r[c]);
+    st4(a.p[PH] + o, h);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) st4(a.p[c] + o, z);
+  } else if (i == n4) {
+    for (int64_t o = n4 * 4; o < n; ++o) {
+      T r0 = a.p[PR][o], r1 = a.p[PR + 1][o], r2 = a.p[PR + 2][o];
+      const T v = a.p[PV][o];
+      a.p[PH][o] += v;
+      km_pixel(a.p[0][o], a.p[1][o], a.p[2][o], a.p[3][o], a.p[4][o], a.p[5][o], v, r0, r1, r2);
+      a.p[PR][o] = r0, a.p[PR + 1][o] = r1, a.p[PR + 2][o] = r2;
+      for (int c = 0; c < 7; ++c) a.p[c][o] = T(0);
+    }
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+void compose_t(pb_context* ctx, int64_t n, const ComposeArgs& a) {
+  ComposePtrs<T> p;
+  bool al = aligned16(a.V);
+  for (int c = 0; c < 3; ++c) {
+    p.K[c]  = static_cast<const T*>(a.K[c]);
+    p.S[c]  = static_cast<const T*>(a.S[c]);
+    p.R0[c] = static_cast<const T*>(a.R0[c]);
+    p.R[c]  = static_cast<T*>(a.R[c]);
+    al      = al && aligned16(a.K[c]) && aligned16(a.S[c]) && aligned16(a.R0[c]) && aligned16(a.R[c]);
+  }
+  p.V = static_cast<const T*>(a.V);
+  if (!al) {
+    km_compose_scalar_kernel<T><<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(p, n);
+    PB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return;
+  }
+  // 8-byte elements keep 16 B alignment for 4-pixel groups too (32 B per group)
+  const int64_t n4     = n / 4;
+  const int64_t blocks = (n4 + 1 + 255) / 256;
+  km_compose_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, ctx->stream>>>(p, n4, n);
+  PB_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+template <typename T>
+void stacked_t(pb_context* ctx, int64_t n, const StackArgs& a) {
+  StackPtrs<T> p;
+  bool al = true;
+  for (int l = 0; l < a.n_layers; ++l) {
+    for (int c = 0; c < 3; ++c) {
+      p.K[l][c] = static_cast<const T*>(a.K[l][c]);
+      p.S[l][c] = static_cast<const T*>(a.S[l][c]);
+      al        = al && aligned16(a.K[l][c]) && aligned16(a.S[l][c]);
+    }
+    p.V[l] = static_cast<const T*>(a.V[l]);
+    al     = al && aligned16(a.V[l]);
+  }
+  for (int c = 0; c < 3; ++c) {
+    p.R0[c] = static_cast<const T*>(a.R0[c]);
+    p.R[c]  = static_cast<T*>(a.R[c]);
+    al      = al && aligned16(a.R0[c]) && aligned16(a.R[c]);
+  }
+  p.n_layers           = a.n_layers;
+  const int64_t n4     = al ? n / 4 : 0;
+  const int64_t blocks = (n4 + 1 + 255) / 256;
+  km_stacked_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, ctx->stream>>>(p, n4, n);
+  PB_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+template <typename T>
+void dry_t(pb_context* ctx, int64_t n, void* const planes[11]) {
+  DryPtrs<T> p;
+  bool al = true;
+  for (int c = 0; c < kCanvasPlanes; ++c) {
+    p.p[c] = static_cast<T*>(planes[c]);
+    al     = al && aligned16(planes[c]);
+  }
+  const int64_t n4     = al ? n / 4 : 0;
+  const int64_t blocks = (n4 + 1 + 255) / 256;
+  km_dry_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, ctx->stream>>>(p, n4, n);
+  PB_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+}  // namespace
+
+void km_compose(pb_context* ctx, int64_t n, const ComposeArgs& a) {
+  if (n <= 0) return;
+  if (ctx->precision == PB_F64)
+    compose_t<double>(ctx, n, a);
+  else
+    compose_t<float>(ctx, n, a);
+}
+
+void km_compose_stacked(pb_context* ctx, int64_t n, const StackArgs& a) {
+  PB_REQUIRE(a.n_layers >= 1 && a.n_layers <= kMaxStack, "compose_stacked: 1..8 layers supported per pass");
+  if (n <= 0) return;
+  if (ctx->precision == PB_F64)
+    stacked_t<double>(ctx, n, a);
+  else
+    stacked_t<float>(ctx, n, a);
+}
+
+void km_dry(pb_context* ctx, int64_t n, void* const planes[11]) {
+  if (n <= 0) return;
+  if (ctx->precision == PB_F64)
+    dry_t<double>(ctx, n, planes);
+  else
+    dry_t<float>(ctx, n, planes);
+}
+
+}  // namespace pb

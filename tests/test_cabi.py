@@ -1,0 +1,106 @@
+"""No-GPU checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, exports every
+symbol include/painty_b200.h declares, runs its host-side f64 calls bit-exactly, and refuses to create a
+context without a CUDA device (there is no CPU fallback)."""
+import ctypes
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.workloads import gui_stroke_imprints
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "painty_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    names = declared_symbols()
+    assert len(names) > 50
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_library_contains_sm100a_code_only(built_lib):
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_host_scalars_match_oracle(built_lib, port):
+    from painty_b200 import api
+
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        K, S, R0 = rng.uniform(0, 2, 3), rng.uniform(0, 1.2, 3), rng.uniform(0, 1, 3)
+        d = float(rng.choice([0.0, 1e-13, rng.uniform(0, 3), 60.0]))
+        if rng.random() < 0.1:
+            S[0] = 0.0
+        assert np.array_equal(api.ComputeReflectance(K, S, R0, d), port.compute_reflectance(K, S, R0, d), equal_nan=True)
+    K, S = api.ComputeScatteringAndAbsorption([.2, .05, .4], [.6, .3, .7])
+    K2, S2 = port.compute_scattering_absorption([.2, .05, .4], [.6, .3, .7])
+    assert np.array_equal(K, K2) and np.array_equal(S, S2)
+    with pytest.raises(ValueError):  # std::invalid_argument in the reference (KubelkaMunk.hxx:98)
+        api.ComputeScatteringAndAbsorption([.7, .05, .4], [.6, .3, .7])
+
+
+def test_mixing_calls(built_lib):
+    from painty_b200 import api, assets
+
+    pk, ps = assets.palette("lindemeier_measured")
+    assert pk.shape == (14, 3)
+    w = np.random.default_rng(0).uniform(0, 1, 14)
+    K, S = api.mixSinglePaint(pk, ps, w)
+    norm = 1.0 / w.sum()
+    eK = np.zeros(3)
+    for l in range(14):  # mixer/src/PaintMixer.cxx:348-353, same accumulation order
+        eK += norm * w[l] * pk[l]
+    assert np.array_equal(K, eK)
+    with pytest.raises(ValueError):
+        api.mixSinglePaint(pk, ps, w[:5])
+    tk, ts = assets.palette("thinning_medium")
+    K2, S2 = api.mixed(K, S, 1.0, tk[0], ts[0], 0.5)
+    assert np.array_equal(K2, ((1.0 * K) + (0.5 * tk[0])) * (1.0 / 1.5))
+
+
+def test_expand_stroke_matches_reference_loops(built_lib, port):
+    from painty_b200 import api
+
+    pts = [(100.3, 200.7), (400.9, 260.2), (700.1, 180.4)]
+    cx, cy, th = api.expand_stroke(pts, mode=1)
+    ex, ey, eth = gui_stroke_imprints(port, pts)
+    assert len(cx) == 615
+    assert np.array_equal(cx, ex) and np.array_equal(cy, ey) and np.array_equal(th, eth)
+    # library form (FootprintBrush.hxx:251-267) with p_pre = path[0] on the first segment
+    pts = np.array([(10.5, 20.25), (60.0, 40.5), (90.75, 90.0), (140.0, 95.5)])
+    cx, cy, th = api.expand_stroke(pts, mode=0)
+    e = []
+    for i in range(len(pts) - 1):
+        a, b, c, d = pts[max(i - 1, 0)], pts[i], pts[i + 1], pts[min(i + 2, len(pts) - 1)]
+        dist = float(np.sqrt(((c - b) * (c - b)).sum()))
+        for pd in range(1, int(dist) + 1):
+            t = pd / dist
+            q, dr = port.catmull_rom(a, b, c, d, t), port.catmull_rom(a, b, c, d, t, True)
+            e.append((q[0], q[1], math.atan2(dr[1], dr[0])))  # libm atan2 like the reference (numpy differs by ulps)
+    e = np.array(e)
+    assert np.array_equal(cx, e[:, 0]) and np.array_equal(cy, e[:, 1]) and np.array_equal(th, e[:, 2])
+    assert len(api.expand_stroke([(1.0, 2.0)], mode=0)[0]) == 0
+
+
+def test_no_cpu_fallback(built_lib):
+    import torch
+
+    from painty_b200 import api
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.PaintyError):
+        api.Context(0, api.F32)

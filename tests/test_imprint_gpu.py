@@ -1,0 +1,251 @@
+"""GPU parity of the footprint-brush imprint engine through the C ABI vs the CPU oracle / reference fixtures.
+FP64 mode must reproduce the reference to 1e-10 (it is in fact bit-exact on K/S/V); FP32 mode within 1e-4 on
+reflectance."""
+import numpy as np
+import pytest
+
+from painty_b200 import assets
+from tests.workloads import sbr_strokes
+
+pytestmark = pytest.mark.gpu
+TOL = {0: 1e-4, 1: 1e-10}
+
+
+def _maxerr(a, b):
+    return float(np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_gui_stroke_matches_reference_fixture(ctx32, ctx64, golden, prec):
+    """painty_gui default stroke, 615 imprints r=30 on 768x1024, then compose."""
+    from painty_b200 import api
+
+    ctx = [ctx32, ctx64][prec]
+    cv = api.Canvas(ctx, 768, 1024)
+    br = api.FootprintBrush(ctx, 30.0)
+    K, S = api.ComputeScatteringAndAbsorption([.2, .05, .4], [.6, .3, .7])
+    br.dip((K, S))
+    cx, cy, th = api.expand_stroke([(100.3, 200.7), (400.9, 260.2), (700.1, 180.4)], mode=1)
+    br.enable_visited_count(True)
+    br.imprint_batch(cv, cx, cy, th)
+    R = cv.compose()
+    st = cv.download("V")
+    assert (st["V"] > 0).sum() == 38022
+    assert _maxerr(R[200:264, 380:444], golden["gui_R_crop"]) <= TOL[prec]
+    assert _maxerr(R.sum(axis=(1, 2)), golden["gui_R_rowsum"]) <= TOL[prec] * 1024 * 3
+    assert abs(R.sum() - float(golden["gui_sumR"])) <= (1e-7 if prec else 2.0)
+    pK, pS, pV = br.getPickupMap()
+    assert _maxerr(pV, golden["gui_pickV"]) <= (1e-12 if prec else 1e-4)
+    if prec:
+        assert np.array_equal(st["V"][200:264, 380:444], golden["gui_V_crop"])  # bit-exact in FP64 mode
+        assert np.array_equal(pV, golden["gui_pickV"]) and np.array_equal(pK, golden["gui_pickK"])
+    visited, active = br.counters()
+    assert (visited, active) == (4235163, 677112)  # the reference's `counter` summed over the stroke
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_border_overhang_fixture(ctx32, ctx64, golden, prec):
+    """Fractional centres overhanging the top-left border: canvas pixels hit up to 4x per imprint (B#11)."""
+    from painty_b200 import api
+
+    ctx = [ctx32, ctx64][prec]
+    cv = api.Canvas(ctx, 96, 128)
+    br = api.FootprintBrush(ctx, 11.0)
+    br.dip(([.3, .2, .1], [.2, .4, .3]))
+    br.imprint_batch(cv, golden["brd_cx"], golden["brd_cy"], golden["brd_theta"])
+    br.dip(([.1, .5, .2], [.4, .1, .3]))
+    br.imprint_batch(cv, golden["brd_cx"][::-1].copy(), golden["brd_cy"][::-1].copy(), golden["brd_theta"])
+    st = cv.download("KSV")
+    if prec:
+        for k in "KSV":
+            assert np.array_equal(st[k], golden["brd_" + k]), k
+    assert _maxerr(cv.compose(), golden["brd_R"]) <= TOL[prec]
+
+
+def _run_both(ctx, port, rows, cols, script):
+    """script(make_canvas, make_brush) drives either implementation through the same calls."""
+    from painty_b200 import api
+
+    class G:  # device side
+        def __init__(self):
+            self.cv = api.Canvas(ctx, rows, cols)
+            self.br = None
+
+        def brush(self, r):
+            self.br = api.FootprintBrush(ctx, r)
+
+        def set_radius(self, r):
+            self.br.setRadius(r)
+
+        def dip(self, K, S):
+            self.br.dip((K, S))
+
+        def rates(self, p, d):
+            self.br.setPickupRate(p)
+            self.br.setDepositionRate(d)
+
+        def snapshot(self, use):
+            self.br.setUseSnapshotBuffer(use)
+
+        def imprints(self, cx, cy, th):
+            self.br.imprint_batch(self.cv, cx, cy, th)
+
+        def background(self, R0):
+            self.cv.setBackground(R0)
+
+        def dry(self):
+            self.cv.dryCanvas()
+
+        def result(self):
+            st = self.cv.download()
+            return st, self.cv.compose(), self.br.getPickupMap(), self.br.getSnapshot(self.cv)
+
+    class O:  # oracle side
+        def __init__(self):
+            self.cv = port.canvas(rows, cols)
+            self.br = None
+
+        def brush(self, r):
+            self.br = port.footprint_brush(r)
+
+        def set_radius(self, r):
+            self.br.set_radius(r)
+
+        def dip(self, K, S):
+            self.br.dip(K, S)
+
+        def rates(self, p, d):
+            self.br.set_rates(p, d)
+
+        def snapshot(self, use):
+            self.br.set_use_snapshot(use)
+
+        def imprints(self, cx, cy, th):
+            self.br.imprint_batch(self.cv, cx, cy, th)
+
+        def background(self, R0):
+            self.cv.set_background(R0)
+
+        def dry(self):
+            self.cv.dry()
+
+        def result(self):
+            import ctypes as C
+
+            n = rows * cols
+            K, S, V = np.empty((rows, cols, 3)), np.empty((rows, cols, 3)), np.empty((rows, cols))
+            f = port.fn("fbrush_get_snapshot", None, [C.c_void_p] + [C.POINTER(C.c_double)] * 3)
+            f(self.br.h, K.ctypes.data_as(C.POINTER(C.c_double)), S.ctypes.data_as(C.POINTER(C.c_double)),
+              V.ctypes.data_as(C.POINTER(C.c_double)))
+            return self.cv.get(), self.cv.compose(), self.br.pickup_map(), (K, S, V)
+
+    g, o = G(), O()
+    script(g)
+    script(o)
+    return g.result(), o.result()
+
+
+def _script_mixed(x):
+    r = np.random.default_rng(21)
+    x.background(np.random.default_rng(2).uniform(0.2, 1.0, (150, 210, 3)))
+    x.brush(8.0)
+    for s in range(8):
+        K, S = r.uniform(0.05, 1.5, 3), r.uniform(0.05, 1.0, 3)
+        n = int(r.integers(5, 70))
+        cx = np.cumsum(r.normal(0.9, 0.4, n)) + r.uniform(-8, 160)
+        cy = np.cumsum(r.normal(0.2, 0.7, n)) + r.uniform(-8, 120)
+        th = np.cumsum(r.normal(0, 0.15, n)) + r.uniform(-3.2, 3.2)
+        if s == 2:
+            x.rates(0.6, 0.2)
+        if s == 3:
+            x.snapshot(False)
+        if s == 5:
+            x.snapshot(True)
+            x.set_radius(4.0)
+        if s == 6:
+            x.set_radius(13.0)
+            x.dry()
+        if s != 4:  # stroke 4 continues with the previous paint and pickup map (no dip)
+            x.dip(K, S)
+        x.imprints(cx, cy, th)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_mixed_script_matches_oracle(ctx32, ctx64, port, prec):
+    """Several strokes with re-dips, rate changes, snapshot off/on, radius changes, a dry in between, strokes
+    crossing older ones (stale snapshot semantics) and running off every canvas border."""
+    ctx = [ctx32, ctx64][prec]
+    (gs, gR, gp, gsn), (os_, oR, op, osn) = _run_both(ctx, port, 150, 210, _script_mixed)
+    if prec:
+        for k in ("K", "S", "V", "R0", "h"):
+            assert np.array_equal(gs[k], os_[k]), k
+        for a, b in zip(gp, op):
+            assert np.array_equal(a, b)
+        for a, b in zip(gsn, osn):
+            assert np.array_equal(a, b)
+    assert _maxerr(gR, oR) <= TOL[prec]
+    assert _maxerr(gs["V"], os_["V"]) <= (0 if prec else 1e-3)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_stroke_batch_matches_sequential_oracle(ctx32, ctx64, port, prec):
+    """sbr-style batch (dip -> setRadius -> paintStroke per stroke, SbrRenderThread.cxx:68-72): concurrent
+    dataflow execution on the device must equal strictly sequential execution on the CPU."""
+    from painty_b200 import api
+
+    ctx = [ctx32, ctx64][prec]
+    rows, cols = 300, 400
+    strokes = sbr_strokes(rows, cols, 60, seed=77, sizes=(60, 40, 30, 20), safe_radius=assets.snap_to_safe_radius)
+    cvo = port.canvas(rows, cols)
+    bro = port.footprint_brush(strokes[0]["radius"])
+    cv = api.Canvas(ctx, rows, cols)
+    br = api.FootprintBrush(ctx, strokes[0]["radius"])
+    br.enable_visited_count(True)
+    rec = np.zeros(len(strokes), dtype=api.STROKE_DTYPE)
+    allx, ally, allt = [], [], []
+    first = 0
+    for i, s in enumerate(strokes):
+        cx, cy, th = api.expand_stroke(s["path"], mode=0)
+        bro.dip(s["K"], s["S"])
+        bro.set_radius(s["radius"])
+        bro.imprint_batch(cvo, cx, cy, th)
+        br.register_radius(s["radius"])
+        rec[i] = (s["radius"], s["K"], s["S"], first, len(cx))
+        first += len(cx)
+        allx.append(cx), ally.append(cy), allt.append(th)
+    br.stroke_batch(cv, rec, np.concatenate(allx), np.concatenate(ally), np.concatenate(allt))
+    a, b = cv.download("KSV"), cvo.get()
+    if prec:
+        for k in "KSV":
+            assert np.array_equal(a[k], b[k]), k
+        for x, y in zip(br.getPickupMap(), bro.pickup_map()):
+            assert np.array_equal(x, y)
+    assert _maxerr(cv.compose(), cvo.compose()) <= TOL[prec]
+    assert br.counters() == bro.counters()
+
+
+def test_unsafe_radius_policy(ctx64, port):
+    """Radii whose padded footprint is narrower than the pickup map (B#2): out-of-range footprint reads are
+    height 0 — same policy in the oracle port and on the device."""
+    from painty_b200 import api
+
+    assert not assets.is_safe_radius(12.0)
+    cv, cvo = api.Canvas(ctx64, 90, 90), port.canvas(90, 90)
+    br, bro = api.FootprintBrush(ctx64, 12.0), port.footprint_brush(12.0)
+    br.dip(([.3, .2, .1], [.2, .4, .3]))
+    bro.dip([.3, .2, .1], [.2, .4, .3])
+    cx, cy, th = np.linspace(20, 70, 50), np.linspace(30, 60, 50), np.linspace(0, 6.0, 50)
+    br.imprint_batch(cv, cx, cy, th)
+    bro.imprint_batch(cvo, cx, cy, th)
+    a, b = cv.download("KSV"), cvo.get()
+    for k in "KSV":
+        assert np.array_equal(a[k], b[k])
+
+
+def test_imprint_before_set_radius_fails(ctx32):
+    from painty_b200 import api
+
+    cv = api.Canvas(ctx32, 16, 16)
+    br = api.FootprintBrush(ctx32, 0.2)  # < 0.5: the reference leaves a 0x0 footprint (FootprintBrush.hxx:47)
+    with pytest.raises(api.PaintyError):
+        br.imprint((5.0, 5.0), 0.0, cv)
