@@ -119,12 +119,13 @@ def test_stacked_layers(ctx32, ctx64, port, prec, layers):
         R = port.compose_onto(K, S, V, R)
         if l == 0:
             r0_first = R0
-        t = torch.tensor(np.concatenate([K.reshape(n, 3).T, S.reshape(n, 3).T, V.reshape(1, n)]), dtype=dt, device="cuda")
+        t = torch.tensor(np.ascontiguousarray(np.concatenate([K.reshape(n, 3).T, S.reshape(n, 3).T, V.reshape(1, n)])), dtype=dt,
+                         device="cuda").contiguous()
         keep.append(t)
         Ks.append([t[i].data_ptr() for i in range(3)])
         Ss.append([t[3 + i].data_ptr() for i in range(3)])
         Vs.append(t[6].data_ptr())
-    r0 = torch.tensor(r0_first.reshape(n, 3).T.copy(), dtype=dt, device="cuda")
+    r0 = torch.tensor(np.ascontiguousarray(r0_first.reshape(n, 3).T), dtype=dt, device="cuda").contiguous()
     out = torch.empty_like(r0)
     torch.cuda.synchronize()
     ctx.km_compose_stacked_planes(n, Ks, Ss, Vs, [r0[i].data_ptr() for i in range(3)], [out[i].data_ptr() for i in range(3)])

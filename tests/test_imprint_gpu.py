@@ -177,8 +177,9 @@ def test_mixed_script_matches_oracle(ctx32, ctx64, port, prec):
     ctx = [ctx32, ctx64][prec]
     (gs, gR, gp, gsn), (os_, oR, op, osn) = _run_both(ctx, port, 150, 210, _script_mixed)
     if prec:
-        for k in ("K", "S", "V", "R0", "h"):
-            assert np.array_equal(gs[k], os_[k]), k
+        for k in ("K", "S", "V", "h"):
+            assert np.array_equal(gs[k], os_[k]), k  # +,-,*,/ only: bit-exact with the FMA-free CPU build
+        assert _maxerr(gs["R0"], os_["R0"]) <= 1e-12  # dried through KM: CUDA vs glibc cosh/sinh differ by ulps
         for a, b in zip(gp, op):
             assert np.array_equal(a, b)
         for a, b in zip(gsn, osn):
