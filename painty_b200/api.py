@@ -169,7 +169,7 @@ class PaintLayer:
         _chk(lib().pb_layer_create(ctx.h, rows, cols, C.byref(self.h)))
 
     def __del__(self):
-        if getattr(self, "h", None) and self.ctx.h:
+        if getattr(self, "h", None) and self.ctx.h and lib is not None:
             lib().pb_layer_destroy(self.h)
             self.h = None
 
@@ -220,7 +220,7 @@ class Canvas:
         self.band = band if band is not None else (0, rows, 0)
 
     def __del__(self):
-        if getattr(self, "h", None) and self.ctx.h:
+        if getattr(self, "h", None) and self.ctx.h and lib is not None:
             lib().pb_canvas_destroy(self.h)
             self.h = None
 
@@ -297,7 +297,7 @@ class FootprintBrush:
         self.setRadius(radius)
 
     def __del__(self):
-        if getattr(self, "h", None) and self.ctx.h:
+        if getattr(self, "h", None) and self.ctx.h and lib is not None:
             lib().pb_fbrush_destroy(self.h)
             self.h = None
 
@@ -388,7 +388,7 @@ class TextureBrush:
         _chk(lib().pb_tbrush_create(ctx.h, tm.shape[0], tm.shape[1], _p(tm), C.byref(self.h)))
 
     def __del__(self):
-        if getattr(self, "h", None) and self.ctx.h:
+        if getattr(self, "h", None) and self.ctx.h and lib is not None:
             lib().pb_tbrush_destroy(self.h)
             self.h = None
 

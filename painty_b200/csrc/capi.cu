@@ -100,6 +100,10 @@ struct pb_fbrush {
   const FootprintGeom* cur = nullptr;
   pb_planes pick;      // dense pickup map, 7 planes of size_map^2
   pb_planes snapshot;  // 7 planes, canvas sized, allocated at the first imprint (:281-284)
+  // 1 byte per canvas pixel: snapshot may differ from canvas there (touched by an imprint since its last ring copy)
+  unsigned char* dirty = nullptr;
+  int dirty_pitch      = 0;
+  uint64_t snap_canvas_id = 0, snap_canvas_version = 0;  // canvas state the dirty map is valid for
   bool use_snapshot = true;
   double pickup_rate = 0.9, deposition_rate = 0.05, capacity = 1.0;  // :477-495
   double paintK[3] = {0, 0, 0}, paintS[3] = {0, 0, 0};                // zero-initialised
@@ -174,13 +178,27 @@ void brush_set_geometry(pb_fbrush* b, double radius, const FootprintGeom* g) {
 }
 
 void ensure_snapshot(pb_fbrush* b, pb_canvas* c) {  // FootprintBrush.hxx:281-284
+  pb_context* ctx = b->ctx;
   if (b->snapshot.base == nullptr || b->snapshot.rows != c->pl.rows || b->snapshot.cols != c->pl.cols) {
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
     planes_free(b->snapshot);
-    planes_alloc(b->ctx, b->snapshot, c->pl.rows, c->pl.cols, kLayerPlanes);
+    if (b->dirty) cudaFree(b->dirty);
+    b->dirty = nullptr;
+    planes_alloc(ctx, b->snapshot, c->pl.rows, c->pl.cols, kLayerPlanes);
     for (int p = 0; p < kLayerPlanes; ++p)
-      PB_CUDA(cudaMemcpyAsync(b->snapshot.plane(p), c->pl.plane(p), static_cast<size_t>(c->pl.n()) * b->ctx->esize(),
-                              cudaMemcpyDeviceToDevice, b->ctx->stream));
+      PB_CUDA(cudaMemcpyAsync(b->snapshot.plane(p), c->pl.plane(p), static_cast<size_t>(c->pl.n()) * ctx->esize(),
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+    b->dirty_pitch = (c->pl.cols + 15) / 16 * 16;
+    const size_t bytes = static_cast<size_t>(b->dirty_pitch) * std::max(c->pl.rows, 1);
+    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->dirty), bytes));
+    PB_CUDA(cudaMemsetAsync(b->dirty, 0, bytes, ctx->stream));
+  } else if (b->snap_canvas_id != c->id || b->snap_canvas_version != c->version) {
+    // the canvas changed behind this brush's back (clear / dry / upload / another brush / another canvas of
+    // the same size): every pixel may now differ from the snapshot
+    PB_CUDA(cudaMemsetAsync(b->dirty, 1, static_cast<size_t>(b->dirty_pitch) * std::max(c->pl.rows, 1), ctx->stream));
   }
+  b->snap_canvas_id      = c->id;
+  b->snap_canvas_version = c->version;
 }
 
 struct HostStroke {
@@ -191,13 +209,17 @@ struct HostStroke {
   int flags;
 };
 
-// Uploads the plan and launches the persistent imprint kernel.
+// Uploads the plan and launches the persistent imprint kernel: one launch per run of consecutive strokes
+// that share a cluster class (CTAs per stroke); runs are ordered by the stream.
 void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs, int64_t n_imprints, const double* cx,
                   const double* cy, const double* theta) {
   pb_context* ctx = b->ctx;
   PB_REQUIRE(c->pl.ctx == ctx, "canvas and brush belong to different contexts");
   if (hs.empty()) return;
-  if (b->use_snapshot) ensure_snapshot(b, c);
+  if (b->use_snapshot || b->snapshot.base != nullptr) {
+    if (b->use_snapshot || (b->snapshot.rows == c->pl.rows && b->snapshot.cols == c->pl.cols)) ensure_snapshot(b, c);
+  }
+  const bool have_dirty = b->dirty != nullptr && b->snapshot.rows == c->pl.rows && b->snapshot.cols == c->pl.cols;
 
   std::vector<DevImprint> im(static_cast<size_t>(n_imprints));
   for (int64_t i = 0; i < n_imprints; ++i) {
@@ -206,86 +228,101 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     im[i].c  = std::cos(-theta[i]);  // FootprintBrush.hxx:95-96, per-imprint constants
     im[i].s  = std::sin(-theta[i]);
   }
-  std::vector<DevStroke> ds(hs.size());
-  std::vector<int32_t> preds;
-  DataflowPlanner planner(c->rows, c->cols);
-  int max_active = 1;
-  for (size_t s = 0; s < hs.size(); ++s) {
-    const HostStroke& h = hs[s];
-    DevStroke& d        = ds[s];
-    d.first_imprint     = h.first;
-    d.n_imprints        = static_cast<int32_t>(h.n);
-    d.n_active          = h.g->n_active;
-    d.xy                = h.g->d_xy;
-    d.fh                = h.g->d_fh;
-    d.size_map          = h.g->size_map;
-    d.side              = h.g->side;
-    d.radius            = h.radius;
-    for (int k = 0; k < 3; ++k) {
-      d.paintK[k] = h.K[k];
-      d.paintS[k] = h.S[k];
-    }
-    d.flags    = h.flags;
-    d.pad      = 0;
-    max_active = std::max(max_active, d.n_active);
-    // region the stroke reads or writes: union of the snapshot "allowed" boxes (:298-305)
-    Region r{1, 1, 0, 0};
-    if (h.n > 0) {
-      double lx = cx[h.first], hx = lx, ly = cy[h.first], hy = ly;
-      for (int64_t i = h.first; i < h.first + h.n; ++i) {
-        lx = std::min(lx, cx[i]);
-        hx = std::max(hx, cx[i]);
-        ly = std::min(ly, cy[i]);
-        hy = std::max(hy, cy[i]);
-      }
-      const double m = (h.g->side - 1) / 2 + h.radius + 2.0;
-      r.x0 = static_cast<int>(std::max(0.0, std::floor(lx - m)));
-      r.y0 = static_cast<int>(std::max(0.0, std::floor(ly - m)));
-      r.x1 = static_cast<int>(std::min<double>(c->cols - 1, std::ceil(hx + m)));
-      r.y1 = static_cast<int>(std::min<double>(c->rows - 1, std::ceil(hy + m)));
-    }
-    planner.add(static_cast<int32_t>(s), r, preds, d.pred_begin, d.pred_end);
-  }
-
-  ImprintLaunch L{};
-  size_t smem = 0;
-  imprint_plan(ctx, max_active, L.block, L.grid, smem, L.smem_cells);
-  L.grid = static_cast<int>(std::min<int64_t>(L.grid, static_cast<int64_t>(hs.size())));
-  for (int p = 0; p < kLayerPlanes; ++p) {
-    L.canvas[p]     = c->pl.plane(p);
-    L.snapshot[p]   = b->use_snapshot ? b->snapshot.plane(p) : c->pl.plane(p);
-    L.pick_dense[p] = b->pick.base ? b->pick.plane(p) : nullptr;
-  }
-  L.use_snapshot    = b->use_snapshot ? 1 : 0;
-  L.rows            = c->rows;
-  L.cols            = c->cols;
-  L.store_first     = c->store_first;
-  L.store_rows      = c->pl.rows;
-  L.pickup_rate     = b->pickup_rate;
-  L.deposition_rate = b->deposition_rate;
-  L.capacity        = b->capacity;
-  L.n_strokes       = static_cast<int64_t>(hs.size());
-
-  DevBuf<DevStroke> d_strokes(ctx, ds.size());
   DevBuf<DevImprint> d_im(ctx, im.size());
-  DevBuf<int32_t> d_preds(ctx, preds.size());
-  DevBuf<int> d_flags(ctx, ds.size() + 1);
-  d_strokes.upload(ds.data(), ds.size());
   d_im.upload(im.data(), im.size());
-  d_preds.upload(preds.data(), preds.size());
-  d_flags.zero(ds.size() + 1);
-  const bool need_scratch = max_active > L.smem_cells;
-  L.scratch_stride        = need_scratch ? static_cast<int64_t>(max_active) * kLayerPlanes : 0;
-  DevBuf<char> d_scratch(ctx, need_scratch ? static_cast<size_t>(L.scratch_stride) * L.grid * ctx->esize() : 0);
-  L.scratch  = d_scratch.p;
-  L.strokes  = d_strokes.p;
-  L.imprints = d_im.p;
-  L.preds    = d_preds.p;
-  L.done     = d_flags.p;
-  L.queue    = d_flags.p + ds.size();
-  L.counters = b->d_counters;
-  imprint_launch(ctx, L, smem);
-  if (b->count_visited) imprint_count_visited(ctx, d_strokes.p, L.n_strokes, d_im.p, c->rows, c->cols, b->d_counters + 1);
+
+  size_t run_begin = 0;
+  while (run_begin < hs.size()) {
+    const int cls  = imprint_cluster_class(hs[run_begin].g->n_active);
+    size_t run_end = run_begin + 1;
+    while (run_end < hs.size() && imprint_cluster_class(hs[run_end].g->n_active) == cls) ++run_end;
+    const size_t n_run = run_end - run_begin;
+
+    std::vector<DevStroke> ds(n_run);
+    std::vector<int32_t> preds;
+    DataflowPlanner planner(c->rows, c->cols);
+    int max_active = 1;
+    for (size_t s = 0; s < n_run; ++s) {
+      const HostStroke& h = hs[run_begin + s];
+      DevStroke& d        = ds[s];
+      d.first_imprint     = h.first;
+      d.n_imprints        = static_cast<int32_t>(h.n);
+      d.n_active          = h.g->n_active;
+      d.xy                = h.g->d_xy;
+      d.fh                = h.g->d_fh;
+      d.size_map          = h.g->size_map;
+      d.side              = h.g->side;
+      d.radius            = h.radius;
+      for (int k = 0; k < 3; ++k) {
+        d.paintK[k] = h.K[k];
+        d.paintS[k] = h.S[k];
+      }
+      d.flags    = h.flags;
+      d.pad      = 0;
+      max_active = std::max(max_active, d.n_active);
+      // region the stroke reads or writes: union of the snapshot "allowed" boxes (:298-305)
+      Region r{1, 1, 0, 0};
+      if (h.n > 0) {
+        double lx = cx[h.first], hx = lx, ly = cy[h.first], hy = ly;
+        for (int64_t i = h.first; i < h.first + h.n; ++i) {
+          lx = std::min(lx, cx[i]);
+          hx = std::max(hx, cx[i]);
+          ly = std::min(ly, cy[i]);
+          hy = std::max(hy, cy[i]);
+        }
+        const double m = (h.g->side - 1) / 2 + h.radius + 2.0;
+        r.x0 = static_cast<int>(std::max(0.0, std::floor(lx - m)));
+        r.y0 = static_cast<int>(std::max(0.0, std::floor(ly - m)));
+        r.x1 = static_cast<int>(std::min<double>(c->cols - 1, std::ceil(hx + m)));
+        r.y1 = static_cast<int>(std::min<double>(c->rows - 1, std::ceil(hy + m)));
+      }
+      planner.add(static_cast<int32_t>(s), r, preds, d.pred_begin, d.pred_end);
+    }
+
+    ImprintLaunch L{};
+    size_t smem = 0;
+    imprint_plan(ctx, max_active, L, smem);
+    L.grid = static_cast<int>(std::min<int64_t>(L.grid, static_cast<int64_t>(n_run) * L.cluster));
+    for (int p = 0; p < kLayerPlanes; ++p) {
+      L.canvas[p]     = c->pl.plane(p);
+      L.snapshot[p]   = b->use_snapshot ? b->snapshot.plane(p) : c->pl.plane(p);
+      L.pick_dense[p] = b->pick.base ? b->pick.plane(p) : nullptr;
+    }
+    L.dirty           = have_dirty ? b->dirty : nullptr;
+    L.dirty_pitch     = b->dirty_pitch;
+    L.use_snapshot    = b->use_snapshot ? 1 : 0;
+    L.rows            = c->rows;
+    L.cols            = c->cols;
+    L.store_first     = c->store_first;
+    L.store_rows      = c->pl.rows;
+    L.pickup_rate     = b->pickup_rate;
+    L.deposition_rate = b->deposition_rate;
+    L.capacity        = b->capacity;
+    L.n_strokes       = static_cast<int64_t>(n_run);
+
+    DevBuf<DevStroke> d_strokes(ctx, ds.size());
+    DevBuf<int32_t> d_preds(ctx, preds.size());
+    DevBuf<int> d_flags(ctx, ds.size() + 1);
+    d_strokes.upload(ds.data(), ds.size());
+    d_preds.upload(preds.data(), preds.size());
+    d_flags.zero(ds.size() + 1);
+    DevBuf<char> d_scratch(ctx, static_cast<size_t>(L.scratch_stride) * L.grid * ctx->esize());
+    L.scratch  = d_scratch.p;
+    L.strokes  = d_strokes.p;
+    L.imprints = d_im.p;
+    L.preds    = d_preds.p;
+    L.done     = d_flags.p;
+    L.queue    = d_flags.p + ds.size();
+    L.counters = b->d_counters;
+    imprint_launch(ctx, L, smem);
+    if (b->count_visited) imprint_count_visited(ctx, d_strokes.p, L.n_strokes, d_im.p, c->rows, c->cols, b->d_counters + 1);
+    run_begin = run_end;
+  }
+  c->version++;
+  if (have_dirty) {
+    b->snap_canvas_id      = c->id;
+    b->snap_canvas_version = c->version;
+  }
 }
 
 }  // namespace
@@ -475,6 +512,8 @@ int pb_canvas_create_band(pb_context* ctx, int rows, int cols, int row_begin, in
   c->row_begin   = row_begin;
   c->row_end     = row_end;
   c->halo        = halo;
+  static uint64_t next_id = 1;
+  c->id          = next_id++;
   c->store_first = std::max(0, row_begin - halo);
   const int last = std::min(rows, row_end + halo);
   planes_alloc(ctx, c->pl, last - c->store_first, cols, kCanvasPlanes);
@@ -505,12 +544,14 @@ int pb_canvas_stored_rows(const pb_canvas* c, int* first_row, int* n_rows) {
 int pb_canvas_clear(pb_canvas* c) {
   PB_API_BEGIN
   DeviceGuard g(c->pl.ctx);
+  c->version++;
   canvas_clear(c);
   PB_API_END
 }
 int pb_canvas_set_background(pb_canvas* c, const double* R0) {
   PB_API_BEGIN
   DeviceGuard g(c->pl.ctx);
+  c->version++;
   canvas_clear(c);
   upload_aos(c->pl.ctx, c->pl, PR, 3, R0);
   PB_API_END
@@ -518,6 +559,7 @@ int pb_canvas_set_background(pb_canvas* c, const double* R0) {
 int pb_canvas_dry(pb_canvas* c) {
   PB_API_BEGIN
   DeviceGuard g(c->pl.ctx);
+  c->version++;
   void* planes[kCanvasPlanes];
   for (int p = 0; p < kCanvasPlanes; ++p) planes[p] = c->pl.plane(p);
   km_dry(c->pl.ctx, c->pl.n(), planes);
@@ -526,6 +568,7 @@ int pb_canvas_dry(pb_canvas* c) {
 int pb_canvas_upload_layer(pb_canvas* c, const double* K, const double* S, const double* V) {
   PB_API_BEGIN
   DeviceGuard g(c->pl.ctx);
+  c->version++;
   if (K) upload_aos(c->pl.ctx, c->pl, PK, 3, K);
   if (S) upload_aos(c->pl.ctx, c->pl, PS, 3, S);
   if (V) upload_aos(c->pl.ctx, c->pl, PV, 1, V);
@@ -650,6 +693,7 @@ int pb_fbrush_destroy(pb_fbrush* b) {
     }
     planes_free(b->pick);
     planes_free(b->snapshot);
+    if (b->dirty) cudaFree(b->dirty);
     cudaFree(b->d_counters);
     delete b;
   }
@@ -720,6 +764,9 @@ int pb_fbrush_update_snapshot(pb_fbrush* b, pb_canvas* c) {
     for (int p = 0; p < kLayerPlanes; ++p)
       PB_CUDA(cudaMemcpyAsync(b->snapshot.plane(p), c->pl.plane(p), static_cast<size_t>(c->pl.n()) * b->ctx->esize(),
                               cudaMemcpyDeviceToDevice, b->ctx->stream));
+    PB_CUDA(cudaMemsetAsync(b->dirty, 0, static_cast<size_t>(b->dirty_pitch) * std::max(c->pl.rows, 1), b->ctx->stream));
+    b->snap_canvas_id      = c->id;
+    b->snap_canvas_version = c->version;
   }
   PB_API_END
 }
@@ -931,6 +978,7 @@ int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const 
   L.done        = d_flags.p;
   L.queue       = d_flags.p + ds.size();
   L.counters    = b->d_counters;
+  c->version++;
   texture_launch(ctx, L);
   PB_API_END
 }

@@ -73,6 +73,8 @@ struct pb_canvas {
   int row_begin = 0, row_end = 0;  // owned band
   int halo      = 0;
   int store_first = 0;  // first stored global row
+  uint64_t id      = 0;  // unique per canvas
+  uint64_t version = 1;  // bumped by every operation that modifies the wet layer
 };
 
 namespace pb {

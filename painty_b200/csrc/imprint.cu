@@ -4,28 +4,38 @@
 // :331-340 (blend), :349-384 (pickupPaint), :393-431 (depositPaint) on SoA planes in HBM.
 //
 // Parallel decomposition (nothing like the reference's serial double loop):
-//   * a STROKE (dip -> setRadius -> chain of imprints) is owned by one persistent CTA; strokes are
-//     popped from a queue in submission order and wait on completion flags of the earlier strokes
-//     whose footprint+snapshot region overlaps theirs (host-built predecessor lists) — a dataflow
-//     schedule that keeps the reference's stroke order wherever it is observable;
+//   * a STROKE (dip -> setRadius -> chain of imprints) is owned by one persistent thread-block CLUSTER
+//     (1..16 CTAs, ~2 active footprint cells per thread); strokes are popped from a queue in submission
+//     order and wait on completion flags of the earlier strokes whose footprint+snapshot region overlaps
+//     theirs (host-built predecessor lists) — a dataflow schedule that keeps the reference's stroke order
+//     wherever it is observable. Consecutive imprints of a stroke are a true dependency chain; the
+//     cluster-wide hardware barrier between them is the latency floor;
 //   * inside an imprint a thread owns ACTIVE pickup-map cells (footprint height > 0, ~14.5 % of the
-//     padded square, compacted once per radius). Its pickup-map state (7 values per cell) lives in shared
-//     memory for the whole stroke (global scratch for footprints too large for 227 KB). For each
-//     imprint the thread inverts the rotation to find the <= 2 canvas pixels whose rotated+rounded
-//     position is its cell, checks each candidate with the reference's exact f64 forward expression, and
-//     applies pickup+deposit to them in row-major order — which is exactly the order in which the
-//     reference's (row, col) loop hits a shared pickup cell. No two threads ever touch the same cell;
+//     padded square, compacted once per radius). Its pickup-map state (7 values per cell) lives in the
+//     CTA's shared memory for the whole stroke. For each imprint the thread inverts the rotation to find
+//     the <= 2 canvas pixels whose rotated+rounded position is its cell, checks each candidate with the
+//     reference's exact f64 forward expression, and applies pickup+deposit to them in row-major order —
+//     exactly the order in which the reference's (row, col) loop hits a shared pickup cell. No two
+//     threads ever touch the same cell;
 //   * canvas pixels are hit at most once per imprint except at the left/top border, where C++
 //     truncation folds column/row (-1,0) onto 0. Those imprints run in <= 4 barrier-separated
 //     phases ordered by (row-negative?, col-negative?) which reproduces the row-major order;
+//   * updateSnapshot copies a canvas ring of ~2x the footprint area on EVERY imprint in the reference. Here a
+//     byte-per-pixel dirty map records where snapshot and canvas can differ (only pixels touched by an
+//     imprint since their last copy); the ring pass scans the map with 32-bit loads and copies just the dirty
+//     pixels — bit-identical result, ~50x less traffic;
 //   * per-imprint constants (centre, cos/sin(-theta)) are computed on the host in f64 with the same libm
 //     as the reference; all index maths on the device is IEEE f64 without FMA contraction, so every
 //     round()/trunc() decision is bit-identical to the CPU's;
-//   * canvas and snapshot planes are accessed with L2-only loads/stores (ld/st.global.cg): they are shared
-//     between SMs, and the 126 MB L2 keeps the working set of the running strokes resident.
+//   * canvas, snapshot and dirty planes are accessed with L2-only loads/stores (ld/st.global.cg): they are
+//     shared between SMs, and the 126 MB L2 keeps the working set of the running strokes resident.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 #include "imprint.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pb {
 namespace {
@@ -39,15 +49,36 @@ __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// FootprintBrush.hxx:331-340
+// FootprintBrush.hxx:331-340: blend(va, a, vb, b) = vt > MinVolume ? (va*a + vb*b)/vt : a, applied to the six
+// K/S components that share one (va, vb). FP64 keeps the reference's exact operation order. FP32 mode evaluates
+// the six quotients with one reciprocal (error ~1e-7 relative, far inside the 1e-4 reflectance budget).
+struct Blend6d {
+  double va, vb, vt;
+  bool on;
+  __device__ __forceinline__ Blend6d(double a, double b) : va(a), vb(b), vt(a + b), on(a + b > kMinVolume) {}
+  __device__ __forceinline__ double operator()(double a, double b) const { return on ? (va * a + vb * b) / vt : a; }
+};
+struct Blend6f {
+  float wa, wb;
+  bool on;
+  __device__ __forceinline__ Blend6f(float a, float b) {
+    const float vt = a + b;
+    on             = vt > static_cast<float>(kMinVolume);
+    const float r  = __frcp_rn(vt);
+    wa             = a * r;
+    wb             = b * r;
+  }
+  __device__ __forceinline__ float operator()(float a, float b) const { return on ? fmaf(wa, a, wb * b) : a; }
+};
 template <typename T>
-__device__ __forceinline__ T blend(T va, T a, T vb, T b) {
-  const T vt = va + vb;
-  return (vt > static_cast<T>(kMinVolume)) ? (va * a + vb * b) / vt : a;
-}
-
-struct Hit {
-  int px, py, cls;
+struct BlendSel;
+template <>
+struct BlendSel<float> {
+  using type = Blend6f;
+};
+template <>
+struct BlendSel<double> {
+  using type = Blend6d;
 };
 
 template <typename T>
@@ -60,9 +91,11 @@ struct OpCtx {
 
 // pickupPaint (:349-384) then depositPaint (:393-431) for one (canvas pixel, pickup cell) pair.
 template <typename T>
-__device__ __forceinline__ void pickup_deposit(const OpCtx<T>& C, int64_t ci, T fh, T* pick, int64_t ps, int cell) {
-  // issue every independent load first
-  T cK[3], cS[3];
+__device__ __forceinline__ void pickup_deposit(const OpCtx<T>& C, int64_t ci, T fh, T* pick, int ps, int slot) {
+  using Blend = typename BlendSel<T>::type;
+  // issue every independent load first (the imprint chain is latency bound)
+  const bool own_src = C.src[PV] == C.can[PV];  // snapshot buffer disabled: pickup source is the canvas itself
+  T cK[3], cS[3], sK[3], sS[3];
   const T vSrc = __ldcg(C.src[PV] + ci);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -70,63 +103,144 @@ __device__ __forceinline__ void pickup_deposit(const OpCtx<T>& C, int64_t ci, T 
     cS[k] = __ldcg(C.can[PS + k] + ci);
   }
   T vCan = __ldcg(C.can[PV] + ci);
-  T vP   = pick[PV * ps + cell];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    sK[k] = own_src ? cK[k] : __ldcg(C.src[PK + k] + ci);
+    sS[k] = own_src ? cS[k] : __ldcg(C.src[PS + k] + ci);
+  }
+  T vP = pick[PV * ps + slot];
   T pK[3], pS[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    pK[k] = pick[(PK + k) * ps + cell];
-    pS[k] = pick[(PS + k) * ps + cell];
+    pK[k] = pick[(PK + k) * ps + slot];
+    pS[k] = pick[(PS + k) * ps + slot];
   }
   // pickup
   const T leave = C.pickup_rate * vSrc * fh;
   if (leave > static_cast<T>(kMinVolume)) {
     const T remain = vSrc - leave;
     __stcg(C.src[PV] + ci, remain);
-    if (C.src[PV] == C.can[PV]) {  // snapshot buffer disabled: pickup source is the canvas itself
-      vCan = remain;
+    if (own_src) vCan = remain;
+    const Blend bl(vP, leave);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        pK[k] = blend(vP, pK[k], leave, cK[k]);
-        pS[k] = blend(vP, pS[k], leave, cS[k]);
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        pK[k] = blend(vP, pK[k], leave, __ldcg(C.src[PK + k] + ci));
-        pS[k] = blend(vP, pS[k], leave, __ldcg(C.src[PS + k] + ci));
-      }
+    for (int k = 0; k < 3; ++k) {
+      pK[k] = bl(pK[k], sK[k]);
+      pS[k] = bl(pS[k], sS[k]);
     }
     vP = vP + leave;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      pick[(PK + k) * ps + cell] = pK[k];
-      pick[(PS + k) * ps + cell] = pS[k];
+      pick[(PK + k) * ps + slot] = pK[k];
+      pick[(PS + k) * ps + slot] = pS[k];
     }
   }
   // deposit
   const T vFree = fmax(static_cast<T>(0), C.cap - vP);
-  T kSrc[3], sSrc[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    kSrc[k] = blend(vP, pK[k], vFree, C.paintK[k]);
-    sSrc[k] = blend(vP, pS[k], vFree, C.paintS[k]);
-  }
+  const Blend b_src(vP, vFree);
   const T vLeave       = C.deposition_rate * vP * fh;
-  pick[PV * ps + cell] = vP - vLeave;
+  pick[PV * ps + slot] = vP - vLeave;
   const T vB           = C.cap * fh;
+  const Blend b_can(vB, vCan);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    __stcg(C.can[PK + k] + ci, blend(vB, kSrc[k], vCan, cK[k]));
-    __stcg(C.can[PS + k] + ci, blend(vB, sSrc[k], vCan, cS[k]));
+    __stcg(C.can[PK + k] + ci, b_can(b_src(pK[k], C.paintK[k]), cK[k]));
+    __stcg(C.can[PS + k] + ci, b_can(b_src(pS[k], C.paintS[k]), cS[k]));
   }
   __stcg(C.can[PV] + ci, vB + vCan);
 }
 
+// updateSnapshot(canvas, centre) (:278-319): copy canvas -> snapshot on the ring "allowed box minus open
+// interior". Only pixels flagged in the dirty map can differ, so the pass scans the map (one 32-bit word = 4
+// pixels) and copies just those. The imprint chain is latency bound, hence every thread first issues ALL of its
+// word loads (kScanBatch independent L2 requests in flight), then all pixel loads of a dirty word, then stores.
+constexpr int kScanBatch = 8;
+
+struct RingGeom {
+  int tlx, tly, brx, bry;  // footprint box corners (exclusive interior bounds)
+  int ax0, ay0, ax1, ay1;  // allowed box, clipped to canvas and stored rows
+};
+
 template <typename T>
-__global__ void __launch_bounds__(1024, 1) imprint_kernel(const ImprintLaunch L) {
+__device__ __forceinline__ void ring_word(const ImprintLaunch& L, const OpCtx<T>& C, const RingGeom& g, int row, int wi,
+                                          unsigned word) {
+  const bool mid = row > g.tly && row < g.bry;
+  unsigned char* drow = L.dirty + static_cast<int64_t>(row - L.store_first) * L.dirty_pitch;
+  const int64_t rbase = static_cast<int64_t>(row - L.store_first) * L.cols;
+  bool need[4];
+  T v[4][kLayerPlanes];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int col = wi * 4 + b;
+    need[b] = ((word >> (8 * b)) & 0xffu) != 0u && col >= g.ax0 && col <= g.ax1 && !(mid && col > g.tlx && col < g.brx);
+    if (need[b]) {
+#pragma unroll
+      for (int k = 0; k < kLayerPlanes; ++k) v[b][k] = __ldcg(C.can[k] + rbase + col);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    if (need[b]) {
+      const int col = wi * 4 + b;
+#pragma unroll
+      for (int k = 0; k < kLayerPlanes; ++k) __stcg(C.src[k] + rbase + col, v[b][k]);
+      __stcg(drow + col, static_cast<unsigned char>(0));
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const OpCtx<T>& C, const RingGeom& g, int gt, int gstride) {
+  if (g.ax1 < g.ax0 || g.ay1 < g.ay0) return;
+  const int w0 = g.ax0 >> 2, nw = (g.ax1 >> 2) - w0 + 1, nrows = g.ay1 - g.ay0 + 1;
+  const int total = nw * nrows;
+  const float inv = 1.0f / static_cast<float>(nw);
+  // words lying completely inside the open interior (on interior rows) are never read
+  const int iw0 = (g.tlx >> 2) + 1, iw1 = (g.brx - 4) >> 2;
+  for (int base = gt; base < total; base += gstride * kScanBatch) {
+    unsigned word[kScanBatch];
+    int rows[kScanBatch], wis[kScanBatch];
+#pragma unroll
+    for (int u = 0; u < kScanBatch; ++u) {
+      const int i = base + u * gstride;
+      word[u]     = 0u;
+      if (i < total) {
+        int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv);  // i / nw without integer division
+        r     = min(r, nrows - 1);
+        if (r * nw > i) --r;
+        if ((r + 1) * nw <= i) ++r;
+        const int wi = w0 + (i - r * nw), row = g.ay0 + r;
+        rows[u] = row;
+        wis[u]  = wi;
+        if (!(row > g.tly && row < g.bry && wi >= iw0 && wi <= iw1))
+          word[u] = __ldcg(reinterpret_cast<const unsigned*>(L.dirty + static_cast<int64_t>(row - L.store_first) * L.dirty_pitch) + wi);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kScanBatch; ++u)
+      if (word[u] != 0u) ring_word(L, C, g, rows[u], wis[u], word[u]);
+  }
+}
+
+constexpr int kRegCells = 2;  // cells per thread whose geometry is kept in registers across the stroke
+
+template <typename T, bool CL, int MAXB>
+__global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_stroke;
   __shared__ unsigned long long s_active;
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, bd = blockDim.x;
+  const int crank   = CL ? static_cast<int>(cluster.block_rank()) : 0;
+  const int csize   = CL ? static_cast<int>(cluster.num_blocks()) : 1;
+  const int gt      = crank * bd + tid;
+  const int gstride = csize * bd;
+  auto sync_all = [&]() {
+    if (CL)
+      cluster.sync();
+    else
+      __syncthreads();
+  };
 
   OpCtx<T> C;
 #pragma unroll
@@ -138,91 +252,125 @@ __global__ void __launch_bounds__(1024, 1) imprint_kernel(const ImprintLaunch L)
   C.deposition_rate = static_cast<T>(L.deposition_rate);
   C.cap             = static_cast<T>(L.capacity);
 
-  const int tid = threadIdx.x, bd = blockDim.x;
   if (tid == 0) s_active = 0ull;
   unsigned long long my_active = 0;
+  const int row_lo = L.store_first, row_hi = L.store_first + L.store_rows - 1;
 
   for (;;) {
-    __syncthreads();
-    if (tid == 0) s_stroke = atomicAdd(L.queue, 1);
-    __syncthreads();
-    const int64_t si = s_stroke;
+    sync_all();
+    if (crank == 0 && tid == 0) s_stroke = atomicAdd(L.queue, 1);
+    sync_all();
+    const int64_t si = CL ? *cluster.map_shared_rank(&s_stroke, 0) : s_stroke;
     if (si >= L.n_strokes) break;
     const DevStroke st = L.strokes[si];
 
     // dataflow wait: every earlier stroke whose region overlaps ours has completed
-    for (int p = st.pred_begin + tid; p < st.pred_end; p += bd) {
-      const int* flag = L.done + L.preds[p];
-      while (ld_acquire(flag) == 0) __nanosleep(64);
+    if (crank == 0) {
+      for (int p = st.pred_begin + tid; p < st.pred_end; p += bd) {
+        const int* flag = L.done + L.preds[p];
+        while (ld_acquire(flag) == 0) __nanosleep(64);
+      }
     }
-    __syncthreads();
+    sync_all();
 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       C.paintK[k] = static_cast<T>(st.paintK[k]);
       C.paintS[k] = static_cast<T>(st.paintS[k]);
     }
-    const int nA       = st.n_active;
-    const int wr       = (st.side - 1) / 2;  // == hr (square footprint), FootprintBrush.hxx:75-78
-    const T* fhs       = static_cast<const T*>(st.fh);
-    const bool in_smem = nA <= L.smem_cells;
-    T* pick            = in_smem ? reinterpret_cast<T*>(smem_raw) : static_cast<T*>(L.scratch) + blockIdx.x * L.scratch_stride;
-    const int64_t ps   = in_smem ? L.smem_cells : L.scratch_stride / kLayerPlanes;
+    const int nA = st.n_active;
+    const int wr = (st.side - 1) / 2;  // == hr (square footprint), FootprintBrush.hxx:75-78
+    const T* fhs = static_cast<const T*>(st.fh);
+    // this CTA's slice of the pickup map: cell = gt + k*gstride lives in slot tid + k*bd
+    const int my_cells  = nA > gt ? (nA - gt + gstride - 1) / gstride : 0;
+    const int cta_cells = ((nA + gstride - 1) / gstride) * bd;
+    const bool in_smem  = cta_cells <= L.smem_cells;
+    T* pick      = in_smem ? reinterpret_cast<T*>(smem_raw) : static_cast<T*>(L.scratch) + blockIdx.x * L.scratch_stride;
+    const int ps = in_smem ? L.smem_cells : static_cast<int>(L.scratch_stride / kLayerPlanes);
 
-    // dip() = clean pickup map (:150-166), or continue with the brush's persistent map
-    for (int cell = tid; cell < nA; cell += bd) {
-      if (st.flags & 1) {
-        const uint32_t xy = st.xy[cell];
-        const int64_t mi  = static_cast<int64_t>(xy >> 16) * st.size_map + (xy & 0xffffu);
+    // per-thread cell geometry in registers; dip() = clean pickup map (:150-166) or continue with the brush's map
+    int cmx[kRegCells], cmy[kRegCells];
+    T cfh[kRegCells];
 #pragma unroll
-        for (int k = 0; k < kLayerPlanes; ++k) pick[k * ps + cell] = static_cast<const T*>(L.pick_dense[k])[mi];
+    for (int k = 0; k < kRegCells; ++k) {
+      cmx[k] = cmy[k] = 0;
+      cfh[k]          = static_cast<T>(0);
+    }
+    for (int k = 0; k < my_cells; ++k) {
+      const int cell = gt + k * gstride, slot = tid + k * bd;
+      const uint32_t xy = st.xy[cell];
+      if (k < kRegCells) {
+#pragma unroll
+        for (int q = 0; q < kRegCells; ++q)
+          if (q == k) {
+            cmx[q] = static_cast<int>(xy & 0xffffu);
+            cmy[q] = static_cast<int>(xy >> 16);
+            cfh[q] = fhs[cell];
+          }
+      }
+      if (st.flags & 1) {
+        const int64_t mi = static_cast<int64_t>(xy >> 16) * st.size_map + (xy & 0xffffu);
+#pragma unroll
+        for (int q = 0; q < kLayerPlanes; ++q) pick[q * ps + slot] = static_cast<const T*>(L.pick_dense[q])[mi];
       } else {
 #pragma unroll
-        for (int k = 0; k < kLayerPlanes; ++k) pick[k * ps + cell] = static_cast<T>(0);
+        for (int q = 0; q < kLayerPlanes; ++q) pick[q * ps + slot] = static_cast<T>(0);
       }
     }
 
+    DevImprint nxt = st.n_imprints > 0 ? L.imprints[st.first_imprint] : DevImprint{0, 0, 1, 0};
     for (int ii = 0; ii < st.n_imprints; ++ii) {
-      const DevImprint im = L.imprints[st.first_imprint + ii];
+      const DevImprint im = nxt;
+      if (ii + 1 < st.n_imprints) nxt = L.imprints[st.first_imprint + ii + 1];  // prefetch (hidden behind this imprint)
 
       if (L.use_snapshot) {
-        // updateSnapshot(canvas, centre) (:278-319): copy the ring allowed-box \ open interior
-        const int tlx = static_cast<int>(im.cx - wr), tly = static_cast<int>(im.cy - wr);
-        const int brx = static_cast<int>(im.cx + wr), bry = static_cast<int>(im.cy + wr);
-        const int ax0 = max(static_cast<int>(im.cx - wr - st.radius), 0);
-        const int ay0 = max(max(static_cast<int>(im.cy - wr - st.radius), 0), L.store_first);
-        const int ax1 = min(static_cast<int>(im.cx + wr + st.radius), L.cols - 1);
-        const int ay1 = min(min(static_cast<int>(im.cy + wr + st.radius), L.rows - 1), L.store_first + L.store_rows - 1);
-        const int w   = ax1 - ax0 + 1;
-        if (w > 0 && ay1 >= ay0) {
-          const int total = w * (ay1 - ay0 + 1);
-          for (int i = tid; i < total; i += bd) {
-            const int row = ay0 + i / w, col = ax0 + i % w;
-            if (row > tly && row < bry && col > tlx && col < brx) continue;
-            const int64_t ci = static_cast<int64_t>(row - L.store_first) * L.cols + col;
-#pragma unroll
-            for (int k = 0; k < kLayerPlanes; ++k) __stcg(C.src[k] + ci, __ldcg(C.can[k] + ci));
-          }
-        }
+        // updateSnapshot(canvas, centre) (:278-319): refresh the ring allowed-box \ open interior
+        RingGeom g;
+        g.tlx = static_cast<int>(im.cx - wr), g.tly = static_cast<int>(im.cy - wr);
+        g.brx = static_cast<int>(im.cx + wr), g.bry = static_cast<int>(im.cy + wr);
+        g.ax0 = max(static_cast<int>(im.cx - wr - st.radius), 0);
+        g.ay0 = max(max(static_cast<int>(im.cy - wr - st.radius), 0), row_lo);
+        g.ax1 = min(static_cast<int>(im.cx + wr + st.radius), L.cols - 1);
+        g.ay1 = min(min(static_cast<int>(im.cy + wr + st.radius), L.rows - 1), row_hi);
+        ring_scan(L, C, g, gt, gstride);
       }
       // left/top overhang: canvas pixels of column/row 0 can be hit twice (B#11) -> ordered phases
       const bool border = (im.cx - wr < 0.0) || (im.cy - wr < 0.0);
-      __syncthreads();
+      const float fc = static_cast<float>(im.c), fs = static_cast<float>(im.s);
+      sync_all();
 
       const int n_phase = border ? 4 : 1;
       for (int ph = 0; ph < n_phase; ++ph) {
-        for (int cell = tid; cell < nA; cell += bd) {
-          const uint32_t xy = st.xy[cell];
-          const int mx = static_cast<int>(xy & 0xffffu), my = static_cast<int>(xy >> 16);
-          const double u = mx - wr, v = my - wr;
-          // inverse rotation gives the centre of the cell's pre-image; its bounding box has half-width
-          // (|c|+|s|)/2 <= 0.7072, so at most 2x2 lattice candidates exist
-          const double colf = u * im.c + v * im.s;
-          const double rowf = v * im.c - u * im.s;
-          const int c_lo = max(static_cast<int>(ceil(colf - 0.7075)), -wr), c_hi = min(static_cast<int>(floor(colf + 0.7075)), wr);
-          const int r_lo = max(static_cast<int>(ceil(rowf - 0.7075)), -wr), r_hi = min(static_cast<int>(floor(rowf + 0.7075)), wr);
-          for (int row = r_lo; row <= r_hi; ++row) {
-            for (int col = c_lo; col <= c_hi; ++col) {
+        for (int k = 0; k < my_cells; ++k) {
+          const int cell = gt + k * gstride, slot = tid + k * bd;
+          int mx, my;
+          T fh;
+          if (k < kRegCells) {
+            mx = k == 0 ? cmx[0] : cmx[1];
+            my = k == 0 ? cmy[0] : cmy[1];
+            fh = k == 0 ? cfh[0] : cfh[1];
+          } else {
+            const uint32_t xy = st.xy[cell];
+            mx = static_cast<int>(xy & 0xffffu);
+            my = static_cast<int>(xy >> 16);
+            fh = fhs[cell];
+          }
+          // Inverse rotation gives the centre (colf,rowf) of the cell's pre-image, a unit square rotated by
+          // theta. A lattice point (col,row) can only map to this cell if its rotated offset from the cell
+          // centre is within 0.5 in both axes; the float pre-filter keeps a 0.01 margin and the survivors
+          // (1 or 2 of the 2x2 neighbourhood) are decided by the reference's exact f64 expression.
+          const float u = static_cast<float>(mx - wr), v = static_cast<float>(my - wr);
+          const float colf = fmaf(u, fc, v * fs), rowf = fmaf(v, fc, -u * fs);
+          const int c0 = static_cast<int>(floorf(colf)), r0 = static_cast<int>(floorf(rowf));
+#pragma unroll
+          for (int dr = 0; dr < 2; ++dr) {
+#pragma unroll
+            for (int dc = 0; dc < 2; ++dc) {
+              const int row = r0 + dr, col = c0 + dc;
+              const float ec = static_cast<float>(col) - colf, er = static_cast<float>(row) - rowf;
+              const float du = fmaf(ec, fc, -er * fs), dv = fmaf(ec, fs, er * fc);
+              if (fabsf(du) > 0.51f || fabsf(dv) > 0.51f) continue;
+              if (col < -wr || col > wr || row < -wr || row > wr) continue;
               // the reference's forward map (:95-100), same expression order, no FMA
               const double rc = col * im.c - row * im.s;
               const double rr = col * im.s + row * im.c;
@@ -231,27 +379,29 @@ __global__ void __launch_bounds__(1024, 1) imprint_kernel(const ImprintLaunch L)
               const int px = static_cast<int>(fx), py = static_cast<int>(fy);  // trunc toward zero (:92-93)
               if (py < 0 || px < 0 || px >= L.cols || py >= L.rows) continue;
               if (border && ((fy >= 0.0 ? 2 : 0) + (fx >= 0.0 ? 1 : 0)) != ph) continue;
-              if (py < L.store_first || py >= L.store_first + L.store_rows) continue;  // band canvas
-              const int64_t ci = static_cast<int64_t>(py - L.store_first) * L.cols + px;
-              pickup_deposit(C, ci, fhs[cell], pick, ps, cell);
+              if (py < row_lo || py > row_hi) continue;  // band canvas
+              const int64_t ci = static_cast<int64_t>(py - row_lo) * L.cols + px;
+              pickup_deposit(C, ci, fh, pick, ps, slot);
+              if (L.dirty) __stcg(L.dirty + static_cast<int64_t>(py - row_lo) * L.dirty_pitch + px, static_cast<unsigned char>(1));
               ++my_active;
             }
           }
         }
-        __syncthreads();
+        sync_all();
       }
     }
 
     if (st.flags & 2) {
-      for (int cell = tid; cell < nA; cell += bd) {
+      for (int k = 0; k < my_cells; ++k) {
+        const int cell = gt + k * gstride, slot = tid + k * bd;
         const uint32_t xy = st.xy[cell];
         const int64_t mi  = static_cast<int64_t>(xy >> 16) * st.size_map + (xy & 0xffffu);
 #pragma unroll
-        for (int k = 0; k < kLayerPlanes; ++k) static_cast<T*>(L.pick_dense[k])[mi] = pick[k * ps + cell];
+        for (int q = 0; q < kLayerPlanes; ++q) static_cast<T*>(L.pick_dense[q])[mi] = pick[q * ps + slot];
       }
     }
-    __syncthreads();
-    if (tid == 0) {
+    sync_all();
+    if (crank == 0 && tid == 0) {
       __threadfence();
       st_release(L.done + si, 1);
     }
@@ -260,6 +410,7 @@ __global__ void __launch_bounds__(1024, 1) imprint_kernel(const ImprintLaunch L)
   if (my_active) atomicAdd(&s_active, my_active);
   __syncthreads();
   if (tid == 0 && s_active) atomicAdd(L.counters, s_active);
+  if (CL) cluster.sync();  // rank 0's shared memory must outlive the last remote read of s_stroke
 }
 
 __global__ void __launch_bounds__(256) count_visited_kernel(const DevStroke* strokes, int64_t n_strokes,
@@ -291,39 +442,92 @@ __global__ void __launch_bounds__(256) count_visited_kernel(const DevStroke* str
   if (threadIdx.x == 0 && s_sum) atomicAdd(counter, s_sum);
 }
 
+// variants by maximum block size: smaller CTAs get a larger register budget (no spills on the critical path)
+template <typename T, bool CL>
+const void* kernel_ptr_b(int block) {
+  if (block <= 256) return reinterpret_cast<const void*>(imprint_kernel<T, CL, 256>);
+  if (block <= 512) return reinterpret_cast<const void*>(imprint_kernel<T, CL, 512>);
+  return reinterpret_cast<const void*>(imprint_kernel<T, CL, 1024>);
+}
+const void* kernel_ptr(int precision, bool cl, int block) {
+  if (precision == PB_F64) return cl ? kernel_ptr_b<double, true>(block) : kernel_ptr_b<double, false>(block);
+  return cl ? kernel_ptr_b<float, true>(block) : kernel_ptr_b<float, false>(block);
+}
+
 }  // namespace
 
-void imprint_plan(pb_context* ctx, int max_active, int& block, int& grid, size_t& smem_bytes, int& smem_cells) {
-  block = 128;
-  while (block < 1024 && block < max_active) block *= 2;
-  const size_t es = ctx->esize();
-  // up to 200 KB of dynamic shared memory for the pickup-map state of one stroke
-  const size_t budget = 200 * 1024;
-  size_t need         = static_cast<size_t>(max_active) * kLayerPlanes * es;
+// A stroke is latency bound (a chain of dependent imprints), so it is spread thin: CTAs of 128..1024 threads on
+// up to 16 SMs (non-portable cluster size), about one active cell per thread.
+int imprint_cluster_class(int n_active) {
+  int c = 1;
+  while (c < 16 && n_active > c * 160) c *= 2;
+  return c;
+}
+
+void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& smem_bytes) {
+  const int cluster = imprint_cluster_class(max_active);
+  int block         = 128;
+  while (block < 1024 && block * cluster < max_active) block *= 2;
+  const size_t es     = ctx->esize();
+  const int gstride   = cluster * block;
+  const int cta_cells = std::max(1, (max_active + gstride - 1) / gstride) * block;
+  const size_t budget = 200 * 1024;  // dynamic shared memory for this CTA's slice of the pickup map
+  size_t need         = static_cast<size_t>(cta_cells) * kLayerPlanes * es;
   if (need <= budget) {
-    smem_cells = std::max(max_active, 1);
-    smem_bytes = static_cast<size_t>(smem_cells) * kLayerPlanes * es;
-  } else {
-    // the large footprints go to global scratch; keep shared memory for the ones that fit
-    smem_cells = static_cast<int>(budget / (kLayerPlanes * es));
-    smem_bytes = static_cast<size_t>(smem_cells) * kLayerPlanes * es;
+    L.smem_cells     = cta_cells;
+    L.scratch_stride = 0;
+  } else {  // only reachable for footprints beyond ~59k active cells (radius > 200): global scratch
+    L.smem_cells     = 0;
+    need             = 0;
+    L.scratch_stride = static_cast<int64_t>(cta_cells) * kLayerPlanes;
   }
-  const void* fn = ctx->precision == PB_F64 ? reinterpret_cast<const void*>(imprint_kernel<double>)
-                                             : reinterpret_cast<const void*>(imprint_kernel<float>);
+  smem_bytes = need;
+  L.block    = block;
+  L.cluster  = cluster;
+  const void* fn = kernel_ptr(ctx->precision, cluster > 1, block);
   PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-  int per_sm = 0;
-  PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem_bytes));
-  PB_REQUIRE(per_sm >= 1, "imprint kernel does not fit on an SM");
-  grid = ctx->sm_count * per_sm;
+  if (cluster > 8) PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  if (cluster == 1) {
+    int per_sm = 0;
+    PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem_bytes));
+    PB_REQUIRE(per_sm >= 1, "imprint kernel does not fit on an SM");
+    L.grid = ctx->sm_count * per_sm;
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = dim3(static_cast<unsigned>(cluster * ctx->sm_count));
+    cfg.blockDim           = dim3(static_cast<unsigned>(block));
+    cfg.dynamicSmemBytes   = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id               = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs                = attr;
+    cfg.numAttrs             = 1;
+    int n_clusters           = 0;
+    PB_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, fn, &cfg));
+    PB_REQUIRE(n_clusters >= 1, "imprint kernel: no cluster of the requested size fits on the device");
+    L.grid = n_clusters * cluster;
+  }
 }
 
 void imprint_launch(pb_context* ctx, const ImprintLaunch& L, size_t smem_bytes) {
   if (L.n_strokes <= 0) return;
-  if (ctx->precision == PB_F64)
-    imprint_kernel<double><<<L.grid, L.block, smem_bytes, ctx->stream>>>(L);
-  else
-    imprint_kernel<float><<<L.grid, L.block, smem_bytes, ctx->stream>>>(L);
-  PB_CUDA(cudaGetLastError());
+  const void* fn = kernel_ptr(ctx->precision, L.cluster > 1, L.block);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim            = dim3(static_cast<unsigned>(L.grid));
+  cfg.blockDim           = dim3(static_cast<unsigned>(L.block));
+  cfg.dynamicSmemBytes   = smem_bytes;
+  cfg.stream             = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id               = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(L.cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs                = attr;
+  cfg.numAttrs             = L.cluster > 1 ? 1 : 0;
+  void* args[]             = {const_cast<ImprintLaunch*>(&L)};
+  PB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   ctx->launches++;
 }
 

@@ -37,6 +37,8 @@ struct ImprintLaunch {
   // canvas
   void* canvas[kLayerPlanes];
   void* snapshot[kLayerPlanes];  // == canvas planes when the snapshot buffer is disabled
+  unsigned char* dirty;          // 1 byte per pixel: snapshot(p) may differ from canvas(p); row pitch dirty_pitch
+  int dirty_pitch;
   int use_snapshot;
   int rows, cols;               // logical canvas size (bounds checks)
   int store_first, store_rows;  // stored row window
@@ -55,14 +57,17 @@ struct ImprintLaunch {
   // per-CTA pick scratch in global memory for footprints that do not fit shared memory
   void* scratch;
   int64_t scratch_stride;  // elements per CTA
-  int smem_cells;          // cells that fit in dynamic shared memory
+  int smem_cells;          // cells per CTA that fit in dynamic shared memory
   int block;               // threads per CTA
-  int grid;
+  int cluster;             // CTAs per stroke (thread-block cluster size)
+  int grid;                // CTAs (multiple of cluster)
 };
 
+// Launch shape for a run of strokes whose largest footprint has max_active cells: a stroke is owned by a
+// thread-block cluster of `cluster` CTAs x `block` threads (~2 active cells per thread).
+void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& smem_bytes);
+int imprint_cluster_class(int n_active);
 void imprint_launch(pb_context* ctx, const ImprintLaunch& L, size_t smem_bytes);
-// grid/block/smem plan for a batch whose largest footprint has max_active cells
-void imprint_plan(pb_context* ctx, int max_active, int& block, int& grid, size_t& smem_bytes, int& smem_cells);
 
 // visited stroke-pixel count (the reference's `counter`, FootprintBrush.hxx:119): one pass over all
 // (2hr+1)(2wr+1) cells of every imprint, both bounds checks evaluated exactly in f64.
