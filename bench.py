@@ -226,6 +226,7 @@ def main():
     # untimed: exact stroke-pixel count of the workload (reference's `counter`)
     br.enable_visited_count(True)
     cv.clear()
+    br.updateSnapshot(cv)
     br.stroke_batch(cv, rec, cx, cy, th)
     ctx.synchronize()
     visited, active = br.counters()
@@ -235,6 +236,7 @@ def main():
 
     def step_device(timers=None):
         cv.clear()
+        br.updateSnapshot(cv)  # FootprintBrush::updateSnapshot(canvas): brush state == a freshly constructed brush
         if timers is not None:
             timers[0].record(stream)
         br.stroke_batch(cv, rec, cx, cy, th)
@@ -284,6 +286,7 @@ def main():
     # e2e: C ABI with host buffers (stroke list H2D, kernels, reflectance D2H as AoS f64)
     def step_e2e():
         cv.clear()
+        br.updateSnapshot(cv)
         br.stroke_batch(cv, rec, cx, cy, th)
         cv.compose(h_R_np)
 

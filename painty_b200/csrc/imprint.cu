@@ -64,7 +64,7 @@ struct Blend6f {
   __device__ __forceinline__ Blend6f(float a, float b) {
     const float vt = a + b;
     on             = vt > static_cast<float>(kMinVolume);
-    const float r  = __frcp_rn(vt);
+    const float r  = __fdividef(1.0f, vt);  // rcp.approx, 1 ulp
     wa             = a * r;
     wb             = b * r;
   }
@@ -89,26 +89,36 @@ struct OpCtx {
   T paintK[3], paintS[3];
 };
 
-// pickupPaint (:349-384) then depositPaint (:393-431) for one (canvas pixel, pickup cell) pair.
+// One (canvas pixel, pickup cell) interaction = pickupPaint (:349-384) then depositPaint (:393-431).
+// Split in two so that a thread can put the loads of all its interactions in flight before it computes any.
 template <typename T>
-__device__ __forceinline__ void pickup_deposit(const OpCtx<T>& C, int64_t ci, T fh, T* pick, int ps, int slot) {
-  using Blend = typename BlendSel<T>::type;
-  // issue every independent load first (the imprint chain is latency bound)
+struct OpData {
+  T cK[3], cS[3], sK[3], sS[3], vSrc, vCan;
+};
+
+template <typename T>
+__device__ __forceinline__ void op_load(const OpCtx<T>& C, int ci, OpData<T>& d) {
   const bool own_src = C.src[PV] == C.can[PV];  // snapshot buffer disabled: pickup source is the canvas itself
-  T cK[3], cS[3], sK[3], sS[3];
-  const T vSrc = __ldcg(C.src[PV] + ci);
+  d.vSrc = __ldcg(C.src[PV] + ci);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    cK[k] = __ldcg(C.can[PK + k] + ci);
-    cS[k] = __ldcg(C.can[PS + k] + ci);
+    d.cK[k] = __ldcg(C.can[PK + k] + ci);
+    d.cS[k] = __ldcg(C.can[PS + k] + ci);
   }
-  T vCan = __ldcg(C.can[PV] + ci);
+  d.vCan = own_src ? d.vSrc : __ldcg(C.can[PV] + ci);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    sK[k] = own_src ? cK[k] : __ldcg(C.src[PK + k] + ci);
-    sS[k] = own_src ? cS[k] : __ldcg(C.src[PS + k] + ci);
+    d.sK[k] = own_src ? d.cK[k] : __ldcg(C.src[PK + k] + ci);
+    d.sS[k] = own_src ? d.cS[k] : __ldcg(C.src[PS + k] + ci);
   }
-  T vP = pick[PV * ps + slot];
+}
+
+template <typename T>
+__device__ __forceinline__ void op_finish(const OpCtx<T>& C, int ci, T fh, const OpData<T>& d, T* pick, int ps, int slot) {
+  using Blend = typename BlendSel<T>::type;
+  const bool own_src = C.src[PV] == C.can[PV];
+  T vCan = d.vCan;
+  T vP   = pick[PV * ps + slot];
   T pK[3], pS[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -116,16 +126,16 @@ __device__ __forceinline__ void pickup_deposit(const OpCtx<T>& C, int64_t ci, T 
     pS[k] = pick[(PS + k) * ps + slot];
   }
   // pickup
-  const T leave = C.pickup_rate * vSrc * fh;
+  const T leave = C.pickup_rate * d.vSrc * fh;
   if (leave > static_cast<T>(kMinVolume)) {
-    const T remain = vSrc - leave;
+    const T remain = d.vSrc - leave;
     __stcg(C.src[PV] + ci, remain);
     if (own_src) vCan = remain;
     const Blend bl(vP, leave);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      pK[k] = bl(pK[k], sK[k]);
-      pS[k] = bl(pS[k], sS[k]);
+      pK[k] = bl(pK[k], d.sK[k]);
+      pS[k] = bl(pS[k], d.sS[k]);
     }
     vP = vP + leave;
 #pragma unroll
@@ -143,10 +153,55 @@ __device__ __forceinline__ void pickup_deposit(const OpCtx<T>& C, int64_t ci, T 
   const Blend b_can(vB, vCan);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    __stcg(C.can[PK + k] + ci, b_can(b_src(pK[k], C.paintK[k]), cK[k]));
-    __stcg(C.can[PS + k] + ci, b_can(b_src(pS[k], C.paintS[k]), cS[k]));
+    __stcg(C.can[PK + k] + ci, b_can(b_src(pK[k], C.paintK[k]), d.cK[k]));
+    __stcg(C.can[PS + k] + ci, b_can(b_src(pS[k], C.paintS[k]), d.cS[k]));
   }
   __stcg(C.can[PV] + ci, vB + vCan);
+}
+
+// The <= 2 canvas pixels whose rotated + rounded position is pickup cell (mx,my), in row-major (row, col) order.
+// Inverse rotation gives the centre (colf,rowf) of the cell's pre-image, a unit square rotated by theta: a lattice
+// point can only map to this cell if its rotated offset from the cell centre is within 0.5 in both axes. A float
+// pre-filter with a 0.01 margin leaves 1-2 of the 2x2 neighbourhood; those are decided by the reference's exact
+// f64 forward expression (:95-100), same operation order, no FMA. Returns the number of hits of phase `ph`.
+struct Hits {
+  int ci[2];   // pixel index in the stored planes (< 2^31, like the reference's int32 K(i))
+  int dof[2];  // byte offset in the dirty map
+  int n;
+};
+__device__ __forceinline__ Hits find_hits(const ImprintLaunch& L, const DevImprint& im, float fc, float fs, int wr, int mx, int my,
+                                          bool border, int ph, int row_lo, int row_hi) {
+  Hits h;
+  h.n = 0;
+  h.ci[0] = h.ci[1] = h.dof[0] = h.dof[1] = 0;
+  const float u = static_cast<float>(mx - wr), v = static_cast<float>(my - wr);
+  const float colf = fmaf(u, fc, v * fs), rowf = fmaf(v, fc, -u * fs);
+  const int c0 = static_cast<int>(floorf(colf)), r0 = static_cast<int>(floorf(rowf));
+#pragma unroll
+  for (int dr = 0; dr < 2; ++dr) {
+#pragma unroll
+    for (int dc = 0; dc < 2; ++dc) {
+      const int row = r0 + dr, col = c0 + dc;
+      const float ec = static_cast<float>(col) - colf, er = static_cast<float>(row) - rowf;
+      const float du = fmaf(ec, fc, -er * fs), dv = fmaf(ec, fs, er * fc);
+      if (fabsf(du) > 0.51f || fabsf(dv) > 0.51f) continue;
+      if (col < -wr || col > wr || row < -wr || row > wr) continue;
+      const double rc = col * im.c - row * im.s;
+      const double rr = col * im.s + row * im.c;
+      if (static_cast<int>(round(rc + wr)) != mx || static_cast<int>(round(rr + wr)) != my) continue;
+      const double fx = col + im.cx, fy = row + im.cy;
+      const int px = static_cast<int>(fx), py = static_cast<int>(fy);  // trunc toward zero (:92-93)
+      if (py < 0 || px < 0 || px >= L.cols || py >= L.rows) continue;
+      if (border && ((fy >= 0.0 ? 2 : 0) + (fx >= 0.0 ? 1 : 0)) != ph) continue;
+      if (py < row_lo || py > row_hi) continue;  // band canvas
+      const int ci = (py - row_lo) * L.cols + px, dof = (py - row_lo) * L.dirty_pitch + px;
+      if (h.n == 0) h.ci[0] = ci, h.dof[0] = dof;
+      if (h.n == 1) h.ci[1] = ci, h.dof[1] = dof;
+      ++h.n;  // a unit cell cannot hold more than 2 lattice points (min distance 1 < diagonal sqrt 2)
+    }
+  }
+  h.n = min(h.n, 2);
+  return h;
 }
 
 // updateSnapshot(canvas, centre) (:278-319): copy canvas -> snapshot on the ring "allowed box minus open
@@ -341,49 +396,45 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
 
       const int n_phase = border ? 4 : 1;
       for (int ph = 0; ph < n_phase; ++ph) {
-        for (int k = 0; k < my_cells; ++k) {
-          const int cell = gt + k * gstride, slot = tid + k * bd;
-          int mx, my;
-          T fh;
-          if (k < kRegCells) {
-            mx = k == 0 ? cmx[0] : cmx[1];
-            my = k == 0 ? cmy[0] : cmy[1];
-            fh = k == 0 ? cfh[0] : cfh[1];
-          } else {
-            const uint32_t xy = st.xy[cell];
-            mx = static_cast<int>(xy & 0xffffu);
-            my = static_cast<int>(xy >> 16);
-            fh = fhs[cell];
+        // CPP cells per pass: all loads of up to 2*CPP interactions are in flight before any is computed
+        constexpr int CPP = MAXB <= 256 ? 2 : 1;
+        for (int k = 0; k < my_cells; k += CPP) {
+          int mx[CPP], my[CPP], slot[CPP];
+          T fh[CPP];
+          bool have[CPP];
+#pragma unroll
+          for (int q = 0; q < CPP; ++q) {
+            have[q] = k + q < my_cells;
+            slot[q] = tid + (k + q) * bd;
+            if (k + q < kRegCells) {
+              mx[q] = cmx[(k + q) & 1], my[q] = cmy[(k + q) & 1], fh[q] = cfh[(k + q) & 1];
+            } else if (have[q]) {
+              const int cell    = gt + (k + q) * gstride;
+              const uint32_t xy = st.xy[cell];
+              mx[q] = static_cast<int>(xy & 0xffffu), my[q] = static_cast<int>(xy >> 16), fh[q] = fhs[cell];
+            } else {
+              mx[q] = my[q] = 0, fh[q] = static_cast<T>(0);
+            }
           }
-          // Inverse rotation gives the centre (colf,rowf) of the cell's pre-image, a unit square rotated by
-          // theta. A lattice point (col,row) can only map to this cell if its rotated offset from the cell
-          // centre is within 0.5 in both axes; the float pre-filter keeps a 0.01 margin and the survivors
-          // (1 or 2 of the 2x2 neighbourhood) are decided by the reference's exact f64 expression.
-          const float u = static_cast<float>(mx - wr), v = static_cast<float>(my - wr);
-          const float colf = fmaf(u, fc, v * fs), rowf = fmaf(v, fc, -u * fs);
-          const int c0 = static_cast<int>(floorf(colf)), r0 = static_cast<int>(floorf(rowf));
+          Hits h[CPP];
+          OpData<T> d[CPP][2];
 #pragma unroll
-          for (int dr = 0; dr < 2; ++dr) {
+          for (int q = 0; q < CPP; ++q) {
+            h[q].n = 0;
+            if (have[q]) h[q] = find_hits(L, im, fc, fs, wr, mx[q], my[q], border, ph, row_lo, row_hi);
 #pragma unroll
-            for (int dc = 0; dc < 2; ++dc) {
-              const int row = r0 + dr, col = c0 + dc;
-              const float ec = static_cast<float>(col) - colf, er = static_cast<float>(row) - rowf;
-              const float du = fmaf(ec, fc, -er * fs), dv = fmaf(ec, fs, er * fc);
-              if (fabsf(du) > 0.51f || fabsf(dv) > 0.51f) continue;
-              if (col < -wr || col > wr || row < -wr || row > wr) continue;
-              // the reference's forward map (:95-100), same expression order, no FMA
-              const double rc = col * im.c - row * im.s;
-              const double rr = col * im.s + row * im.c;
-              if (static_cast<int>(round(rc + wr)) != mx || static_cast<int>(round(rr + wr)) != my) continue;
-              const double fx = col + im.cx, fy = row + im.cy;
-              const int px = static_cast<int>(fx), py = static_cast<int>(fy);  // trunc toward zero (:92-93)
-              if (py < 0 || px < 0 || px >= L.cols || py >= L.rows) continue;
-              if (border && ((fy >= 0.0 ? 2 : 0) + (fx >= 0.0 ? 1 : 0)) != ph) continue;
-              if (py < row_lo || py > row_hi) continue;  // band canvas
-              const int64_t ci = static_cast<int64_t>(py - row_lo) * L.cols + px;
-              pickup_deposit(C, ci, fh, pick, ps, slot);
-              if (L.dirty) __stcg(L.dirty + static_cast<int64_t>(py - row_lo) * L.dirty_pitch + px, static_cast<unsigned char>(1));
-              ++my_active;
+            for (int j = 0; j < 2; ++j)
+              if (j < h[q].n) op_load(C, h[q].ci[j], d[q][j]);
+          }
+#pragma unroll
+          for (int q = 0; q < CPP; ++q) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (j < h[q].n) {
+                op_finish(C, h[q].ci[j], fh[q], d[q][j], pick, ps, slot[q]);
+                if (L.dirty) __stcg(L.dirty + h[q].dof[j], static_cast<unsigned char>(1));
+                ++my_active;
+              }
             }
           }
         }
@@ -467,7 +518,8 @@ int imprint_cluster_class(int n_active) {
 void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& smem_bytes) {
   const int cluster = imprint_cluster_class(max_active);
   int block         = 128;
-  while (block < 1024 && block * cluster < max_active) block *= 2;
+  while (block < 256 && block * cluster < max_active) block *= 2;
+  if (block * cluster * 2 < max_active) block = 512;  // big footprints: more warps per SM, 1 cell per pass
   const size_t es     = ctx->esize();
   const int gstride   = cluster * block;
   const int cta_cells = std::max(1, (max_active + gstride - 1) / gstride) * block;

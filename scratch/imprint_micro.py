@@ -13,7 +13,7 @@ for r in radii:
     br.dip(([.3,.2,.1],[.2,.4,.3]))
     cx = np.linspace(600, 600+n, n); cy = np.linspace(700, 700+0.3*n, n); th = np.full(n, 0.29)
     for rep in range(3):
-        cv.clear(); ctx.synchronize()
+        cv.clear(); br.updateSnapshot(cv); ctx.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream); br.imprint_batch(cv, cx, cy, th); e1.record(stream); ctx.synchronize()
     ms = e0.elapsed_time(e1)

@@ -19,5 +19,5 @@ for r in rows[hi + 1:]:
         pass
 tot_s = sum(v[0] for v in lines.values()); tot_i = sum(v[1] for v in lines.values())
 print("total samples", tot_s, "total warp-instructions", tot_i)
-for (ln, src), (s, i) in sorted(lines.items(), key=lambda kv: -kv[1][0])[:top]:
+for (ln, src), (s, i) in sorted(lines.items(), key=lambda kv: -kv[1][int(sys.argv[3]) if len(sys.argv) > 3 else 0])[:top]:
     print(f"{100*s/max(tot_s,1):5.1f}% smp {100*i/max(tot_i,1):5.1f}% ins  L{ln:>4} {src.strip()[:130]}")
