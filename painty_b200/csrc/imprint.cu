@@ -32,6 +32,8 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <map>
+#include <tuple>
 
 #include "imprint.cuh"
 
@@ -288,8 +290,8 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
   const int tid = threadIdx.x, bd = blockDim.x;
   const int crank   = CL ? static_cast<int>(cluster.block_rank()) : 0;
   const int csize   = CL ? static_cast<int>(cluster.num_blocks()) : 1;
-  const int gt      = crank * bd + tid;
   const int gstride = csize * bd;
+  const int sgt     = crank * bd + tid;  // contiguous numbering for the coalesced dirty-map scan
   auto sync_all = [&]() {
     if (CL)
       cluster.sync();
@@ -336,9 +338,13 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
     const int nA = st.n_active;
     const int wr = (st.side - 1) / 2;  // == hr (square footprint), FootprintBrush.hxx:75-78
     const T* fhs = static_cast<const T*>(st.fh);
-    // this CTA's slice of the pickup map: cell = gt + k*gstride lives in slot tid + k*bd
-    const int my_cells  = nA > gt ? (nA - gt + gstride - 1) / gstride : 0;
-    const int cta_cells = ((nA + gstride - 1) / gstride) * bd;
+    // The compacted cell list is cut into csize contiguous chunks (neighbouring cells -> neighbouring lanes ->
+    // neighbouring canvas pixels); cell = cell0 + k*bd of this thread lives in shared-memory slot tid + k*bd.
+    const int per_cta   = (nA + csize - 1) / csize;
+    const int cell_end  = min(nA, (crank + 1) * per_cta);
+    const int cell0     = crank * per_cta + tid;
+    const int my_cells  = cell_end > cell0 ? (cell_end - cell0 + bd - 1) / bd : 0;
+    const int cta_cells = ((per_cta + bd - 1) / bd) * bd;
     const bool in_smem  = cta_cells <= L.smem_cells;
     T* pick      = in_smem ? reinterpret_cast<T*>(smem_raw) : static_cast<T*>(L.scratch) + blockIdx.x * L.scratch_stride;
     const int ps = in_smem ? L.smem_cells : static_cast<int>(L.scratch_stride / kLayerPlanes);
@@ -352,7 +358,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
       cfh[k]          = static_cast<T>(0);
     }
     for (int k = 0; k < my_cells; ++k) {
-      const int cell = gt + k * gstride, slot = tid + k * bd;
+      const int cell = cell0 + k * bd, slot = tid + k * bd;
       const uint32_t xy = st.xy[cell];
       if (k < kRegCells) {
 #pragma unroll
@@ -387,7 +393,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
         g.ay0 = max(max(static_cast<int>(im.cy - wr - st.radius), 0), row_lo);
         g.ax1 = min(static_cast<int>(im.cx + wr + st.radius), L.cols - 1);
         g.ay1 = min(min(static_cast<int>(im.cy + wr + st.radius), L.rows - 1), row_hi);
-        ring_scan(L, C, g, gt, gstride);
+        ring_scan(L, C, g, sgt, gstride);
       }
       // left/top overhang: canvas pixels of column/row 0 can be hit twice (B#11) -> ordered phases
       const bool border = (im.cx - wr < 0.0) || (im.cy - wr < 0.0);
@@ -409,7 +415,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
             if (k + q < kRegCells) {
               mx[q] = cmx[(k + q) & 1], my[q] = cmy[(k + q) & 1], fh[q] = cfh[(k + q) & 1];
             } else if (have[q]) {
-              const int cell    = gt + (k + q) * gstride;
+              const int cell    = cell0 + (k + q) * bd;
               const uint32_t xy = st.xy[cell];
               mx[q] = static_cast<int>(xy & 0xffffu), my[q] = static_cast<int>(xy >> 16), fh[q] = fhs[cell];
             } else {
@@ -444,7 +450,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
 
     if (st.flags & 2) {
       for (int k = 0; k < my_cells; ++k) {
-        const int cell = gt + k * gstride, slot = tid + k * bd;
+        const int cell = cell0 + k * bd, slot = tid + k * bd;
         const uint32_t xy = st.xy[cell];
         const int64_t mi  = static_cast<int64_t>(xy >> 16) * st.size_map + (xy & 0xffffu);
 #pragma unroll
@@ -509,20 +515,26 @@ const void* kernel_ptr(int precision, bool cl, int block) {
 
 // A stroke is latency bound (a chain of dependent imprints), so it is spread thin: CTAs of 128..1024 threads on
 // up to 16 SMs (non-portable cluster size), about one active cell per thread.
-int imprint_cluster_class(int n_active) {
-  int c = 1;
-  while (c < 16 && n_active > c * 160) c *= 2;
-  return c;
-}
+// Launch classes (a run of consecutive strokes of one class shares a launch):
+//   1  : tiny footprints (<= 256 active cells), one CTA per stroke
+//   16 : cluster of 16 CTAs x 128 threads (<= 4096 cells, <= 2 per thread)
+//   17 : cluster of 16 CTAs x 256 or 512 threads for the large footprints
+int imprint_cluster_class(int n_active) { return n_active <= 256 ? 1 : (n_active <= 4096 ? 16 : 17); }
 
 void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& smem_bytes) {
-  const int cluster = imprint_cluster_class(max_active);
-  int block         = 128;
-  while (block < 256 && block * cluster < max_active) block *= 2;
-  if (block * cluster * 2 < max_active) block = 512;  // big footprints: more warps per SM, 1 cell per pass
+  const int cluster = imprint_cluster_class(max_active) == 1 ? 1 : 16;
+  // <= 256 threads per CTA: that kernel variant keeps two cells' interactions (56 loads) in flight without
+  // spills; the largest footprints (> 2 cells per thread at 256) trade that for twice the warps per SM.
+  int block = 128;
+  if (cluster == 1) {
+    block = max_active <= 128 ? 128 : 256;
+  } else {
+    block = max_active <= 4096 ? 128 : (max_active <= 8192 ? 256 : 512);
+  }
   const size_t es     = ctx->esize();
   const int gstride   = cluster * block;
-  const int cta_cells = std::max(1, (max_active + gstride - 1) / gstride) * block;
+  const int per_cta   = (std::max(max_active, 1) + cluster - 1) / cluster;
+  const int cta_cells = (per_cta + block - 1) / block * block;
   const size_t budget = 200 * 1024;  // dynamic shared memory for this CTA's slice of the pickup map
   size_t need         = static_cast<size_t>(cta_cells) * kLayerPlanes * es;
   if (need <= budget) {
@@ -536,8 +548,16 @@ void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& sme
   smem_bytes = need;
   L.block    = block;
   L.cluster  = cluster;
+  // occupancy queries and attribute changes cost milliseconds: do them once per launch shape
+  static std::map<std::tuple<int, int, int, int, size_t>, int> cache;
+  const auto key = std::make_tuple(ctx->device, ctx->precision, cluster, block, smem_bytes);
+  auto it        = cache.find(key);
+  if (it != cache.end()) {
+    L.grid = it->second;
+    return;
+  }
   const void* fn = kernel_ptr(ctx->precision, cluster > 1, block);
-  PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+  PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (cluster > 8) PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   if (cluster == 1) {
     int per_sm = 0;
@@ -561,6 +581,7 @@ void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& sme
     PB_REQUIRE(n_clusters >= 1, "imprint kernel: no cluster of the requested size fits on the device");
     L.grid = n_clusters * cluster;
   }
+  cache[key] = L.grid;
 }
 
 void imprint_launch(pb_context* ctx, const ImprintLaunch& L, size_t smem_bytes) {
