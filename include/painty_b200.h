@@ -69,6 +69,8 @@ int pb_expand_stroke(int mode, int n, const double* path_xy, int64_t capacity, d
 /* ---- PaintLayer ------------------------------------------------------------------------------ */
 int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out);
 int pb_layer_destroy(pb_layer* l);
+int pb_layer_rows(const pb_layer* l);
+int pb_layer_cols(const pb_layer* l);
 int pb_layer_clear(pb_layer* l);                                                    /* PaintLayer.hxx:68-74 */
 int pb_layer_upload(pb_layer* l, const double* K, const double* S, const double* V); /* host AoS f64 -> SoA */
 int pb_layer_download(pb_layer* l, double* K, double* S, double* V);                 /* any may be NULL */
@@ -102,6 +104,11 @@ int pb_canvas_compose_band_device(pb_canvas* c, void* d_out, int64_t plane_strid
 /* Device plane pointers (element type of the context): 0-2 K, 3-5 S, 6 V, 7-9 R0, 10 h. */
 int pb_canvas_device_planes(pb_canvas* c, void* planes[11], int64_t* elems_per_plane);
 int pb_canvas_stored_rows(const pb_canvas* c, int* first_row, int* n_rows);
+/* Canvas::getPaintLayer(): a non-owning pb_layer aliasing the canvas' wet planes (destroy with pb_layer_destroy;
+ * it must not outlive the canvas). */
+int pb_canvas_paint_layer(pb_canvas* c, pb_layer** out);
+/* Write R0 (getR0()) and/or h (get_h()) from host AoS f64; either may be NULL. Does not clear the wet layer. */
+int pb_canvas_upload_substrate(pb_canvas* c, const double* R0, const double* h);
 
 /* ---- raw streaming compose on caller-owned device SoA planes (roofline bench, stacked layers) --- */
 /* R = KM(K,S,V over R0) for n pixels; pointers are device pointers of the context's element type.
@@ -132,6 +139,8 @@ int pb_fbrush_get_use_snapshot(const pb_fbrush* b);
 int pb_fbrush_size_map(const pb_fbrush* b);
 /* getPickupMap (:174) as host AoS f64 (size_map^2 pixels). */
 int pb_fbrush_pickup_map(pb_fbrush* b, double* K, double* S, double* V);
+/* Same as a non-owning pb_layer view (valid until the next setRadius that acts). */
+int pb_fbrush_pickup_layer(pb_fbrush* b, pb_layer** out);
 /* public updateSnapshot(canvas) (:168-172): full copy canvas wet layer -> snapshot. */
 int pb_fbrush_update_snapshot(pb_fbrush* b, pb_canvas* c);
 int pb_fbrush_snapshot_download(pb_fbrush* b, double* K, double* S, double* V);

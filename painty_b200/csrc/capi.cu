@@ -440,21 +440,27 @@ int pb_layer_destroy(pb_layer* l) {
   PB_API_BEGIN
   if (l) {
     DeviceGuard g(l->pl.ctx);
-    PB_CUDA(cudaStreamSynchronize(l->pl.ctx->stream));
-    planes_free(l->pl);
+    if (l->owns) {
+      PB_CUDA(cudaStreamSynchronize(l->pl.ctx->stream));
+      planes_free(l->pl);
+    }
     delete l;
   }
   PB_API_END
 }
+int pb_layer_rows(const pb_layer* l) { return l->pl.rows; }
+int pb_layer_cols(const pb_layer* l) { return l->pl.cols; }
 int pb_layer_clear(pb_layer* l) {
   PB_API_BEGIN
   DeviceGuard g(l->pl.ctx);
+  if (l->canvas) l->canvas->version++;
   for (int p = 0; p < kLayerPlanes; ++p) fill_plane(l->pl.ctx, l->pl.plane(p), l->pl.n(), 0.0);
   PB_API_END
 }
 int pb_layer_upload(pb_layer* l, const double* K, const double* S, const double* V) {
   PB_API_BEGIN
   DeviceGuard g(l->pl.ctx);
+  if (l->canvas) l->canvas->version++;
   if (K) upload_aos(l->pl.ctx, l->pl, PK, 3, K);
   if (S) upload_aos(l->pl.ctx, l->pl, PS, 3, S);
   if (V) upload_aos(l->pl.ctx, l->pl, PV, 1, V);
@@ -471,7 +477,9 @@ int pb_layer_download(pb_layer* l, double* K, double* S, double* V) {
 int pb_layer_copy(const pb_layer* src, pb_layer* dst) {
   PB_API_BEGIN
   DeviceGuard g(src->pl.ctx);
+  if (dst->canvas) dst->canvas->version++;
   if (dst->pl.rows != src->pl.rows || dst->pl.cols != src->pl.cols) {  // PaintLayer.hxx:104-107
+    PB_REQUIRE(dst->owns, "copyTo: cannot resize a layer view");
     PB_CUDA(cudaStreamSynchronize(dst->pl.ctx->stream));
     planes_free(dst->pl);
     planes_alloc(src->pl.ctx, dst->pl, src->pl.rows, src->pl.cols, kLayerPlanes);
@@ -621,6 +629,23 @@ int pb_canvas_compose(pb_canvas* c, double* out) {
   planes_free(r);
   PB_API_END
 }
+int pb_canvas_paint_layer(pb_canvas* c, pb_layer** out) {
+  PB_API_BEGIN
+  auto l        = std::make_unique<pb_layer>();
+  l->pl         = c->pl;
+  l->pl.nplanes = kLayerPlanes;
+  l->owns       = false;
+  l->canvas     = c;
+  *out          = l.release();
+  PB_API_END
+}
+int pb_canvas_upload_substrate(pb_canvas* c, const double* R0, const double* h) {
+  PB_API_BEGIN
+  DeviceGuard g(c->pl.ctx);
+  if (R0) upload_aos(c->pl.ctx, c->pl, PR, 3, R0);
+  if (h) upload_aos(c->pl.ctx, c->pl, PH, 1, h);
+  PB_API_END
+}
 int pb_canvas_device_planes(pb_canvas* c, void* planes[11], int64_t* elems_per_plane) {
   for (int p = 0; p < kCanvasPlanes; ++p) planes[p] = c->pl.plane(p);
   if (elems_per_plane) *elems_per_plane = c->pl.n();
@@ -753,6 +778,15 @@ int pb_fbrush_pickup_map(pb_fbrush* b, double* K, double* S, double* V) {
   if (K) download_aos(b->ctx, b->pick, PK, 3, K);
   if (S) download_aos(b->ctx, b->pick, PS, 3, S);
   if (V) download_aos(b->ctx, b->pick, PV, 1, V);
+  PB_API_END
+}
+int pb_fbrush_pickup_layer(pb_fbrush* b, pb_layer** out) {
+  PB_API_BEGIN
+  PB_REQUIRE(b->pick.base != nullptr, "brush has no pickup map yet (setRadius was never applied)");
+  auto l  = std::make_unique<pb_layer>();
+  l->pl   = b->pick;
+  l->owns = false;
+  *out    = l.release();
   PB_API_END
 }
 int pb_fbrush_update_snapshot(pb_fbrush* b, pb_canvas* c) {

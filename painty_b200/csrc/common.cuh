@@ -51,6 +51,7 @@ struct pb_context {
   size_t esize() const { return precision == PB_F64 ? 8 : 4; }
 };
 
+struct pb_canvas;
 // 7 (layer) or 11 (canvas) dense planes carved out of one allocation; plane p at base + p*stride bytes.
 struct pb_planes {
   pb_context* ctx = nullptr;
@@ -64,6 +65,8 @@ struct pb_planes {
 
 struct pb_layer {
   pb_planes pl;
+  bool owns         = true;     // false: a view of a canvas' wet planes or of a brush's pickup map
+  pb_canvas* canvas = nullptr;  // set for canvas views (writes bump the canvas version)
 };
 
 struct pb_canvas {
