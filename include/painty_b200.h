@@ -165,6 +165,38 @@ int pb_fbrush_stroke_batch(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const 
 int pb_fbrush_enable_visited_count(pb_fbrush* b, int enable);
 int pb_fbrush_counters(pb_fbrush* b, uint64_t* visited, uint64_t* active);
 
+/* ---- multi-GPU: one canvas cut into row bands over the GPUs of an NVSwitch node -------------------- */
+/* Rank r (one process per GPU) owns rows [r*rows_per_band, min((r+1)*rows_per_band, rows)) as a band canvas
+ * (pb_canvas_create_band(..., halo 0)). Compose / dry / texture strokes need no exchange. Footprint strokes are
+ * executed entirely by the rank whose band holds their first imprint; where their footprint or snapshot ring
+ * leaves the band, the kernel reads and writes the neighbour's HBM directly through NVLink peer mappings, and
+ * strokes wait on completion flags of conflicting earlier strokes on any GPU (system-scope acquire/release).
+ * The host exchanges the CUDA IPC handles (e.g. torch.distributed.all_gather_object) and fills pb_dist_desc. */
+#define PB_IPC_HANDLE_BYTES 64
+#define PB_MAX_BANDS 8
+typedef struct pb_dist_desc {
+  int32_t world, rank, rows_per_band, reserved;
+  void* canvas_base[PB_MAX_BANDS]; /* [rank] = own allocation, others = pb_ipc_import'ed */
+  int64_t canvas_stride[PB_MAX_BANDS];   /* bytes between planes */
+  void* snapshot_base[PB_MAX_BANDS];
+  int64_t snapshot_stride[PB_MAX_BANDS];
+  void* dirty_base[PB_MAX_BANDS];
+  void* flags_base[PB_MAX_BANDS];
+} pb_dist_desc;
+int pb_ipc_export(pb_context* ctx, void* dev_ptr, unsigned char handle[PB_IPC_HANDLE_BYTES]);
+int pb_ipc_import(pb_context* ctx, const unsigned char handle[PB_IPC_HANDLE_BYTES], void** dev_ptr);
+int pb_ipc_close(pb_context* ctx, void* dev_ptr);
+int pb_canvas_storage(pb_canvas* c, void** base, int64_t* plane_stride_bytes);
+/* Makes sure the brush's snapshot buffer (full copy of the band, FootprintBrush.hxx:281-284), dirty map and flag
+ * buffer exist for this canvas and returns their base pointers for export. */
+int pb_fbrush_dist_storage(pb_fbrush* b, pb_canvas* c, void** snapshot_base, int64_t* snapshot_stride_bytes, void** dirty_base,
+                           void** flags_base);
+/* Same contract as pb_fbrush_stroke_batch; every rank passes the SAME global stroke list. The caller must place a
+ * process-group barrier before (all ranks have finished preparing their bands) and after (all ranks' kernels have
+ * completed) this call. */
+int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* dist, int64_t n_strokes, const pb_stroke* strokes,
+                                int64_t n_imprints, const double* cx, const double* cy, const double* theta);
+
 /* ---- TextureBrush (smudge off; Smudge is SURVEY.md §8f) ---------------------------------------- */
 /* thickness map: rows*cols host f64 (BrushStrokeSample::getThicknessMap). */
 int pb_tbrush_create(pb_context* ctx, int map_rows, int map_cols, const double* thickness_map, pb_tbrush** out);

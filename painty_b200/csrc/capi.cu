@@ -104,6 +104,10 @@ struct pb_fbrush {
   unsigned char* dirty = nullptr;
   int dirty_pitch      = 0;
   uint64_t snap_canvas_id = 0, snap_canvas_version = 0;  // canvas state the dirty map is valid for
+  // multi-GPU: completion flags other GPUs poll (kDistFlagCapacity ints + 1024 queue counters), batch epoch
+  int* dist_flags       = nullptr;
+  int dist_epoch        = 0;
+  int dist_queue_slot   = 0;
   bool use_snapshot = true;
   double pickup_rate = 0.9, deposition_rate = 0.05, capacity = 1.0;  // :477-495
   double paintK[3] = {0, 0, 0}, paintS[3] = {0, 0, 0};                // zero-initialised
@@ -209,42 +213,112 @@ struct HostStroke {
   int flags;
 };
 
-// Uploads the plan and launches the persistent imprint kernel: one launch per run of consecutive strokes
-// that share a cluster class (CTAs per stroke); runs are ordered by the stream.
+// Multi-GPU view of one logical canvas: band b (rows [b*rows_per_band, ...)) lives on GPU b; the base pointers of
+// the other ranks' allocations are CUDA-IPC peer mappings.
+struct DistInfo {
+  int world = 1, rank = 0, rows_per_band = 0;
+  void* canvas_base[kMaxBands]   = {};
+  int64_t canvas_stride[kMaxBands] = {};
+  void* snapshot_base[kMaxBands] = {};
+  int64_t snapshot_stride[kMaxBands] = {};
+  unsigned char* dirty_base[kMaxBands] = {};
+  int* flags_base[kMaxBands] = {};
+};
+constexpr int64_t kDistFlagCapacity = int64_t(1) << 22;
+
+Region stroke_region(const HostStroke& h, const double* cx, const double* cy, int rows, int cols) {
+  // everything the stroke reads or writes: union of the snapshot "allowed" boxes (:298-305)
+  Region r{1, 1, 0, 0};
+  if (h.n <= 0) return r;
+  double lx = cx[h.first], hx = lx, ly = cy[h.first], hy = ly;
+  for (int64_t i = h.first; i < h.first + h.n; ++i) {
+    lx = std::min(lx, cx[i]);
+    hx = std::max(hx, cx[i]);
+    ly = std::min(ly, cy[i]);
+    hy = std::max(hy, cy[i]);
+  }
+  const double m = (h.g->side - 1) / 2 + h.radius + 2.0;
+  r.x0 = static_cast<int>(std::max(0.0, std::floor(lx - m)));
+  r.y0 = static_cast<int>(std::max(0.0, std::floor(ly - m)));
+  r.x1 = static_cast<int>(std::min<double>(cols - 1, std::ceil(hx + m)));
+  r.y1 = static_cast<int>(std::min<double>(rows - 1, std::ceil(hy + m)));
+  return r;
+}
+
+// Plans and launches the persistent imprint kernel for a submission-ordered stroke list: one launch per run of
+// consecutive (local) strokes that share a launch class; dependencies are tracked across runs and — with `dist` —
+// across GPUs (every rank plans the same global list and executes the strokes whose first imprint lies in its band).
 void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs, int64_t n_imprints, const double* cx,
-                  const double* cy, const double* theta) {
+                  const double* cy, const double* theta, const DistInfo* dist = nullptr) {
   pb_context* ctx = b->ctx;
   PB_REQUIRE(c->pl.ctx == ctx, "canvas and brush belong to different contexts");
   if (hs.empty()) return;
+  const bool multi = dist != nullptr && dist->world > 1;
   if (b->use_snapshot || b->snapshot.base != nullptr) {
     if (b->use_snapshot || (b->snapshot.rows == c->pl.rows && b->snapshot.cols == c->pl.cols)) ensure_snapshot(b, c);
   }
   const bool have_dirty = b->dirty != nullptr && b->snapshot.rows == c->pl.rows && b->snapshot.cols == c->pl.cols;
+  PB_REQUIRE(!multi || (have_dirty && b->use_snapshot), "distributed strokes need the snapshot buffer enabled");
+
+  // global plan: executor rank, predecessors (global indices), local numbering
+  const size_t n = hs.size();
+  std::vector<int32_t> executor(n, 0), local_index(n, -1), pred_begin(n), pred_end(n), preds;
+  std::vector<int32_t> counts(kMaxBands, 0);
+  std::vector<char> remote(n, 0);
+  DataflowPlanner planner(c->rows, c->cols);
+  for (size_t s = 0; s < n; ++s) {
+    const HostStroke& h = hs[s];
+    const Region r      = stroke_region(h, cx, cy, c->rows, c->cols);
+    planner.add(static_cast<int32_t>(s), r, preds, pred_begin[s], pred_end[s]);
+    if (multi && h.n > 0) {
+      const int y0 = std::min(std::max(static_cast<int>(cy[h.first]), 0), c->rows - 1);
+      executor[s]  = std::min(y0 / dist->rows_per_band, dist->world - 1);
+      const int b0 = executor[s] * dist->rows_per_band, b1 = std::min(b0 + dist->rows_per_band, c->rows) - 1;
+      remote[s]    = (r.y1 >= r.y0) && (r.y0 < b0 || r.y1 > b1);
+    }
+    local_index[s] = counts[executor[s]]++;
+  }
+  std::vector<size_t> mine;
+  for (size_t s = 0; s < n; ++s)
+    if (executor[s] == (multi ? dist->rank : 0)) mine.push_back(s);
+  PB_REQUIRE(static_cast<int64_t>(mine.size()) <= kDistFlagCapacity, "too many strokes in one batch");
 
   std::vector<DevImprint> im(static_cast<size_t>(n_imprints));
-  for (int64_t i = 0; i < n_imprints; ++i) {
-    im[i].cx = cx[i];
-    im[i].cy = cy[i];
-    im[i].c  = std::cos(-theta[i]);  // FootprintBrush.hxx:95-96, per-imprint constants
-    im[i].s  = std::sin(-theta[i]);
+  for (size_t k = 0; k < mine.size(); ++k) {  // only the imprints this rank executes
+    const HostStroke& h = hs[mine[k]];
+    for (int64_t i = h.first; i < h.first + h.n; ++i) {
+      im[i].cx = cx[i];
+      im[i].cy = cy[i];
+      im[i].c  = std::cos(-theta[i]);  // FootprintBrush.hxx:95-96, per-imprint constants
+      im[i].s  = std::sin(-theta[i]);
+    }
   }
   DevBuf<DevImprint> d_im(ctx, im.size());
   d_im.upload(im.data(), im.size());
 
+  // completion flags: a per-batch buffer on one GPU, the brush's exported buffer + a fresh epoch across GPUs
+  DevBuf<int> d_flags(ctx, multi ? 0 : mine.size() + 1);
+  int epoch = 1;
+  if (multi) {
+    epoch = ++b->dist_epoch;
+  } else {
+    d_flags.zero(mine.size() + 1);
+  }
+
   size_t run_begin = 0;
-  while (run_begin < hs.size()) {
-    const int cls  = imprint_cluster_class(hs[run_begin].g->n_active);
+  while (run_begin < mine.size()) {
+    const int cls  = imprint_cluster_class(hs[mine[run_begin]].g->n_active);
     size_t run_end = run_begin + 1;
-    while (run_end < hs.size() && imprint_cluster_class(hs[run_end].g->n_active) == cls) ++run_end;
+    while (run_end < mine.size() && imprint_cluster_class(hs[mine[run_end]].g->n_active) == cls) ++run_end;
     const size_t n_run = run_end - run_begin;
 
     std::vector<DevStroke> ds(n_run);
-    std::vector<int32_t> preds;
-    DataflowPlanner planner(c->rows, c->cols);
+    std::vector<int32_t> run_preds;
     int max_active = 1;
-    for (size_t s = 0; s < n_run; ++s) {
-      const HostStroke& h = hs[run_begin + s];
-      DevStroke& d        = ds[s];
+    for (size_t k = 0; k < n_run; ++k) {
+      const size_t s      = mine[run_begin + k];
+      const HostStroke& h = hs[s];
+      DevStroke& d        = ds[k];
       d.first_imprint     = h.first;
       d.n_imprints        = static_cast<int32_t>(h.n);
       d.n_active          = h.g->n_active;
@@ -253,42 +327,54 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
       d.size_map          = h.g->size_map;
       d.side              = h.g->side;
       d.radius            = h.radius;
-      for (int k = 0; k < 3; ++k) {
-        d.paintK[k] = h.K[k];
-        d.paintS[k] = h.S[k];
+      for (int q = 0; q < 3; ++q) {
+        d.paintK[q] = h.K[q];
+        d.paintS[q] = h.S[q];
       }
-      d.flags    = h.flags;
+      d.flags    = h.flags | (remote[s] ? 4 : 0);
       d.pad      = 0;
       max_active = std::max(max_active, d.n_active);
-      // region the stroke reads or writes: union of the snapshot "allowed" boxes (:298-305)
-      Region r{1, 1, 0, 0};
-      if (h.n > 0) {
-        double lx = cx[h.first], hx = lx, ly = cy[h.first], hy = ly;
-        for (int64_t i = h.first; i < h.first + h.n; ++i) {
-          lx = std::min(lx, cx[i]);
-          hx = std::max(hx, cx[i]);
-          ly = std::min(ly, cy[i]);
-          hy = std::max(hy, cy[i]);
-        }
-        const double m = (h.g->side - 1) / 2 + h.radius + 2.0;
-        r.x0 = static_cast<int>(std::max(0.0, std::floor(lx - m)));
-        r.y0 = static_cast<int>(std::max(0.0, std::floor(ly - m)));
-        r.x1 = static_cast<int>(std::min<double>(c->cols - 1, std::ceil(hx + m)));
-        r.y1 = static_cast<int>(std::min<double>(c->rows - 1, std::ceil(hy + m)));
+      d.pred_begin = static_cast<int32_t>(run_preds.size());
+      for (int32_t p = pred_begin[s]; p < pred_end[s]; ++p) {
+        const int32_t g = preds[p];
+        run_preds.push_back(multi ? ((executor[g] << 27) | local_index[g]) : local_index[g]);
       }
-      planner.add(static_cast<int32_t>(s), r, preds, d.pred_begin, d.pred_end);
+      d.pred_end = static_cast<int32_t>(run_preds.size());
     }
 
     ImprintLaunch L{};
+    L.n_bands = multi ? dist->world : 1;
     size_t smem = 0;
     imprint_plan(ctx, max_active, L, smem);
     L.grid = static_cast<int>(std::min<int64_t>(L.grid, static_cast<int64_t>(n_run) * L.cluster));
-    for (int p = 0; p < kLayerPlanes; ++p) {
-      L.canvas[p]     = c->pl.plane(p);
-      L.snapshot[p]   = b->use_snapshot ? b->snapshot.plane(p) : c->pl.plane(p);
-      L.pick_dense[p] = b->pick.base ? b->pick.plane(p) : nullptr;
+    if (multi) {
+      for (int r = 0; r < dist->world; ++r) {
+        for (int p = 0; p < kLayerPlanes; ++p) {
+          L.canvas[r][p]   = static_cast<char*>(dist->canvas_base[r]) + static_cast<size_t>(p) * dist->canvas_stride[r];
+          L.snapshot[r][p] = static_cast<char*>(dist->snapshot_base[r]) + static_cast<size_t>(p) * dist->snapshot_stride[r];
+        }
+        L.dirty[r] = dist->dirty_base[r];
+        L.done[r]  = dist->flags_base[r];
+      }
+      L.rows_per_band = dist->rows_per_band;
+      L.my_band       = dist->rank;
+      L.queue         = b->dist_flags + kDistFlagCapacity + (b->dist_queue_slot++ % 1024);
+      PB_CUDA(cudaMemsetAsync(L.queue, 0, sizeof(int), ctx->stream));
+    } else {
+      for (int p = 0; p < kLayerPlanes; ++p) {
+        L.canvas[0][p]   = c->pl.plane(p);
+        L.snapshot[0][p] = b->use_snapshot ? b->snapshot.plane(p) : c->pl.plane(p);
+      }
+      L.dirty[0]      = have_dirty ? b->dirty : nullptr;
+      L.done[0]       = d_flags.p;
+      L.rows_per_band = std::max(c->pl.rows, 1);
+      L.my_band       = 0;
+      L.queue         = d_flags.p + mine.size();
+      if (run_begin > 0) PB_CUDA(cudaMemsetAsync(L.queue, 0, sizeof(int), ctx->stream));
     }
-    L.dirty           = have_dirty ? b->dirty : nullptr;
+    for (int p = 0; p < kLayerPlanes; ++p) L.pick_dense[p] = b->pick.base ? b->pick.plane(p) : nullptr;
+    L.epoch           = epoch;
+    L.flag_offset     = static_cast<int>(run_begin);
     L.dirty_pitch     = b->dirty_pitch;
     L.use_snapshot    = b->use_snapshot ? 1 : 0;
     L.rows            = c->rows;
@@ -301,18 +387,14 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     L.n_strokes       = static_cast<int64_t>(n_run);
 
     DevBuf<DevStroke> d_strokes(ctx, ds.size());
-    DevBuf<int32_t> d_preds(ctx, preds.size());
-    DevBuf<int> d_flags(ctx, ds.size() + 1);
+    DevBuf<int32_t> d_preds(ctx, run_preds.size());
     d_strokes.upload(ds.data(), ds.size());
-    d_preds.upload(preds.data(), preds.size());
-    d_flags.zero(ds.size() + 1);
+    d_preds.upload(run_preds.data(), run_preds.size());
     DevBuf<char> d_scratch(ctx, static_cast<size_t>(L.scratch_stride) * L.grid * ctx->esize());
     L.scratch  = d_scratch.p;
     L.strokes  = d_strokes.p;
     L.imprints = d_im.p;
     L.preds    = d_preds.p;
-    L.done     = d_flags.p;
-    L.queue    = d_flags.p + ds.size();
     L.counters = b->d_counters;
     imprint_launch(ctx, L, smem);
     if (b->count_visited) imprint_count_visited(ctx, d_strokes.p, L.n_strokes, d_im.p, c->rows, c->cols, b->d_counters + 1);
@@ -719,6 +801,7 @@ int pb_fbrush_destroy(pb_fbrush* b) {
     planes_free(b->pick);
     planes_free(b->snapshot);
     if (b->dirty) cudaFree(b->dirty);
+    if (b->dist_flags) cudaFree(b->dist_flags);
     cudaFree(b->d_counters);
     delete b;
   }
@@ -833,12 +916,11 @@ int pb_fbrush_imprint_batch(pb_fbrush* b, pb_canvas* c, int64_t n, const double*
   run_imprints(b, c, {h}, n, cx, cy, theta);
   PB_API_END
 }
-int pb_fbrush_stroke_batch(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_stroke* strokes, int64_t n_imprints,
-                           const double* cx, const double* cy, const double* theta) {
-  PB_API_BEGIN
-  DeviceGuard g(b->ctx);
-  if (n_strokes <= 0) return 0;
-  PB_REQUIRE(n_strokes < (int64_t(1) << 31), "too many strokes in one batch");
+namespace {
+void stroke_batch_impl(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_stroke* strokes, int64_t n_imprints,
+                       const double* cx, const double* cy, const double* theta, const DistInfo* dist) {
+  if (n_strokes <= 0) return;
+  PB_REQUIRE(n_strokes < (int64_t(1) << 27), "too many strokes in one batch");
   std::vector<HostStroke> hs(static_cast<size_t>(n_strokes));
   double radius            = b->radius;
   const FootprintGeom* cur = b->cur;
@@ -874,7 +956,85 @@ int pb_fbrush_stroke_batch(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const 
     b->paintS[i] = strokes[n_strokes - 1].S[i];
   }
   hs.back().flags = 2;
-  run_imprints(b, c, hs, n_imprints, cx, cy, theta);
+  run_imprints(b, c, hs, n_imprints, cx, cy, theta, dist);
+}
+}  // namespace
+
+int pb_fbrush_stroke_batch(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_stroke* strokes, int64_t n_imprints,
+                           const double* cx, const double* cy, const double* theta) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  stroke_batch_impl(b, c, n_strokes, strokes, n_imprints, cx, cy, theta, nullptr);
+  PB_API_END
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------------
+int pb_ipc_export(pb_context* ctx, void* dev_ptr, unsigned char handle[PB_IPC_HANDLE_BYTES]) {
+  PB_API_BEGIN
+  DeviceGuard g(ctx);
+  static_assert(sizeof(cudaIpcMemHandle_t) == PB_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  PB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+  std::memcpy(handle, &h, sizeof(h));
+  PB_API_END
+}
+int pb_ipc_import(pb_context* ctx, const unsigned char handle[PB_IPC_HANDLE_BYTES], void** dev_ptr) {
+  PB_API_BEGIN
+  DeviceGuard g(ctx);
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  PB_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  PB_API_END
+}
+int pb_ipc_close(pb_context* ctx, void* dev_ptr) {
+  PB_API_BEGIN
+  DeviceGuard g(ctx);
+  PB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  PB_API_END
+}
+int pb_canvas_storage(pb_canvas* c, void** base, int64_t* plane_stride_bytes) {
+  if (base) *base = c->pl.base;
+  if (plane_stride_bytes) *plane_stride_bytes = static_cast<int64_t>(c->pl.stride);
+  return 0;
+}
+int pb_fbrush_dist_storage(pb_fbrush* b, pb_canvas* c, void** snapshot_base, int64_t* snapshot_stride_bytes, void** dirty_base,
+                           void** flags_base) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  ensure_snapshot(b, c);
+  if (b->dist_flags == nullptr) {
+    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->dist_flags), sizeof(int) * (kDistFlagCapacity + 1024)));
+    PB_CUDA(cudaMemsetAsync(b->dist_flags, 0, sizeof(int) * (kDistFlagCapacity + 1024), b->ctx->stream));
+  }
+  PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  if (snapshot_base) *snapshot_base = b->snapshot.base;
+  if (snapshot_stride_bytes) *snapshot_stride_bytes = static_cast<int64_t>(b->snapshot.stride);
+  if (dirty_base) *dirty_base = b->dirty;
+  if (flags_base) *flags_base = b->dist_flags;
+  PB_API_END
+}
+int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* d, int64_t n_strokes, const pb_stroke* strokes,
+                                int64_t n_imprints, const double* cx, const double* cy, const double* theta) {
+  PB_API_BEGIN
+  DeviceGuard g(b->ctx);
+  PB_REQUIRE(d != nullptr && d->world >= 1 && d->world <= kMaxBands && d->rank >= 0 && d->rank < d->world, "invalid pb_dist_desc");
+  PB_REQUIRE(d->rows_per_band > 0 && c->halo == 0 && c->row_begin == d->rank * d->rows_per_band &&
+               c->row_end == std::min(c->rows, (d->rank + 1) * d->rows_per_band),
+             "canvas is not this rank's band of a rows_per_band partition");
+  PB_REQUIRE(b->dist_flags != nullptr, "call pb_fbrush_dist_storage first");
+  DistInfo di;
+  di.world         = d->world;
+  di.rank          = d->rank;
+  di.rows_per_band = d->rows_per_band;
+  for (int r = 0; r < d->world; ++r) {
+    di.canvas_base[r]     = d->canvas_base[r];
+    di.canvas_stride[r]   = d->canvas_stride[r];
+    di.snapshot_base[r]   = d->snapshot_base[r];
+    di.snapshot_stride[r] = d->snapshot_stride[r];
+    di.dirty_base[r]      = static_cast<unsigned char*>(d->dirty_base[r]);
+    di.flags_base[r]      = static_cast<int*>(d->flags_base[r]);
+  }
+  stroke_batch_impl(b, c, n_strokes, strokes, n_imprints, cx, cy, theta, &di);
   PB_API_END
 }
 int pb_fbrush_enable_visited_count(pb_fbrush* b, int enable) {

@@ -50,6 +50,14 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // FootprintBrush.hxx:331-340: blend(va, a, vb, b) = vt > MinVolume ? (va*a + vb*b)/vt : a, applied to the six
 // K/S components that share one (va, vb). FP64 keeps the reference's exact operation order. FP32 mode evaluates
@@ -85,10 +93,22 @@ struct BlendSel<double> {
 
 template <typename T>
 struct OpCtx {
-  T* can[kLayerPlanes];
-  T* src[kLayerPlanes];
   T pickup_rate, deposition_rate, cap;
   T paintK[3], paintS[3];
+};
+
+// plane pointers of one row band (constant-bank loads; band is a compile-time 0 on the single-GPU path)
+template <typename T>
+struct Band {
+  T* can[kLayerPlanes];
+  T* src[kLayerPlanes];
+  __device__ __forceinline__ Band(const ImprintLaunch& L, int band) {
+#pragma unroll
+    for (int k = 0; k < kLayerPlanes; ++k) {
+      can[k] = static_cast<T*>(L.canvas[band][k]);
+      src[k] = static_cast<T*>(L.snapshot[band][k]);
+    }
+  }
 };
 
 // One (canvas pixel, pickup cell) interaction = pickupPaint (:349-384) then depositPaint (:393-431).
@@ -99,7 +119,7 @@ struct OpData {
 };
 
 template <typename T>
-__device__ __forceinline__ void op_load(const OpCtx<T>& C, int ci, OpData<T>& d) {
+__device__ __forceinline__ void op_load(const Band<T>& C, int ci, OpData<T>& d) {
   const bool own_src = C.src[PV] == C.can[PV];  // snapshot buffer disabled: pickup source is the canvas itself
   d.vSrc = __ldcg(C.src[PV] + ci);
 #pragma unroll
@@ -116,7 +136,8 @@ __device__ __forceinline__ void op_load(const OpCtx<T>& C, int ci, OpData<T>& d)
 }
 
 template <typename T>
-__device__ __forceinline__ void op_finish(const OpCtx<T>& C, int ci, T fh, const OpData<T>& d, T* pick, int ps, int slot) {
+__device__ __forceinline__ void op_finish(const OpCtx<T>& P, const Band<T>& C, int ci, T fh, const OpData<T>& d, T* pick, int ps,
+                                          int slot) {
   using Blend = typename BlendSel<T>::type;
   const bool own_src = C.src[PV] == C.can[PV];
   T vCan = d.vCan;
@@ -128,7 +149,7 @@ __device__ __forceinline__ void op_finish(const OpCtx<T>& C, int ci, T fh, const
     pS[k] = pick[(PS + k) * ps + slot];
   }
   // pickup
-  const T leave = C.pickup_rate * d.vSrc * fh;
+  const T leave = P.pickup_rate * d.vSrc * fh;
   if (leave > static_cast<T>(kMinVolume)) {
     const T remain = d.vSrc - leave;
     __stcg(C.src[PV] + ci, remain);
@@ -147,16 +168,16 @@ __device__ __forceinline__ void op_finish(const OpCtx<T>& C, int ci, T fh, const
     }
   }
   // deposit
-  const T vFree = fmax(static_cast<T>(0), C.cap - vP);
+  const T vFree = fmax(static_cast<T>(0), P.cap - vP);
   const Blend b_src(vP, vFree);
-  const T vLeave       = C.deposition_rate * vP * fh;
+  const T vLeave       = P.deposition_rate * vP * fh;
   pick[PV * ps + slot] = vP - vLeave;
-  const T vB           = C.cap * fh;
+  const T vB           = P.cap * fh;
   const Blend b_can(vB, vCan);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    __stcg(C.can[PK + k] + ci, b_can(b_src(pK[k], C.paintK[k]), d.cK[k]));
-    __stcg(C.can[PS + k] + ci, b_can(b_src(pS[k], C.paintS[k]), d.cS[k]));
+    __stcg(C.can[PK + k] + ci, b_can(b_src(pK[k], P.paintK[k]), d.cK[k]));
+    __stcg(C.can[PS + k] + ci, b_can(b_src(pS[k], P.paintS[k]), d.cS[k]));
   }
   __stcg(C.can[PV] + ci, vB + vCan);
 }
@@ -169,13 +190,15 @@ __device__ __forceinline__ void op_finish(const OpCtx<T>& C, int ci, T fh, const
 struct Hits {
   int ci[2];   // pixel index in the stored planes (< 2^31, like the reference's int32 K(i))
   int dof[2];  // byte offset in the dirty map
+  int band[2];
   int n;
 };
+template <bool MULTI>
 __device__ __forceinline__ Hits find_hits(const ImprintLaunch& L, const DevImprint& im, float fc, float fs, int wr, int mx, int my,
                                           bool border, int ph, int row_lo, int row_hi) {
   Hits h;
   h.n = 0;
-  h.ci[0] = h.ci[1] = h.dof[0] = h.dof[1] = 0;
+  h.ci[0] = h.ci[1] = h.dof[0] = h.dof[1] = h.band[0] = h.band[1] = 0;
   const float u = static_cast<float>(mx - wr), v = static_cast<float>(my - wr);
   const float colf = fmaf(u, fc, v * fs), rowf = fmaf(v, fc, -u * fs);
   const int c0 = static_cast<int>(floorf(colf)), r0 = static_cast<int>(floorf(rowf));
@@ -195,10 +218,16 @@ __device__ __forceinline__ Hits find_hits(const ImprintLaunch& L, const DevImpri
       const int px = static_cast<int>(fx), py = static_cast<int>(fy);  // trunc toward zero (:92-93)
       if (py < 0 || px < 0 || px >= L.cols || py >= L.rows) continue;
       if (border && ((fy >= 0.0 ? 2 : 0) + (fx >= 0.0 ? 1 : 0)) != ph) continue;
-      if (py < row_lo || py > row_hi) continue;  // band canvas
-      const int ci = (py - row_lo) * L.cols + px, dof = (py - row_lo) * L.dirty_pitch + px;
-      if (h.n == 0) h.ci[0] = ci, h.dof[0] = dof;
-      if (h.n == 1) h.ci[1] = ci, h.dof[1] = dof;
+      int band = 0, lrow = py - row_lo;
+      if (MULTI) {
+        band = py / L.rows_per_band;  // the row's owner GPU
+        lrow = py - band * L.rows_per_band;
+      } else if (py < row_lo || py > row_hi) {
+        continue;  // band canvas without peers: rows outside the stored window are not ours
+      }
+      const int ci = lrow * L.cols + px, dof = lrow * L.dirty_pitch + px;
+      if (h.n == 0) h.ci[0] = ci, h.dof[0] = dof, h.band[0] = band;
+      if (h.n == 1) h.ci[1] = ci, h.dof[1] = dof, h.band[1] = band;
       ++h.n;  // a unit cell cannot hold more than 2 lattice points (min distance 1 < diagonal sqrt 2)
     }
   }
@@ -217,12 +246,14 @@ struct RingGeom {
   int ax0, ay0, ax1, ay1;  // allowed box, clipped to canvas and stored rows
 };
 
-template <typename T>
-__device__ __forceinline__ void ring_word(const ImprintLaunch& L, const OpCtx<T>& C, const RingGeom& g, int row, int wi,
-                                          unsigned word) {
+template <typename T, bool MULTI>
+__device__ __forceinline__ void ring_word(const ImprintLaunch& L, const RingGeom& g, int row, int wi, unsigned word) {
   const bool mid = row > g.tly && row < g.bry;
-  unsigned char* drow = L.dirty + static_cast<int64_t>(row - L.store_first) * L.dirty_pitch;
-  const int64_t rbase = static_cast<int64_t>(row - L.store_first) * L.cols;
+  const int band = MULTI ? row / L.rows_per_band : 0;
+  const int lrow = MULTI ? row - band * L.rows_per_band : row - L.store_first;
+  const Band<T> C(L, band);
+  unsigned char* drow = L.dirty[band] + static_cast<int64_t>(lrow) * L.dirty_pitch;
+  const int64_t rbase = static_cast<int64_t>(lrow) * L.cols;
   bool need[4];
   T v[4][kLayerPlanes];
 #pragma unroll
@@ -245,8 +276,8 @@ __device__ __forceinline__ void ring_word(const ImprintLaunch& L, const OpCtx<T>
   }
 }
 
-template <typename T>
-__device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const OpCtx<T>& C, const RingGeom& g, int gt, int gstride) {
+template <typename T, bool MULTI>
+__device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const RingGeom& g, int gt, int gstride) {
   if (g.ax1 < g.ax0 || g.ay1 < g.ay0) return;
   const int w0 = g.ax0 >> 2, nw = (g.ax1 >> 2) - w0 + 1, nrows = g.ay1 - g.ay0 + 1;
   const int total = nw * nrows;
@@ -268,19 +299,22 @@ __device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const OpCtx<T>
         const int wi = w0 + (i - r * nw), row = g.ay0 + r;
         rows[u] = row;
         wis[u]  = wi;
-        if (!(row > g.tly && row < g.bry && wi >= iw0 && wi <= iw1))
-          word[u] = __ldcg(reinterpret_cast<const unsigned*>(L.dirty + static_cast<int64_t>(row - L.store_first) * L.dirty_pitch) + wi);
+        if (!(row > g.tly && row < g.bry && wi >= iw0 && wi <= iw1)) {
+          const int band = MULTI ? row / L.rows_per_band : 0;
+          const int lrow = MULTI ? row - band * L.rows_per_band : row - L.store_first;
+          word[u] = __ldcg(reinterpret_cast<const unsigned*>(L.dirty[band] + static_cast<int64_t>(lrow) * L.dirty_pitch) + wi);
+        }
       }
     }
 #pragma unroll
     for (int u = 0; u < kScanBatch; ++u)
-      if (word[u] != 0u) ring_word(L, C, g, rows[u], wis[u], word[u]);
+      if (word[u] != 0u) ring_word<T, MULTI>(L, g, rows[u], wis[u], word[u]);
   }
 }
 
 constexpr int kRegCells = 2;  // cells per thread whose geometry is kept in registers across the stroke
 
-template <typename T, bool CL, int MAXB>
+template <typename T, bool CL, int MAXB, bool MULTI>
 __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_stroke;
@@ -292,7 +326,9 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
   const int csize   = CL ? static_cast<int>(cluster.num_blocks()) : 1;
   const int gstride = csize * bd;
   const int sgt     = crank * bd + tid;  // contiguous numbering for the coalesced dirty-map scan
+  bool remote   = false;  // current stroke touches rows of another GPU: barriers need system-scope fences
   auto sync_all = [&]() {
+    if (MULTI && remote) __threadfence_system();
     if (CL)
       cluster.sync();
     else
@@ -300,11 +336,6 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
   };
 
   OpCtx<T> C;
-#pragma unroll
-  for (int k = 0; k < kLayerPlanes; ++k) {
-    C.can[k] = static_cast<T*>(L.canvas[k]);
-    C.src[k] = static_cast<T*>(L.snapshot[k]);
-  }
   C.pickup_rate     = static_cast<T>(L.pickup_rate);
   C.deposition_rate = static_cast<T>(L.deposition_rate);
   C.cap             = static_cast<T>(L.capacity);
@@ -324,8 +355,14 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
     // dataflow wait: every earlier stroke whose region overlaps ours has completed
     if (crank == 0) {
       for (int p = st.pred_begin + tid; p < st.pred_end; p += bd) {
-        const int* flag = L.done + L.preds[p];
-        while (ld_acquire(flag) == 0) __nanosleep(64);
+        const int code = L.preds[p];
+        if (MULTI) {  // the predecessor may have run on another GPU: poll its flag through NVLink
+          const int* flag = L.done[code >> 27] + (code & 0x7ffffff);
+          while (ld_acquire_sys(flag) != L.epoch) __nanosleep(256);
+        } else {
+          const int* flag = L.done[0] + code;
+          while (ld_acquire(flag) != L.epoch) __nanosleep(64);
+        }
       }
     }
     sync_all();
@@ -335,6 +372,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
       C.paintK[k] = static_cast<T>(st.paintK[k]);
       C.paintS[k] = static_cast<T>(st.paintS[k]);
     }
+    remote       = MULTI && (st.flags & 4) != 0;
     const int nA = st.n_active;
     const int wr = (st.side - 1) / 2;  // == hr (square footprint), FootprintBrush.hxx:75-78
     const T* fhs = static_cast<const T*>(st.fh);
@@ -390,10 +428,10 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
         g.tlx = static_cast<int>(im.cx - wr), g.tly = static_cast<int>(im.cy - wr);
         g.brx = static_cast<int>(im.cx + wr), g.bry = static_cast<int>(im.cy + wr);
         g.ax0 = max(static_cast<int>(im.cx - wr - st.radius), 0);
-        g.ay0 = max(max(static_cast<int>(im.cy - wr - st.radius), 0), row_lo);
+        g.ay0 = max(max(static_cast<int>(im.cy - wr - st.radius), 0), MULTI ? 0 : row_lo);
         g.ax1 = min(static_cast<int>(im.cx + wr + st.radius), L.cols - 1);
-        g.ay1 = min(min(static_cast<int>(im.cy + wr + st.radius), L.rows - 1), row_hi);
-        ring_scan(L, C, g, sgt, gstride);
+        g.ay1 = min(min(static_cast<int>(im.cy + wr + st.radius), L.rows - 1), MULTI ? L.rows - 1 : row_hi);
+        ring_scan<T, MULTI>(L, g, sgt, gstride);
       }
       // left/top overhang: canvas pixels of column/row 0 can be hit twice (B#11) -> ordered phases
       const bool border = (im.cx - wr < 0.0) || (im.cy - wr < 0.0);
@@ -427,18 +465,19 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
 #pragma unroll
           for (int q = 0; q < CPP; ++q) {
             h[q].n = 0;
-            if (have[q]) h[q] = find_hits(L, im, fc, fs, wr, mx[q], my[q], border, ph, row_lo, row_hi);
+            if (have[q]) h[q] = find_hits<MULTI>(L, im, fc, fs, wr, mx[q], my[q], border, ph, row_lo, row_hi);
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              if (j < h[q].n) op_load(C, h[q].ci[j], d[q][j]);
+              if (j < h[q].n) op_load(Band<T>(L, MULTI ? h[q].band[j] : 0), h[q].ci[j], d[q][j]);
           }
 #pragma unroll
           for (int q = 0; q < CPP; ++q) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               if (j < h[q].n) {
-                op_finish(C, h[q].ci[j], fh[q], d[q][j], pick, ps, slot[q]);
-                if (L.dirty) __stcg(L.dirty + h[q].dof[j], static_cast<unsigned char>(1));
+                const int band = MULTI ? h[q].band[j] : 0;
+                op_finish(C, Band<T>(L, band), h[q].ci[j], fh[q], d[q][j], pick, ps, slot[q]);
+                if (L.dirty[0]) __stcg(L.dirty[band] + h[q].dof[j], static_cast<unsigned char>(1));
                 ++my_active;
               }
             }
@@ -459,8 +498,13 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
     }
     sync_all();
     if (crank == 0 && tid == 0) {
-      __threadfence();
-      st_release(L.done + si, 1);
+      if (MULTI) {
+        __threadfence_system();
+        st_release_sys(L.done[L.my_band] + L.flag_offset + si, L.epoch);
+      } else {
+        __threadfence();
+        st_release(L.done[0] + L.flag_offset + si, L.epoch);
+      }
     }
   }
 
@@ -500,15 +544,18 @@ __global__ void __launch_bounds__(256) count_visited_kernel(const DevStroke* str
 }
 
 // variants by maximum block size: smaller CTAs get a larger register budget (no spills on the critical path)
-template <typename T, bool CL>
+template <typename T, bool CL, bool MULTI>
 const void* kernel_ptr_b(int block) {
-  if (block <= 256) return reinterpret_cast<const void*>(imprint_kernel<T, CL, 256>);
-  if (block <= 512) return reinterpret_cast<const void*>(imprint_kernel<T, CL, 512>);
-  return reinterpret_cast<const void*>(imprint_kernel<T, CL, 1024>);
+  if (block <= 256) return reinterpret_cast<const void*>(imprint_kernel<T, CL, 256, MULTI>);
+  return reinterpret_cast<const void*>(imprint_kernel<T, CL, 512, MULTI>);
 }
-const void* kernel_ptr(int precision, bool cl, int block) {
-  if (precision == PB_F64) return cl ? kernel_ptr_b<double, true>(block) : kernel_ptr_b<double, false>(block);
-  return cl ? kernel_ptr_b<float, true>(block) : kernel_ptr_b<float, false>(block);
+template <typename T>
+const void* kernel_ptr_t(bool cl, int block, bool multi) {
+  if (multi) return cl ? kernel_ptr_b<T, true, true>(block) : kernel_ptr_b<T, false, true>(block);
+  return cl ? kernel_ptr_b<T, true, false>(block) : kernel_ptr_b<T, false, false>(block);
+}
+const void* kernel_ptr(int precision, bool cl, int block, bool multi) {
+  return precision == PB_F64 ? kernel_ptr_t<double>(cl, block, multi) : kernel_ptr_t<float>(cl, block, multi);
 }
 
 }  // namespace
@@ -550,13 +597,14 @@ void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& sme
   L.cluster  = cluster;
   // occupancy queries and attribute changes cost milliseconds: do them once per launch shape
   static std::map<std::tuple<int, int, int, int, size_t>, int> cache;
-  const auto key = std::make_tuple(ctx->device, ctx->precision, cluster, block, smem_bytes);
+  const bool multi = L.n_bands > 1;
+  const auto key   = std::make_tuple(ctx->device, ctx->precision * 2 + (multi ? 1 : 0), cluster, block, smem_bytes);
   auto it        = cache.find(key);
   if (it != cache.end()) {
     L.grid = it->second;
     return;
   }
-  const void* fn = kernel_ptr(ctx->precision, cluster > 1, block);
+  const void* fn = kernel_ptr(ctx->precision, cluster > 1, block, multi);
   PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (cluster > 8) PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   if (cluster == 1) {
@@ -586,7 +634,7 @@ void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& sme
 
 void imprint_launch(pb_context* ctx, const ImprintLaunch& L, size_t smem_bytes) {
   if (L.n_strokes <= 0) return;
-  const void* fn = kernel_ptr(ctx->precision, L.cluster > 1, L.block);
+  const void* fn = kernel_ptr(ctx->precision, L.cluster > 1, L.block, L.n_bands > 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim            = dim3(static_cast<unsigned>(L.grid));
   cfg.blockDim           = dim3(static_cast<unsigned>(L.block));

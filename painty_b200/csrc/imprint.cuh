@@ -19,6 +19,8 @@ struct DevImprint {  // per-imprint constants, computed on the host in f64 (Foot
   double cx, cy, c, s;  // c = cos(-theta), s = sin(-theta)
 };
 
+constexpr int kMaxBands = 8;  // GPUs of one NVSwitch node
+
 struct DevStroke {
   int64_t first_imprint;
   int32_t n_imprints;
@@ -29,19 +31,24 @@ struct DevStroke {
   double radius;  // FootprintBrush::_radius as used by updateSnapshot (:298-305)
   double paintK[3], paintS[3];
   int32_t pred_begin, pred_end;  // into preds[]
-  int32_t flags;                 // bit0: load pick state from the dense map, bit1: store it back
+  int32_t flags;                 // bit0: load pick state from the dense map, bit1: store it back,
+                                 // bit2: the stroke touches rows owned by another GPU (system-scope fences)
   int32_t pad;
 };
 
 struct ImprintLaunch {
-  // canvas
-  void* canvas[kLayerPlanes];
-  void* snapshot[kLayerPlanes];  // == canvas planes when the snapshot buffer is disabled
-  unsigned char* dirty;          // 1 byte per pixel: snapshot(p) may differ from canvas(p); row pitch dirty_pitch
+  // Canvas / snapshot / dirty planes per row band. Single GPU: one band (n_bands = 1) holding the rows
+  // [store_first, store_first + store_rows). Multi GPU (n_bands > 1): band b holds the rows
+  // [b*rows_per_band, min((b+1)*rows_per_band, rows)) and lives in GPU b's HBM; the pointers of the other bands are
+  // peer mappings (CUDA IPC) reached through NVLink.
+  void* canvas[kMaxBands][kLayerPlanes];
+  void* snapshot[kMaxBands][kLayerPlanes];  // == canvas planes when the snapshot buffer is disabled
+  unsigned char* dirty[kMaxBands];          // 1 byte per pixel: snapshot(p) may differ from canvas(p)
+  int n_bands, rows_per_band, my_band;
   int dirty_pitch;
   int use_snapshot;
   int rows, cols;               // logical canvas size (bounds checks)
-  int store_first, store_rows;  // stored row window
+  int store_first, store_rows;  // stored row window (single band only)
   // brush constants
   double pickup_rate, deposition_rate, capacity;
   // dense pickup map of the brush (7 planes of size_map^2), used by strokes with flags
@@ -50,8 +57,10 @@ struct ImprintLaunch {
   const DevStroke* strokes;
   int64_t n_strokes;
   const DevImprint* imprints;
-  const int32_t* preds;
-  int* done;                     // per stroke completion flags (zeroed)
+  const int32_t* preds;          // single GPU: stroke index; multi GPU: (rank << 27) | index on that rank
+  int* done[kMaxBands];          // per-rank completion flags ([my_band] is local); a stroke is done when == epoch
+  int epoch;
+  int flag_offset;               // flag index of this launch's stroke 0 (strokes of earlier launches come first)
   int* queue;                    // single counter (zeroed)
   unsigned long long* counters;  // [0] active stroke-pixels
   // per-CTA pick scratch in global memory for footprints that do not fit shared memory

@@ -1,0 +1,92 @@
+"""torch.distributed glue for one canvas sharded into row bands over the GPUs of a node (one process per GPU).
+
+Plumbing only: it creates this rank's band canvas, exchanges CUDA IPC handles of the canvas / snapshot / dirty-map /
+flag allocations with `all_gather_object`, maps the peers' memory (NVLink) and fills the `pb_dist_desc` that
+`pb_fbrush_stroke_batch_dist` consumes. The rendering itself is the C ABI / CUDA library.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import api
+
+_VP = C.c_void_p
+MAX_BANDS = 8
+
+
+class pb_dist_desc(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("rows_per_band", C.c_int32), ("reserved", C.c_int32),
+                ("canvas_base", _VP * MAX_BANDS), ("canvas_stride", C.c_int64 * MAX_BANDS),
+                ("snapshot_base", _VP * MAX_BANDS), ("snapshot_stride", C.c_int64 * MAX_BANDS),
+                ("dirty_base", _VP * MAX_BANDS), ("flags_base", _VP * MAX_BANDS)]
+
+
+def rows_per_band(rows, world):
+    return (rows + world - 1) // world
+
+
+class DistCanvas:
+    """This rank's band of a rows x cols canvas. Rank r owns rows [r*rpb, min((r+1)*rpb, rows))."""
+
+    def __init__(self, ctx, rows, cols, dist):
+        self.ctx, self.rows, self.cols, self.dist = ctx, rows, cols, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        assert self.world <= MAX_BANDS
+        self.rpb = rows_per_band(rows, self.world)
+        self.row_begin = min(self.rank * self.rpb, rows)
+        self.row_end = min(self.row_begin + self.rpb, rows)
+        self.canvas = api.Canvas(ctx, rows, cols, band=(self.row_begin, self.row_end, 0))
+        self._desc = {}
+        self._imported = []
+
+    def _export(self, ptr):
+        h = (C.c_ubyte * 64)()
+        api._chk(api.lib().pb_ipc_export(self.ctx.h, _VP(ptr), h))
+        return bytes(h)
+
+    def _import(self, handle):
+        p = _VP()
+        api._chk(api.lib().pb_ipc_import(self.ctx.h, (C.c_ubyte * 64).from_buffer_copy(handle), C.byref(p)))
+        self._imported.append(p.value)
+        return p.value
+
+    def attach(self, brush):
+        """Exchange the peer mappings for this (canvas, brush) pair. Collective: every rank must call it."""
+        lib = api.lib()
+        cbase, cstride = _VP(), C.c_int64()
+        api._chk(lib.pb_canvas_storage(self.canvas.h, C.byref(cbase), C.byref(cstride)))
+        sbase, sstride, dbase, fbase = _VP(), C.c_int64(), _VP(), _VP()
+        api._chk(lib.pb_fbrush_dist_storage(brush.h, self.canvas.h, C.byref(sbase), C.byref(sstride), C.byref(dbase), C.byref(fbase)))
+        mine = dict(canvas=self._export(cbase.value), cstride=cstride.value, snapshot=self._export(sbase.value), sstride=sstride.value,
+                    dirty=self._export(dbase.value), flags=self._export(fbase.value))
+        everyone = [None] * self.world
+        self.dist.all_gather_object(everyone, mine)
+        d = pb_dist_desc()
+        d.world, d.rank, d.rows_per_band = self.world, self.rank, self.rpb
+        own = dict(canvas=cbase.value, snapshot=sbase.value, dirty=dbase.value, flags=fbase.value)
+        for r, e in enumerate(everyone):
+            for key, arr in (("canvas", d.canvas_base), ("snapshot", d.snapshot_base), ("dirty", d.dirty_base), ("flags", d.flags_base)):
+                arr[r] = own[key] if r == self.rank else self._import(e[key])
+            d.canvas_stride[r], d.snapshot_stride[r] = e["cstride"], e["sstride"]
+        self._desc[id(brush)] = d
+        self.dist.barrier()
+        return d
+
+    def stroke_batch(self, brush, strokes, cx, cy, theta):
+        """Every rank passes the same global stroke list (submission order)."""
+        d = self._desc.get(id(brush)) or self.attach(brush)
+        strokes = np.ascontiguousarray(strokes, dtype=api.STROKE_DTYPE)
+        cx, cy, theta = api._f64(cx), api._f64(cy), api._f64(theta)
+        self.ctx.synchronize()
+        self.dist.barrier()  # every band is ready (cleared / snapshot taken) before any kernel touches peer rows
+        api._chk(api.lib().pb_fbrush_stroke_batch_dist(brush.h, self.canvas.h, C.byref(d), C.c_int64(len(strokes)),
+                                                        strokes.ctypes.data_as(_VP), C.c_int64(len(cx)), api._p(cx), api._p(cy), api._p(theta)))
+        self.ctx.synchronize()
+        self.dist.barrier()  # all GPUs have finished writing into each other's bands
+
+    def close(self):
+        self.ctx.synchronize()
+        self.dist.barrier()
+        for p in self._imported:
+            api.lib().pb_ipc_close(self.ctx.h, _VP(p))
+        self._imported = []
