@@ -17,11 +17,12 @@ in an untimed pass.
   e2e      : same metric through the C ABI with HOST buffers: stroke list H2D + kernels + reflectance D2H
              (AoS f64 like Renderer::compose returns) inside the timed region.
   roofline : the KM compose kernel (the path's HBM-bound kernel): 52 B/px algorithmic / event time.
-N > 1: one process per GPU (torchrun), weak scaling: every rank renders its own 4K canvas with its own seeded
-stroke list (the canvases are the independent row bands of an N x 2160-row sheet whose strokes never cross a band),
-then the N reflectance images are assembled with one NCCL all_gather. Exact band sharding of ONE canvas is
-implemented for compose and texture strokes (painty_b200/bands.py, tests/test_bands_cpu.py); footprint strokes
-that straddle bands need the halo exchange planned for the next round.
+N > 1: one process per GPU (torchrun), weak scaling of ONE canvas: the canvas grows to (N x 2160) x 3840 with N x S
+strokes of the same size distribution and is cut into N row bands, one per GPU. A stroke is executed by the GPU
+whose band holds its first imprint; where it leaves the band the kernel reads / writes the neighbour's HBM through
+NVLink peer mappings and strokes wait on completion flags of conflicting earlier strokes on any GPU
+(painty_b200/dist.py, bit-exact vs one GPU: tests/test_dist_gpu.py). The reflectance bands are assembled with one NCCL
+all_gather inside the timed step.
 """
 import argparse
 import json
@@ -213,24 +214,40 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    rec, cx, cy, th, radii = build_workload(args.strokes, seed=1234 + rank)
+    rows_total = ROWS * world
+    rec, cx, cy, th, radii = build_workload(args.strokes * world, rows=rows_total)  # same list on every rank
     ctx = api.Context(local, api.F32)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
-    cv = api.Canvas(ctx, ROWS, COLS)
+    dc = None
+    if world > 1:
+        from painty_b200.dist import DistCanvas
+
+        dc = DistCanvas(ctx, rows_total, COLS, dist)
+        cv = dc.canvas
+    else:
+        cv = api.Canvas(ctx, ROWS, COLS)
     br = api.FootprintBrush(ctx, radii[0])
     for r in radii:
         br.register_radius(r)
-    n_px = ROWS * COLS
+    if dc is not None:
+        dc.attach(br)
+    n_px = cv.store_rows * COLS
     d_R = torch.empty((3, n_px), dtype=torch.float32, device="cuda")
-    h_R = torch.empty((ROWS, COLS, 3), dtype=torch.float64).pin_memory()
+    h_R = torch.empty((cv.store_rows, COLS, 3), dtype=torch.float64).pin_memory()
     h_R_np = h_R.numpy()
     gathered = torch.empty((world, 3, n_px), dtype=torch.float32, device="cuda") if world > 1 else None
+
+    def strokes_all():
+        if dc is not None:
+            dc.stroke_batch(br, rec, cx, cy, th)
+        else:
+            br.stroke_batch(cv, rec, cx, cy, th)
 
     # untimed: exact stroke-pixel count of the workload (reference's `counter`)
     br.enable_visited_count(True)
     cv.clear()
     br.updateSnapshot(cv)
-    br.stroke_batch(cv, rec, cx, cy, th)
+    strokes_all()
     ctx.synchronize()
     visited, active = br.counters()
     br.enable_visited_count(False)
@@ -242,7 +259,7 @@ def main():
         br.updateSnapshot(cv)  # FootprintBrush::updateSnapshot(canvas): brush state == a freshly constructed brush
         if timers is not None:
             timers[0].record(stream)
-        br.stroke_batch(cv, rec, cx, cy, th)
+        strokes_all()
         if timers is not None:
             timers[1].record(stream)
         cv.compose_device(d_R.data_ptr(), n_px)
@@ -296,7 +313,7 @@ def main():
     def step_e2e():
         cv.clear()
         br.updateSnapshot(cv)
-        br.stroke_batch(cv, rec, cx, cy, th)
+        strokes_all()
         cv.compose(h_R_np)
 
     # one warm-up pass (first use of the host-buffer path allocates staging memory), one timed pass
@@ -327,8 +344,10 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "stroke-pixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "sbr-style 3840x2160, %d footprint strokes (%d imprints) + KM compose" % (len(rec), len(cx)),
-                   "parallelism": "single GPU" if world == 1 else "%d independent 4K canvases (one per GPU), NCCL all_gather of reflectance" % world,
+        "config": {"workload": "sbr-style 3840x%d, %d footprint strokes (%d imprints) + KM compose" % (rows_total, len(rec), len(cx)),
+                   "parallelism": "single GPU" if world == 1 else
+                   "one %dx%d canvas in %d row bands (one per GPU), strokes cross bands through NVLink peer memory, NCCL all_gather of "
+                   "reflectance" % (rows_total, COLS, world),
                    "stroke_pixels_per_step": int(visited), "active_stroke_pixels_per_step": int(active),
                    "l2": "canvas working set 8.3 Mpx x 14 planes x 4 B = 464 MB > 126 MB L2; canvas cleared every step",
                    "imprint_ms": t_imp / args.steps, "compose_ms": cmp_ms},
