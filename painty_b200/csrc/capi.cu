@@ -3,6 +3,7 @@
 // that computes pixels needs a CUDA device and fails loudly otherwise.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -153,6 +154,26 @@ const FootprintGeom* register_footprint(pb_fbrush* b, double radius, int side, c
         }
       }
     g.n_active = static_cast<int>(xy.size());
+    if (std::getenv("PB_CELL_ORDER") == nullptr || std::atoi(std::getenv("PB_CELL_ORDER")) != 0) {
+      // Order the compacted cells by 8x4 tiles of the pickup map: a warp (32 consecutive cells) then covers a compact
+      // 2-D patch whose rotated image touches far fewer 32 B sectors of the SoA canvas planes than a 32-cell row
+      // segment does at oblique angles. Cells are thread-private, so their order is free.
+      std::vector<size_t> order(xy.size());
+      for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+      auto key = [&](size_t i) {
+        const uint64_t mx = xy[i] & 0xffffu, my = xy[i] >> 16;
+        return ((my >> 2) << 40) | ((mx >> 3) << 20) | ((my & 3) << 3) | (mx & 7);
+      };
+      std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return key(a) < key(b); });
+      std::vector<uint32_t> xy2(xy.size());
+      std::vector<double> fh2(fh.size());
+      for (size_t i = 0; i < order.size(); ++i) {
+        xy2[i] = xy[order[i]];
+        fh2[i] = fh[order[i]];
+      }
+      xy.swap(xy2);
+      fh.swap(fh2);
+    }
     if (g.n_active) {
       PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&g.d_xy), sizeof(uint32_t) * xy.size()));
       PB_CUDA(cudaMemcpyAsync(g.d_xy, xy.data(), sizeof(uint32_t) * xy.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -346,7 +367,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     L.n_bands = multi ? dist->world : 1;
     size_t smem = 0;
     imprint_plan(ctx, max_active, L, smem);
-    L.grid = static_cast<int>(std::min<int64_t>(L.grid, static_cast<int64_t>(n_run) * L.cluster));
+    L.grid = static_cast<int>(std::min<int64_t>(L.grid, static_cast<int64_t>(n_run) * L.cluster * L.group));
     if (multi) {
       for (int r = 0; r < dist->world; ++r) {
         for (int p = 0; p < kLayerPlanes; ++p) {
@@ -391,6 +412,11 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     d_strokes.upload(ds.data(), ds.size());
     d_preds.upload(run_preds.data(), run_preds.size());
     DevBuf<char> d_scratch(ctx, static_cast<size_t>(L.scratch_stride) * L.grid * ctx->esize());
+    const size_t n_groups = static_cast<size_t>(L.grid / (L.cluster * L.group));
+    DevBuf<long long> d_group(ctx, L.group > 1 ? 2 * n_groups : 0);  // [0,n): stroke slots, [n,2n): barrier counters
+    if (L.group > 1) d_group.zero(2 * n_groups);
+    L.group_stroke = d_group.p;
+    L.group_bar    = reinterpret_cast<unsigned*>(d_group.p + n_groups);
     L.scratch  = d_scratch.p;
     L.strokes  = d_strokes.p;
     L.imprints = d_im.p;

@@ -32,6 +32,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <tuple>
 
@@ -322,17 +323,35 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
 
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, bd = blockDim.x;
-  const int crank   = CL ? static_cast<int>(cluster.block_rank()) : 0;
-  const int csize   = CL ? static_cast<int>(cluster.num_blocks()) : 1;
+  // A stroke is owned by `G` clusters of `csize0` CTAs. Within a cluster the hardware barrier synchronises; across
+  // the clusters of a group a monotonic counter in L2 does (arrive = fence + atomicAdd by one thread per cluster,
+  // wait = acquire-poll), bracketed by two cluster barriers — the classic grid-sync construction at group scope.
+  const int csize0 = CL ? static_cast<int>(cluster.num_blocks()) : 1;
+  const int G      = CL ? L.group : 1;
+  const int cid    = static_cast<int>(blockIdx.x) / csize0;  // cluster index in the grid
+  const int group  = cid / G, grank = cid % G;
+  const int crank  = (CL ? static_cast<int>(cluster.block_rank()) : 0) + grank * csize0;  // CTA rank within the group
+  const int csize  = csize0 * G;
   const int gstride = csize * bd;
   const int sgt     = crank * bd + tid;  // contiguous numbering for the coalesced dirty-map scan
   bool remote   = false;  // current stroke touches rows of another GPU: barriers need system-scope fences
   auto sync_all = [&]() {
     if (MULTI && remote) __threadfence_system();
-    if (CL)
+    if (CL) {
       cluster.sync();
-    else
+      if (G > 1) {
+        if (cluster.block_rank() == 0 && tid == 0) {
+          __threadfence();
+          const unsigned ticket = atomicAdd(L.group_bar + group, 1u);
+          const unsigned target = (ticket / static_cast<unsigned>(G) + 1u) * static_cast<unsigned>(G);
+          while (static_cast<unsigned>(ld_acquire(reinterpret_cast<const int*>(L.group_bar + group))) < target) {
+          }
+        }
+        cluster.sync();
+      }
+    } else {
       __syncthreads();
+    }
   };
 
   OpCtx<T> C;
@@ -346,9 +365,12 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
 
   for (;;) {
     sync_all();
-    if (crank == 0 && tid == 0) s_stroke = atomicAdd(L.queue, 1);
+    if (crank == 0 && tid == 0) {
+      s_stroke = atomicAdd(L.queue, 1);
+      if (G > 1) __stcg(L.group_stroke + group, s_stroke);
+    }
     sync_all();
-    const int64_t si = CL ? *cluster.map_shared_rank(&s_stroke, 0) : s_stroke;
+    const int64_t si = G > 1 ? __ldcg(L.group_stroke + group) : (CL ? *cluster.map_shared_rank(&s_stroke, 0) : s_stroke);
     if (si >= L.n_strokes) break;
     const DevStroke st = L.strokes[si];
 
@@ -569,18 +591,25 @@ const void* kernel_ptr(int precision, bool cl, int block, bool multi) {
 int imprint_cluster_class(int n_active) { return n_active <= 256 ? 1 : (n_active <= 4096 ? 16 : 17); }
 
 void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& smem_bytes) {
-  const int cluster = imprint_cluster_class(max_active) == 1 ? 1 : 16;
+  const int cls     = imprint_cluster_class(max_active);
+  const int cluster = cls == 1 ? 1 : 16;
+  // Large footprints are bound by the per-SM L2 sector rate of their scattered SoA accesses. PB_IMPRINT_GROUP=G lets
+  // G clusters (G x 16 SMs) cooperate on one stroke (1.8x faster per stroke at G = 4), but on the sbr workload the
+  // cluster slots are worth more as concurrent strokes (measured: 2.31 s vs 2.50 s per 2000 strokes), so G = 1.
+  const char* genv = std::getenv("PB_IMPRINT_GROUP");
+  int group        = (cls == 17 && genv) ? std::min(8, std::max(1, std::atoi(genv))) : 1;
   // <= 256 threads per CTA: that kernel variant keeps two cells' interactions (56 loads) in flight without
-  // spills; the largest footprints (> 2 cells per thread at 256) trade that for twice the warps per SM.
+  // spills; without groups the largest footprints (> 2 cells per thread at 256) trade that for twice the warps.
   int block = 128;
   if (cluster == 1) {
     block = max_active <= 128 ? 128 : 256;
+  } else if (group > 1) {
+    block = max_active <= group * 16 * 128 * 2 ? 128 : 256;
   } else {
     block = max_active <= 4096 ? 128 : (max_active <= 8192 ? 256 : 512);
   }
   const size_t es     = ctx->esize();
-  const int gstride   = cluster * block;
-  const int per_cta   = (std::max(max_active, 1) + cluster - 1) / cluster;
+  const int per_cta   = (std::max(max_active, 1) + cluster * group - 1) / (cluster * group);
   const int cta_cells = (per_cta + block - 1) / block * block;
   const size_t budget = 200 * 1024;  // dynamic shared memory for this CTA's slice of the pickup map
   size_t need         = static_cast<size_t>(cta_cells) * kLayerPlanes * es;
@@ -595,10 +624,11 @@ void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& sme
   smem_bytes = need;
   L.block    = block;
   L.cluster  = cluster;
+  L.group    = group;
   // occupancy queries and attribute changes cost milliseconds: do them once per launch shape
   static std::map<std::tuple<int, int, int, int, size_t>, int> cache;
   const bool multi = L.n_bands > 1;
-  const auto key   = std::make_tuple(ctx->device, ctx->precision * 2 + (multi ? 1 : 0), cluster, block, smem_bytes);
+  const auto key   = std::make_tuple(ctx->device, ctx->precision * 2 + (multi ? 1 : 0), cluster * 100 + group, block, smem_bytes);
   auto it        = cache.find(key);
   if (it != cache.end()) {
     L.grid = it->second;
@@ -626,8 +656,8 @@ void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& sme
     cfg.numAttrs             = 1;
     int n_clusters           = 0;
     PB_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, fn, &cfg));
-    PB_REQUIRE(n_clusters >= 1, "imprint kernel: no cluster of the requested size fits on the device");
-    L.grid = n_clusters * cluster;
+    PB_REQUIRE(n_clusters >= group, "imprint kernel: the cooperating clusters of one stroke do not fit on the device");
+    L.grid = (n_clusters / group) * group * cluster;
   }
   cache[key] = L.grid;
 }

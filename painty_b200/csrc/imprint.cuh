@@ -68,7 +68,10 @@ struct ImprintLaunch {
   int64_t scratch_stride;  // elements per CTA
   int smem_cells;          // cells per CTA that fit in dynamic shared memory
   int block;               // threads per CTA
-  int cluster;             // CTAs per stroke (thread-block cluster size)
+  int cluster;             // CTAs per thread-block cluster
+  int group;               // clusters cooperating on one stroke (software barrier on top of the hardware one)
+  unsigned* group_bar;     // per group: monotonic arrival counter of the inter-cluster barrier (zeroed)
+  long long* group_stroke; // per group: stroke index popped by the group leader
   int grid;                // CTAs (multiple of cluster)
 };
 

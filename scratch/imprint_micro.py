@@ -11,7 +11,7 @@ for r in radii:
     r = assets.snap_to_safe_radius(r)
     br = api.FootprintBrush(ctx, r)
     br.dip(([.3,.2,.1],[.2,.4,.3]))
-    cx = np.linspace(600, 600+n, n); cy = np.linspace(700, 700+0.3*n, n); th = np.full(n, 0.29)
+    cx = np.linspace(600, 600+n, n); cy = np.linspace(700, 700+0.3*n, n); th = np.full(n, float(sys.argv[3]) if len(sys.argv)>3 else 0.29)
     for rep in range(3):
         cv.clear(); br.updateSnapshot(cv); ctx.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
