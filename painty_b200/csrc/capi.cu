@@ -247,8 +247,9 @@ struct DistInfo {
 };
 constexpr int64_t kDistFlagCapacity = int64_t(1) << 22;
 
-Region stroke_region(const HostStroke& h, const double* cx, const double* cy, int rows, int cols) {
-  // everything the stroke reads or writes: union of the snapshot "allowed" boxes (:298-305)
+// margin 0: the BOX the stroke modifies (footprint square around every centre); margin = radius: everything it
+// reads or writes, i.e. the union of the snapshot "allowed" boxes (:298-305). Both padded by 2 px.
+Region stroke_region(const HostStroke& h, const double* cx, const double* cy, int rows, int cols, double margin) {
   Region r{1, 1, 0, 0};
   if (h.n <= 0) return r;
   double lx = cx[h.first], hx = lx, ly = cy[h.first], hy = ly;
@@ -258,7 +259,7 @@ Region stroke_region(const HostStroke& h, const double* cx, const double* cy, in
     ly = std::min(ly, cy[i]);
     hy = std::max(hy, cy[i]);
   }
-  const double m = (h.g->side - 1) / 2 + h.radius + 2.0;
+  const double m = (h.g->side - 1) / 2 + margin + 2.0;
   r.x0 = static_cast<int>(std::max(0.0, std::floor(lx - m)));
   r.y0 = static_cast<int>(std::max(0.0, std::floor(ly - m)));
   r.x1 = static_cast<int>(std::min<double>(cols - 1, std::ceil(hx + m)));
@@ -289,8 +290,13 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
   DataflowPlanner planner(c->rows, c->cols);
   for (size_t s = 0; s < n; ++s) {
     const HostStroke& h = hs[s];
-    const Region r      = stroke_region(h, cx, cy, c->rows, c->cols);
-    planner.add(static_cast<int32_t>(s), r, preds, pred_begin[s], pred_end[s]);
+    const Region r      = stroke_region(h, cx, cy, c->rows, c->cols, h.radius);
+    if (b->use_snapshot) {
+      planner.add_footprint(static_cast<int32_t>(s), stroke_region(h, cx, cy, c->rows, c->cols, 0.0), r, preds, pred_begin[s],
+                            pred_end[s]);
+    } else {
+      planner.add(static_cast<int32_t>(s), stroke_region(h, cx, cy, c->rows, c->cols, 0.0), preds, pred_begin[s], pred_end[s]);
+    }
     if (multi && h.n > 0) {
       const int y0 = std::min(std::max(static_cast<int>(cy[h.first]), 0), c->rows - 1);
       executor[s]  = std::min(y0 / dist->rows_per_band, dist->world - 1);

@@ -43,9 +43,44 @@ class DataflowPlanner {
     end = static_cast<int32_t>(preds.size());
   }
 
+  // Footprint strokes have two footprints on the canvas: the BOX they modify (canvas, snapshot, dirty flags under
+  // the brush) and the larger ALLOWED region in which their snapshot ring only refreshes pixels that are already
+  // dirty (an idempotent copy of values the stroke itself never changes). Two strokes must keep their order iff the
+  // box of one meets the allowed region of the other; two rings that merely overlap each other commute.
+  // Per tile we keep the last stroke whose box touched it and the strokes whose ring touched it since then.
+  void add_footprint(int32_t index, const Region& box, const Region& allowed, std::vector<int32_t>& preds, int32_t& begin,
+                     int32_t& end) {
+    begin = static_cast<int32_t>(preds.size());
+    if (ring_.empty()) ring_.resize(last_.size());
+    auto push = [&](int32_t l) {
+      if (l < 0 || l == index) return;
+      for (int32_t k = static_cast<int32_t>(preds.size()) - 1; k >= begin; --k)
+        if (preds[k] == l) return;
+      preds.push_back(l);
+    };
+    auto tiles = [&](const Region& r, auto&& fn) {
+      if (r.x1 < r.x0 || r.y1 < r.y0) return;
+      const int tx0 = r.x0 / tile_, tx1 = std::min(r.x1 / tile_, tx_ - 1);
+      const int ty0 = r.y0 / tile_, ty1 = std::min(r.y1 / tile_, ty_ - 1);
+      for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) fn(static_cast<size_t>(ty) * tx_ + tx);
+    };
+    tiles(allowed, [&](size_t t) { push(last_[t]); });  // earlier boxes under our ring or box
+    tiles(box, [&](size_t t) {                          // earlier rings over our box
+      for (int32_t l : ring_[t]) push(l);
+    });
+    tiles(allowed, [&](size_t t) { ring_[t].push_back(index); });
+    tiles(box, [&](size_t t) {
+      last_[t] = index;
+      ring_[t].clear();
+    });
+    end = static_cast<int32_t>(preds.size());
+  }
+
  private:
   int tile_, tx_, ty_;
   std::vector<int32_t> last_;
+  std::vector<std::vector<int32_t>> ring_;
 };
 
 }  // namespace pb

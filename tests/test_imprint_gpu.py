@@ -250,3 +250,51 @@ def test_imprint_before_set_radius_fails(ctx32):
     br = api.FootprintBrush(ctx32, 0.2)  # < 0.5: the reference leaves a 0x0 footprint (FootprintBrush.hxx:47)
     with pytest.raises(api.PaintyError):
         br.imprint((5.0, 5.0), 0.0, cv)
+
+
+@pytest.mark.parametrize("use_snapshot", [True, False])
+def test_dense_overlap_stress_is_order_exact(ctx64, port, use_snapshot):
+    """Hundreds of short strokes piled on a small canvas: almost every pair conflicts through boxes or snapshot
+    rings, some only through rings (which commute). The concurrent device schedule must equal the sequential CPU
+    order bit for bit — canvas, snapshot and final pickup map."""
+    from painty_b200 import api
+
+    rows, cols = 256, 288
+    r = np.random.default_rng(99)
+    radii = [4.0, 6.0, 8.0, 9.0, 11.0, 13.0]
+    cvo, cv = port.canvas(rows, cols), api.Canvas(ctx64, rows, cols)
+    bro, br = port.footprint_brush(radii[0]), api.FootprintBrush(ctx64, radii[0])
+    bro.set_use_snapshot(use_snapshot)
+    br.setUseSnapshotBuffer(use_snapshot)
+    for rad in radii:
+        br.register_radius(rad)
+    n = 300
+    rec = np.zeros(n, dtype=api.STROKE_DTYPE)
+    xs, ys, ts, first = [], [], [], 0
+    for i in range(n):
+        rad = float(r.choice(radii))
+        m = int(r.integers(3, 45))
+        cx = np.cumsum(r.normal(0.7, 0.5, m)) + r.uniform(-10, cols + 10)
+        cy = np.cumsum(r.normal(0.1, 0.7, m)) + r.uniform(-10, rows + 10)
+        th = np.cumsum(r.normal(0, 0.2, m)) + r.uniform(-3.2, 3.2)
+        K, S = r.uniform(0.05, 1.5, 3), r.uniform(0.05, 1.0, 3)
+        bro.dip(K, S)
+        bro.set_radius(rad)
+        bro.imprint_batch(cvo, cx, cy, th)
+        rec[i] = (rad, K, S, first, m)
+        first += m
+        xs.append(cx), ys.append(cy), ts.append(th)
+    br.stroke_batch(cv, rec, np.concatenate(xs), np.concatenate(ys), np.concatenate(ts))
+    a, b = cv.download("KSV"), cvo.get()
+    for k in "KSV":
+        assert np.array_equal(a[k], b[k]), k
+    for x, y in zip(br.getPickupMap(), bro.pickup_map()):
+        assert np.array_equal(x, y)
+    if use_snapshot:
+        import ctypes as C
+
+        Ks, Ss, Vs = np.empty((rows, cols, 3)), np.empty((rows, cols, 3)), np.empty((rows, cols))
+        PD = C.POINTER(C.c_double)
+        port.fn("fbrush_get_snapshot", None, [C.c_void_p, PD, PD, PD])(bro.h, Ks.ctypes.data_as(PD), Ss.ctypes.data_as(PD), Vs.ctypes.data_as(PD))
+        gK, gS, gV = br.getSnapshot(cv)
+        assert np.array_equal(gV, Vs) and np.array_equal(gK, Ks) and np.array_equal(gS, Ss)
