@@ -1137,9 +1137,9 @@ int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const 
   std::vector<DevTStroke> ds;
   ds.reserve(static_cast<size_t>(n_strokes));
   std::vector<host::V2> poly, uv;
-  std::vector<int32_t> preds;
-  DataflowPlanner planner(c->rows, c->cols);
-  double radius = b->radius;
+  const int tile = kTextureTile, tiles_x = (c->cols + tile - 1) / tile, tiles_y = (c->rows + tile - 1) / tile;
+  int64_t n_items = 0;
+  double radius   = b->radius;
   for (int64_t s = 0; s < n_strokes; ++s) {
     const pb_tstroke& in = strokes[s];
     PB_REQUIRE(in.first_vertex >= 0 && in.n_vertices >= 0 && in.first_vertex + in.n_vertices <= n_vertices,
@@ -1154,7 +1154,9 @@ int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const 
     }
     d.thickness_scale = in.thickness_scale;
     d.poly_begin      = static_cast<int32_t>(poly.size());
-    Region r{1, 1, 0, 0};
+    d.item_begin      = n_items;
+    d.tx0 = d.ty0 = 0;
+    d.tx1 = d.ty1 = -1;
     if (f.valid) {
       PB_REQUIRE(f.poly.size() <= static_cast<size_t>(kMaxPoly), "stroke has too many vertices (max 510 per stroke)");
       d.x0 = f.x0, d.x1 = f.x1, d.y0 = f.y0, d.y1 = f.y1;
@@ -1163,13 +1165,18 @@ int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const 
       d.n_poly     = static_cast<int32_t>(f.poly.size());
       poly.insert(poly.end(), f.poly.begin(), f.poly.end());
       uv.insert(uv.end(), f.uv.begin(), f.uv.end());
-      r = Region{std::max(f.x0, 0), std::max(f.y0, 0), std::min(f.x1, c->cols - 1), std::min(f.y1, c->rows - 1)};
+      // tiles of the part of the bounding box that lies on the canvas and in the stored rows
+      const int bx0 = std::max(f.x0, 0), bx1 = std::min(f.x1, c->cols - 1);
+      const int by0 = std::max(f.y0, c->store_first), by1 = std::min(f.y1, c->store_first + c->pl.rows - 1);
+      if (bx1 >= bx0 && by1 >= by0) {
+        d.tx0 = bx0 / tile, d.tx1 = bx1 / tile, d.ty0 = by0 / tile, d.ty1 = by1 / tile;
+        n_items += static_cast<int64_t>(d.tx1 - d.tx0 + 1) * (d.ty1 - d.ty0 + 1);
+      }
     } else {
       d.x0 = d.y0 = 0;
       d.x1 = d.y1 = -1;
       d.n_poly    = 0;
     }
-    planner.add(static_cast<int32_t>(s), r, preds, d.pred_begin, d.pred_end);
     ds.push_back(d);
   }
   b->radius = radius;
@@ -1180,13 +1187,12 @@ int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const 
   static_assert(sizeof(host::V2) == sizeof(double2), "V2 must match double2");
   DevBuf<DevTStroke> d_strokes(ctx, ds.size());
   DevBuf<double2> d_poly(ctx, poly.size()), d_uv(ctx, uv.size());
-  DevBuf<int32_t> d_preds(ctx, preds.size());
-  DevBuf<int> d_flags(ctx, ds.size() + 1);
+  DevBuf<int32_t> d_ticket(ctx, static_cast<size_t>(n_items));
+  DevBuf<int> d_tiles(ctx, static_cast<size_t>(tiles_x) * tiles_y + 2);
   d_strokes.upload(ds.data(), ds.size());
   d_poly.upload(reinterpret_cast<const double2*>(poly.data()), poly.size());
   d_uv.upload(reinterpret_cast<const double2*>(uv.data()), uv.size());
-  d_preds.upload(preds.data(), preds.size());
-  d_flags.zero(ds.size() + 1);
+  d_tiles.zero(static_cast<size_t>(tiles_x) * tiles_y + 2);
   TextureLaunch L{};
   for (int p = 0; p < kLayerPlanes; ++p) L.canvas[p] = c->pl.plane(p);
   L.rows        = c->rows;
@@ -1200,9 +1206,13 @@ int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const 
   L.n_strokes   = n_strokes;
   L.poly        = d_poly.p;
   L.uv          = d_uv.p;
-  L.preds       = d_preds.p;
-  L.done        = d_flags.p;
-  L.queue       = d_flags.p + ds.size();
+  L.tile        = tile;
+  L.tiles_x     = tiles_x;
+  L.tiles_y     = tiles_y;
+  L.n_items     = n_items;
+  L.ticket      = d_ticket.p;
+  L.tile_done   = d_tiles.p;
+  L.queue       = reinterpret_cast<unsigned long long*>(d_tiles.p + static_cast<size_t>(tiles_x) * tiles_y + (((tiles_x * tiles_y) & 1) ? 1 : 0));
   L.counters    = b->d_counters;
   c->version++;
   texture_launch(ctx, L);

@@ -7,8 +7,11 @@
 // the host in f64 (texture_host.hpp) — it is per-stroke work.
 //
 // Decomposition: the reference first collects the covered pixels, then deposits; without smudge the
-// two loops fuse exactly because a pixel's result depends only on that pixel. One persistent CTA owns a
-// stroke (dataflow order as in imprint.cu), threads sweep the bounding box x-major like the reference.
+// two loops fuse exactly because a pixel's result depends only on that pixel — so a pixel only needs the strokes
+// that cover it applied in submission order. Work items are (stroke, 64x64 canvas tile) pairs in stroke-major
+// order; every canvas tile has a ticket counter, an item runs when all earlier strokes covering its tile are done
+// with it (tickets are assigned on the device by one thread per tile walking the stroke list). Persistent CTAs pop
+// items from a queue: all SMs stay busy even when consecutive strokes overlap completely.
 // The warp and the sample decide discrete outcomes (inside [0,1]^2, Vtex > 0), so they are always
 // evaluated in IEEE f64 without FMA contraction, in the reference's operation order; only the final
 // blend runs in the context's element type. The polygon (<= kMaxPoly vertices) is staged in shared memory.
@@ -106,43 +109,84 @@ __device__ __forceinline__ void mvc(const double2* __restrict__ poly, const doub
   }
 }
 
+// One thread per canvas tile walks the strokes in submission order and hands out that tile's tickets.
+__global__ void __launch_bounds__(256) texture_ticket_kernel(const TextureLaunch L) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L.tiles_x * L.tiles_y) return;
+  const int tx = t % L.tiles_x, ty = t / L.tiles_x;
+  int next = 0;
+  for (int64_t s = 0; s < L.n_strokes; ++s) {
+    const DevTStroke& st = L.strokes[s];
+    if (tx >= st.tx0 && tx <= st.tx1 && ty >= st.ty0 && ty <= st.ty1)
+      L.ticket[st.item_begin + static_cast<int64_t>(ty - st.ty0) * (st.tx1 - st.tx0 + 1) + (tx - st.tx0)] = next++;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) texture_kernel(const TextureLaunch L) {
-  __shared__ long long s_stroke;
+  __shared__ long long s_item, s_stroke;
   __shared__ unsigned long long s_pixels;
   __shared__ double2 s_poly[kMaxPoly];
   __shared__ double2 s_uv[kMaxPoly];
   const int tid = threadIdx.x, bd = blockDim.x;
-  if (tid == 0) s_pixels = 0ull;
+  if (tid == 0) {
+    s_pixels = 0ull;
+    s_stroke = -1;
+  }
   unsigned long long mine = 0;
+  long long staged         = -1;  // stroke whose polygon currently sits in shared memory
   T* can[kLayerPlanes];
 #pragma unroll
   for (int k = 0; k < kLayerPlanes; ++k) can[k] = static_cast<T*>(L.canvas[k]);
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_stroke = atomicAdd(L.queue, 1);
-    __syncthreads();
-    const int64_t si = s_stroke;
-    if (si >= L.n_strokes) break;
-    const DevTStroke st = L.strokes[si];
-    for (int p = st.pred_begin + tid; p < st.pred_end; p += bd) {
-      const int* flag = L.done + L.preds[p];
-      while (ld_acquire(flag) == 0) __nanosleep(64);
+    if (tid == 0) {
+      const long long i = static_cast<long long>(atomicAdd(L.queue, 1ull));
+      s_item            = i;
+      if (i < L.n_items) {  // stroke of item i: last stroke with item_begin <= i
+        long long lo = 0, hi = L.n_strokes - 1;
+        while (lo < hi) {
+          const long long mid = (lo + hi + 1) >> 1;
+          if (L.strokes[mid].item_begin <= i)
+            lo = mid;
+          else
+            hi = mid - 1;
+        }
+        s_stroke = lo;
+      }
     }
-    for (int i = tid; i < st.n_poly; i += bd) {
-      s_poly[i] = L.poly[st.poly_begin + i];
-      s_uv[i]   = L.uv[st.poly_begin + i];
+    __syncthreads();
+    const long long item = s_item;
+    if (item >= L.n_items) break;
+    const long long si  = s_stroke;
+    const DevTStroke st = L.strokes[si];
+    const int tw        = st.tx1 - st.tx0 + 1;
+    const int local     = static_cast<int>(item - st.item_begin);
+    const int tx = st.tx0 + local % tw, ty = st.ty0 + local / tw;
+    const int tile_id = ty * L.tiles_x + tx;
+    if (tid == 0) {
+      const int want = L.ticket[item];
+      while (ld_acquire(L.tile_done + tile_id) != want) __nanosleep(32);
+    }
+    if (staged != si) {
+      for (int i = tid; i < st.n_poly; i += bd) {
+        s_poly[i] = L.poly[st.poly_begin + i];
+        s_uv[i]   = L.uv[st.poly_begin + i];
+      }
+      staged = si;
     }
     __syncthreads();
 
     const T pK[3] = {static_cast<T>(st.K[0]), static_cast<T>(st.K[1]), static_cast<T>(st.K[2])};
     const T pS[3] = {static_cast<T>(st.S[0]), static_cast<T>(st.S[1]), static_cast<T>(st.S[2])};
-    const int h   = st.y1 - st.y0 + 1;
-    const int64_t total = st.n_poly >= 2 ? static_cast<int64_t>(st.x1 - st.x0 + 1) * h : 0;
-    for (int64_t i = tid; i < total; i += bd) {
-      // x outer / y inner like the reference (:142-145); order is irrelevant for the result
-      const int x = st.x0 + static_cast<int>(i / h), y = st.y0 + static_cast<int>(i % h);
+    // this tile's part of the reference's (int)boundMin .. (int)boundMax sweep (:142-145)
+    const int px0 = max(st.x0, tx * L.tile), px1 = min(st.x1, tx * L.tile + L.tile - 1);
+    const int py0 = max(st.y0, ty * L.tile), py1 = min(st.y1, ty * L.tile + L.tile - 1);
+    const int w = px1 - px0 + 1, h = py1 - py0 + 1;
+    const int total = (st.n_poly >= 2 && w > 0 && h > 0) ? w * h : 0;
+    for (int i = tid; i < total; i += bd) {
+      const int x = px0 + i % w, y = py0 + i / w;
       if (x < 0 || x >= L.cols || y < 0 || y >= L.rows) continue;
       double u, v;
       mvc(s_poly, s_uv, st.n_poly, static_cast<double>(x), static_cast<double>(y), u, v);
@@ -172,7 +216,7 @@ __global__ void __launch_bounds__(256) texture_kernel(const TextureLaunch L) {
     __syncthreads();
     if (tid == 0) {
       __threadfence();
-      st_release(L.done + si, 1);
+      st_release(L.tile_done + tile_id, L.ticket[item] + 1);
     }
   }
   if (mine) atomicAdd(&s_pixels, mine);
@@ -183,13 +227,17 @@ __global__ void __launch_bounds__(256) texture_kernel(const TextureLaunch L) {
 }  // namespace
 
 void texture_launch(pb_context* ctx, const TextureLaunch& L) {
-  if (L.n_strokes <= 0) return;
+  if (L.n_strokes <= 0 || L.n_items <= 0) return;
+  const int n_tiles = L.tiles_x * L.tiles_y;
+  texture_ticket_kernel<<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(L);
+  PB_CUDA(cudaGetLastError());
+  ctx->launches++;
   const void* fn = ctx->precision == PB_F64 ? reinterpret_cast<const void*>(texture_kernel<double>)
                                              : reinterpret_cast<const void*>(texture_kernel<float>);
   int per_sm = 0;
   PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
   PB_REQUIRE(per_sm >= 1, "texture kernel does not fit on an SM");
-  const int grid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(ctx->sm_count) * per_sm, L.n_strokes));
+  const int grid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(ctx->sm_count) * per_sm, L.n_items));
   if (ctx->precision == PB_F64)
     texture_kernel<double><<<grid, 256, 0, ctx->stream>>>(L);
   else

@@ -14,7 +14,8 @@ struct DevTStroke {
   int32_t x0, x1, y0, y1;          // (int)boundMin .. (int)boundMax, TextureBrush.hxx:142-145
   int32_t local_rows, local_cols;  // size of the reference's local thicknessMap (:135-136)
   int32_t poly_begin, n_poly;
-  int32_t pred_begin, pred_end;
+  int32_t tx0, ty0, tx1, ty1;  // canvas tiles covered by the bounding box (inclusive); empty if tx1 < tx0
+  int64_t item_begin;          // first work item (stroke, tile) of this stroke
 };
 
 struct TextureLaunch {
@@ -26,11 +27,17 @@ struct TextureLaunch {
   int64_t n_strokes;
   const double2* poly;
   const double2* uv;
-  const int32_t* preds;
-  int* done;
-  int* queue;
+  // tile-ticket dataflow: item i = (stroke, canvas tile); an item may run when `tile_done[tile] == ticket[i]`,
+  // i.e. when every earlier stroke that covers the tile has finished with it
+  int tile, tiles_x, tiles_y;
+  int64_t n_items;
+  int32_t* ticket;               // per item, filled on the device by texture_ticket_kernel
+  int* tile_done;                // per canvas tile (zeroed)
+  unsigned long long* queue;     // item counter (zeroed)
   unsigned long long* counters;  // [0] deposited stroke-pixels
 };
+
+constexpr int kTextureTile = 64;
 
 void texture_launch(pb_context* ctx, const TextureLaunch& L);
 
