@@ -101,6 +101,15 @@ int pb_canvas_compose(pb_canvas* c, double* out);
 int pb_canvas_compose_device(pb_canvas* c, void* d_out, int64_t plane_stride);
 /* Compose only the owned band rows [row_begin,row_end) into d_out (3 planes, band_rows*cols each). */
 int pb_canvas_compose_band_device(pb_canvas* c, void* d_out, int64_t plane_stride);
+/* Display / IO epilogue fused into the compose kernel: compose -> ColorConverter::rgb2srgb
+ * (core/Color.hxx:198-206) -> quantise, so only 4 (or 3 / 6) bytes per pixel cross PCIe instead of 24.
+ *   pb_canvas_compose_qrgb32: the GUI path (apps/painty_gui/DigitalCanvas.cxx:164-177): qRgb(uint8(r*255), ...) =
+ *     0xffRRGGBB per pixel, truncating cast; out = rows*cols uint32 (host).
+ *   pb_canvas_compose_bgr: the io::imSave path up to the encoder (io/src/ImageIO.cxx:158-191): convertTo with
+ *     scale 0xff (bits = 8) or 0xffff (bits = 16) = round-half-even + saturate, channel order BGR interleaved;
+ *     out = rows*cols*3 uint8 / uint16 (host). srgb = 0 skips the sRGB conversion (convertTo_sRGB = false). */
+int pb_canvas_compose_qrgb32(pb_canvas* c, uint32_t* out);
+int pb_canvas_compose_bgr(pb_canvas* c, int bits, int srgb, void* out);
 /* Device plane pointers (element type of the context): 0-2 K, 3-5 S, 6 V, 7-9 R0, 10 h. */
 int pb_canvas_device_planes(pb_canvas* c, void* planes[11], int64_t* elems_per_plane);
 int pb_canvas_stored_rows(const pb_canvas* c, int* first_row, int* n_rows);

@@ -130,6 +130,22 @@ class Cpu:
         t = self.fn("compose_timed", C.c_double, [C.c_int64] + [_PD] * 5 + [C.c_int])(V.size, _p(K), _p(S), _p(V), _p(R0), _p(out), threads)
         return t, out
 
+    def qrgb32(self, rgb):
+        """linear RGB [.., 3] f64 -> uint32 0xffRRGGBB like DigitalCanvas::updateCanvas."""
+        rgb = _f64(rgb)
+        out = np.empty(rgb.shape[:-1], dtype=np.uint32)
+        self.fn("qrgb32", None, [C.c_int64, _PD, C.c_void_p])(out.size, _p(rgb), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def bgr(self, rgb, bits=8, srgb=True):
+        """io::imSave's pixel path (port only: cv::Mat::convertTo is restated, OpenCV is not available)."""
+        rgb = _f64(rgb)
+        out = np.empty(rgb.shape, dtype=np.uint8 if bits == 8 else np.uint16)
+        f = self.lib.ora_bgr
+        f.restype, f.argtypes = None, [C.c_int64, _PD, C.c_int, C.c_int, C.c_void_p]
+        f(rgb.size // 3, _p(rgb), bits, int(srgb), out.ctypes.data_as(C.c_void_p))
+        return out
+
     # ---- asset registration (ref only; no-ops for the port) -------------------------------------
     def _ensure_footprint(self, radius):
         if self.kind != "ref":

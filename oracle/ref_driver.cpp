@@ -233,6 +233,22 @@ double ref_compose_timed(int64_t n, const double* K, const double* S, const doub
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// ---- display epilogue: the reference's ColorConverter::rgb2srgb + the GUI's qRgb cast ---------------
+// (apps/painty_gui/DigitalCanvas.cxx:164-177; clamped outside [0,255] where the reference's cast is UB)
+void ref_qrgb32(int64_t n, const double* rgb, uint32_t* out) {
+  painty::ColorConverter<double> converter;
+  for (int64_t i = 0; i < n; ++i) {
+    vec3 v(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+    converter.rgb2srgb(v, v);
+    uint32_t q[3];
+    for (size_t c = 0; c < 3; ++c) {
+      const double s = v[c] * 255.0;
+      q[c]           = s >= 255.0 ? 255u : (s > 0.0 ? static_cast<uint32_t>(static_cast<uint8_t>(s)) : 0u);
+    }
+    out[i] = 0xff000000u | (q[0] << 16) | (q[1] << 8) | q[2];
+  }
+}
+
 // ---- Canvas -------------------------------------------------------------------------------------
 void* ref_canvas_create(int rows, int cols) {
   auto* c = new Canvas(rows, cols);

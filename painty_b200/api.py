@@ -261,6 +261,18 @@ class Canvas:
         _chk(lib().pb_canvas_compose(self.h, _p(out)))
         return out
 
+    def compose_qrgb32(self):
+        """compose + rgb2srgb + 8-bit like DigitalCanvas::updateCanvas: uint32 0xffRRGGBB [rows, cols]."""
+        out = np.empty((self.store_rows, self.cols), dtype=np.uint32)
+        _chk(lib().pb_canvas_compose_qrgb32(self.h, out.ctypes.data_as(_VP)))
+        return out
+
+    def compose_bgr(self, bits=8, srgb=True):
+        """compose + (rgb2srgb) + convertTo(8|16 bit) + RGB2BGR like io::imSave before the encoder."""
+        out = np.empty((self.store_rows, self.cols, 3), dtype=np.uint8 if bits == 8 else np.uint16)
+        _chk(lib().pb_canvas_compose_bgr(self.h, bits, int(srgb), out.ctypes.data_as(_VP)))
+        return out
+
     def compose_device(self, d_out_ptr, plane_stride):
         _chk(lib().pb_canvas_compose_device(self.h, _VP(int(d_out_ptr)), C.c_int64(plane_stride)))
 

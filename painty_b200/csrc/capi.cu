@@ -743,6 +743,30 @@ int pb_canvas_compose(pb_canvas* c, double* out) {
   planes_free(r);
   PB_API_END
 }
+namespace {
+void compose_display(pb_canvas* c, int mode, bool srgb, size_t bytes_per_px, void* host_out) {
+  pb_context* ctx = c->pl.ctx;
+  DeviceGuard g(ctx);
+  const int64_t n = c->pl.n();
+  if (n == 0) return;
+  DevBuf<unsigned char> d(ctx, static_cast<size_t>(n) * bytes_per_px);
+  void* none[3] = {nullptr, nullptr, nullptr};
+  km_compose_display(ctx, n, compose_args(c->pl, c->pl, PR, none, 0, ctx->esize()), mode, srgb, d.p);
+  PB_CUDA(cudaMemcpyAsync(host_out, d.p, static_cast<size_t>(n) * bytes_per_px, cudaMemcpyDeviceToHost, ctx->stream));
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+}  // namespace
+int pb_canvas_compose_qrgb32(pb_canvas* c, uint32_t* out) {
+  PB_API_BEGIN
+  compose_display(c, 0, true, 4, out);
+  PB_API_END
+}
+int pb_canvas_compose_bgr(pb_canvas* c, int bits, int srgb, void* out) {
+  PB_API_BEGIN
+  PB_REQUIRE(bits == 8 || bits == 16, "pb_canvas_compose_bgr: bits must be 8 or 16");
+  compose_display(c, bits == 8 ? 1 : 2, srgb != 0, bits == 8 ? 3 : 6, out);
+  PB_API_END
+}
 int pb_canvas_paint_layer(pb_canvas* c, pb_layer** out) {
   PB_API_BEGIN
   auto l        = std::make_unique<pb_layer>();

@@ -207,6 +207,49 @@ __global__ void __launch_bounds__(256) km_stacked_kernel(StackPtrs<T> a, int64_t
   }
 }
 
+// ColorConverter::rgb2srgb (core/Color.hxx:198-206)
+__device__ __forceinline__ float to_srgb(float l) {
+  return l <= 0.00313066844250063f ? l * 12.92f : fmaf(1.055f, powf(l, 1.0f / 2.4f), -0.055f);
+}
+__device__ __forceinline__ double to_srgb(double l) {
+  return l <= 0.00313066844250063 ? l * 12.92 : 1.055 * pow(l, 1.0 / 2.4) - 0.055;
+}
+
+// compose + display epilogue, one pixel per thread (the output is 3-6 B/px against 40 B/px of input)
+template <typename T>
+__global__ void __launch_bounds__(256) km_compose_display_kernel(ComposePtrs<T> a, int64_t n, int mode, bool srgb, void* out) {
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  T r[3] = {__ldcs(a.R0[0] + o), __ldcs(a.R0[1] + o), __ldcs(a.R0[2] + o)};
+  km_pixel(__ldcs(a.K[0] + o), __ldcs(a.K[1] + o), __ldcs(a.K[2] + o), __ldcs(a.S[0] + o), __ldcs(a.S[1] + o), __ldcs(a.S[2] + o),
+           __ldcs(a.V + o), r[0], r[1], r[2]);
+  if (srgb) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r[c] = to_srgb(r[c]);
+  }
+  if (mode == 0) {  // qRgb(static_cast<uint8_t>(v * 255.0)): truncation; out-of-range values are clamped here
+    unsigned q[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const T v = r[c] * static_cast<T>(255.0);
+      q[c]      = v >= static_cast<T>(255.0) ? 255u : (v > static_cast<T>(0) ? static_cast<unsigned>(v) : 0u);
+    }
+    static_cast<unsigned*>(out)[o] = 0xff000000u | (q[0] << 16) | (q[1] << 8) | q[2];
+  } else {  // cv::Mat::convertTo: saturate_cast(cvRound(v * scale)), then RGB -> BGR
+    const T scale = mode == 1 ? static_cast<T>(255.0) : static_cast<T>(65535.0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const T v   = rint(r[c] * scale);  // round half to even like cvRound
+      const T cl  = v < static_cast<T>(0) ? static_cast<T>(0) : (v > scale ? scale : v);
+      const int q = isnan(v) ? 0 : static_cast<int>(cl);
+      if (mode == 1)
+        static_cast<unsigned char*>(out)[3 * o + (2 - c)] = static_cast<unsigned char>(q);
+      else
+        static_cast<unsigned short*>(out)[3 * o + (2 - c)] = static_cast<unsigned short>(q);
+    }
+  }
+}
+
 template <typename T>
 struct DryPtrs {
   T* p[kCanvasPlanes];
@@ -327,6 +370,34 @@ void km_compose(pb_context* ctx, int64_t n, const ComposeArgs& a) {
     compose_t<double>(ctx, n, a);
   else
     compose_t<float>(ctx, n, a);
+}
+
+void km_compose_display(pb_context* ctx, int64_t n, const ComposeArgs& a, int mode, bool srgb, void* out) {
+  if (n <= 0) return;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  if (ctx->precision == PB_F64) {
+    ComposePtrs<double> p;
+    for (int c = 0; c < 3; ++c) {
+      p.K[c]  = static_cast<const double*>(a.K[c]);
+      p.S[c]  = static_cast<const double*>(a.S[c]);
+      p.R0[c] = static_cast<const double*>(a.R0[c]);
+      p.R[c]  = nullptr;
+    }
+    p.V = static_cast<const double*>(a.V);
+    km_compose_display_kernel<double><<<blocks, 256, 0, ctx->stream>>>(p, n, mode, srgb, out);
+  } else {
+    ComposePtrs<float> p;
+    for (int c = 0; c < 3; ++c) {
+      p.K[c]  = static_cast<const float*>(a.K[c]);
+      p.S[c]  = static_cast<const float*>(a.S[c]);
+      p.R0[c] = static_cast<const float*>(a.R0[c]);
+      p.R[c]  = nullptr;
+    }
+    p.V = static_cast<const float*>(a.V);
+    km_compose_display_kernel<float><<<blocks, 256, 0, ctx->stream>>>(p, n, mode, srgb, out);
+  }
+  PB_CUDA(cudaGetLastError());
+  ctx->launches++;
 }
 
 void km_compose_stacked(pb_context* ctx, int64_t n, const StackArgs& a) {

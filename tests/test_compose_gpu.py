@@ -187,3 +187,29 @@ def test_band_canvas_compose(ctx32, ctx64, port, prec):
         ctx.synchronize()
         got = out.cpu().numpy().T.reshape(e - b, cols, 3).astype(np.float64)
         _cmp(got, want[b:e], TOL[prec])
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_display_epilogue(ctx32, ctx64, port, prec):
+    """compose fused with rgb2srgb + quantisation (GUI qRgb path, imSave 8/16-bit BGR path). FP64 mode is exact;
+    in FP32 mode a value within 1e-6 of a quantisation step may land on the neighbouring code (<= 1 LSB, rare)."""
+    from painty_b200 import api
+
+    ctx = [ctx32, ctx64][prec]
+    rows, cols = 90, 131
+    K, S, V, R0 = km_random_planes(rows, cols, seed=15)
+    cv = api.Canvas(ctx, rows, cols)
+    cv.setBackground(R0)
+    cv.upload_layer(K, S, V)
+    want_rgb = port.compose(K, S, V, R0)
+    for got, want in ((cv.compose_qrgb32(), port.qrgb32(want_rgb)), (cv.compose_bgr(8), port.bgr(want_rgb, 8)),
+                      (cv.compose_bgr(16), port.bgr(want_rgb, 16)), (cv.compose_bgr(16, srgb=False), port.bgr(want_rgb, 16, False))):
+        if got.dtype == np.uint32:
+            got = np.stack([(got >> s) & 0xFF for s in (16, 8, 0)], -1).astype(np.int64)
+            want = np.stack([(want >> s) & 0xFF for s in (16, 8, 0)], -1).astype(np.int64)
+        diff = np.abs(got.astype(np.int64) - want.astype(np.int64))
+        if prec:
+            assert diff.max() == 0
+        else:
+            lsb = 1 if got.max() <= 255 else 8  # 16 bit: 1e-4 of 65535 = 6.5 codes
+            assert diff.max() <= lsb and (diff > 0).mean() < (0.01 if lsb == 1 else 1.0)
