@@ -356,7 +356,9 @@ def main():
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "km_compose_kernel<float>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                     "frac": achieved / peak, "peak_source": peak_src,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one 4K launch, ncu --set full (profiles/r01_compose_f32_raw.csv)
+                     "traffic": 401643264 if world == 1 else None, "algorithmic_bytes_per_launch": COMPOSE_BYTES_PER_PX * n_px,
                      "frac_of_8TBs_nominal": achieved / 8000.0},
     }
     if rank == 0 and not args.no_cpu and world == 1:
