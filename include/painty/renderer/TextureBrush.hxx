@@ -1,8 +1,7 @@
 /**
- * Drop-in for painty/renderer/TextureBrush.hxx (reference lines 19-237), smudge off. The stroke-texture sample
- * is still loaded by painty's own BrushStrokeSample (host); the warp + sample + deposit runs on the device.
- * Smudge (reference Smudge.hxx, default-on in the CPU TextureBrush, off in sbr_painter's config) is the next item of
- * enableSmudge(true) makes paintStroke throw instead of silently rendering something else.
+ * Drop-in for painty/renderer/TextureBrush.hxx (reference lines 19-237). The stroke-texture sample is still loaded
+ * by painty's own BrushStrokeSample (host); the warp + sample + deposit and the Smudge walk (renderer/Smudge.hxx,
+ * default-on like the reference, off in sbr_painter's config) run on the device.
  */
 #pragma once
 
@@ -34,9 +33,10 @@ class TextureBrush final : public BrushBase<vector_type> {
   TextureBrush(const std::string& sampleDir) : _brushStrokeSample(sampleDir), _h(std::make_shared<Handle>()) {
     const Mat<double>& m = _brushStrokeSample.getThicknessMap();
     b200::check(pb_tbrush_create(b200::context(), m.rows, m.cols, m.data, &_h->h));
+    b200::check(pb_tbrush_enable_smudge(_h->h, 1));  // TextureBrush.hxx:236: _useSmudge = true
   }
 
-  void setRadius(const double radius) override { pb_tbrush_set_radius(_h->h, radius); }  // reference :33-41
+  void setRadius(const double radius) override { b200::check(pb_tbrush_set_radius(_h->h, radius)); }  // reference :33-41
 
   void dip(const std::array<vector_type, 2UL>& paint) override {  // reference :48-50
     const double K[3] = {paint[0U][0U], paint[0U][1U], paint[0U][2U]}, S[3] = {paint[1U][0U], paint[1U][1U], paint[1U][2U]};
@@ -44,7 +44,6 @@ class TextureBrush final : public BrushBase<vector_type> {
   }
 
   void paintStroke(const std::vector<vec2>& verticesArg, Canvas<vector_type>& canvas) override {  // reference :52-205
-    if (_useSmudge) throw std::runtime_error("painty_b200: Smudge is not implemented on the device path (enableSmudge(false))");
     if (verticesArg.size() < 2UL) return;
     std::vector<double> xy(2 * verticesArg.size());
     for (size_t i = 0; i < verticesArg.size(); ++i) xy[2 * i] = verticesArg[i][0U], xy[2 * i + 1] = verticesArg[i][1U];
@@ -53,11 +52,10 @@ class TextureBrush final : public BrushBase<vector_type> {
     canvas.deviceWritten();
   }
 
-  void enableSmudge(const bool enable) { _useSmudge = enable; }
+  void enableSmudge(const bool enable) { b200::check(pb_tbrush_enable_smudge(_h->h, enable ? 1 : 0)); }
 
  private:
   BrushStrokeSample _brushStrokeSample;
   std::shared_ptr<Handle> _h;
-  bool _useSmudge = false;  // the reference defaults to true (TextureBrush.hxx:236); see the header comment
 };
 }  // namespace painty

@@ -206,13 +206,18 @@ int pb_fbrush_dist_storage(pb_fbrush* b, pb_canvas* c, void** snapshot_base, int
 int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* dist, int64_t n_strokes, const pb_stroke* strokes,
                                 int64_t n_imprints, const double* cx, const double* cy, const double* theta);
 
-/* ---- TextureBrush (smudge off; Smudge is SURVEY.md §8f) ---------------------------------------- */
+/* ---- TextureBrush -------------------------------------------------------------------------------- */
 /* thickness map: rows*cols host f64 (BrushStrokeSample::getThicknessMap). */
 int pb_tbrush_create(pb_context* ctx, int map_rows, int map_cols, const double* thickness_map, pb_tbrush** out);
 int pb_tbrush_destroy(pb_tbrush* b);
 int pb_tbrush_set_radius(pb_tbrush* b, double radius); /* TextureBrush.hxx:33-41 */
 int pb_tbrush_dip(pb_tbrush* b, const double K[3], const double S[3]);
 int pb_tbrush_set_thickness_scale(pb_tbrush* b, double scale); /* BrushBase.hxx:24-30 */
+/* TextureBrush::enableSmudge (TextureBrush.hxx:207) + renderer/Smudge.hxx. Off by default here (the CPU class
+ * defaults to on, sbr_painter's config to off). The smudge windows are (re)created by the next set_radius that acts
+ * while smudge is enabled, exactly like the reference (TextureBrush.hxx:36-40). With smudge on, strokes form a serial
+ * chain (the windows carry over from stroke to stroke). */
+int pb_tbrush_enable_smudge(pb_tbrush* b, int enable);
 /* TextureBrush::paintStroke (TextureBrush.hxx:52-205), path = n*2 doubles. */
 int pb_tbrush_paint_stroke(pb_tbrush* b, pb_canvas* c, int n, const double* path_xy);
 typedef struct pb_tstroke {

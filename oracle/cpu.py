@@ -309,6 +309,9 @@ class CpuTextureBrush:
     def set_thickness_scale(self, s):
         self.cpu.fn("tbrush_set_thickness_scale", None, [C.c_void_p, C.c_double])(self.h, s)
 
+    def enable_smudge(self, enable):
+        self.cpu.fn("tbrush_enable_smudge", None, [C.c_void_p, C.c_int])(self.h, int(enable))
+
     def paint_stroke(self, canvas, path):
         path = _f64(path).reshape(-1, 2)
         return self.cpu.fn("tbrush_paint_stroke", C.c_double, [C.c_void_p, C.c_void_p, C.c_int, _PD])(self.h, canvas.h, len(path), _p(path))

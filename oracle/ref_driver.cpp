@@ -343,6 +343,7 @@ void* ref_tbrush_create(const char* sample_dir, int enable_smudge) {
 }
 void ref_tbrush_destroy(void* b) { delete static_cast<TBrush*>(b); }
 void ref_tbrush_set_radius(void* b, double r) { static_cast<TBrush*>(b)->setRadius(r); }
+void ref_tbrush_enable_smudge(void* b, int enable) { static_cast<TBrush*>(b)->enableSmudge(enable != 0); }
 void ref_tbrush_dip(void* b, const double* K, const double* S) {
   static_cast<TBrush*>(b)->dip({vec3(K[0], K[1], K[2]), vec3(S[0], S[1], S[2])});
 }

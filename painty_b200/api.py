@@ -405,13 +405,16 @@ class TextureBrush:
             self.h = None
 
     def setRadius(self, r):
-        lib().pb_tbrush_set_radius(self.h, C.c_double(r))
+        _chk(lib().pb_tbrush_set_radius(self.h, C.c_double(r)))
 
     def dip(self, paint):
         lib().pb_tbrush_dip(self.h, _d3(paint[0]), _d3(paint[1]))
 
     def setThicknessScale(self, s):
         lib().pb_tbrush_set_thickness_scale(self.h, C.c_double(s))
+
+    def enableSmudge(self, enable):
+        lib().pb_tbrush_enable_smudge(self.h, int(bool(enable)))
 
     def paintStroke(self, path, canvas):
         path = _f64(path).reshape(-1, 2)

@@ -123,7 +123,14 @@ struct pb_tbrush {
   double paintK[3] = {0.1, 0.1, 0.1}, paintS[3] = {0.1, 0.1, 0.1};      // TextureBrush.hxx:29-31
   int map_rows = 0, map_cols = 0;
   double* d_map = nullptr;
-  unsigned long long* d_counters = nullptr;
+  unsigned long long* d_counters = nullptr;  // [0] deposited stroke-pixels, [1] scratch: max thickness bits
+  // Smudge (renderer/Smudge.hxx): two ping-pong pickup windows of size x size, state carried across strokes
+  bool use_smudge       = false;  // the reference defaults to true (TextureBrush.hxx:236), see INTEGRATION.md
+  int smudge_size       = 0;      // Smudge(0) as built by TextureBrush's ctor (:27): empty maps, _maxSize = 1
+  int smudge_max_size   = 1;
+  int smudge_dst        = 0;      // which window currently is _pickupMapDst
+  double smudge_rotation = 0.0;   // Smudge::_currentRotation
+  pb_planes smudge_map[2];
 };
 
 namespace {
@@ -1109,6 +1116,95 @@ int pb_fbrush_counters(pb_fbrush* b, uint64_t* visited, uint64_t* active) {
 }
 
 // ---- TextureBrush -----------------------------------------------------------------------------------------
+namespace {
+// TextureBrush::paintStroke with _useSmudge (TextureBrush.hxx:52-205 + Smudge.hxx). The smudge windows and their
+// orientation carry over from stroke to stroke, so strokes are a serial chain: per stroke a parallel thickness pass,
+// the serial walk along the spine (one cluster), and a parallel deposit pass, all ordered by the stream.
+void smudge_strokes(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const pb_tstroke* strokes, int64_t n_vertices,
+                    const double* path_xy) {
+  pb_context* ctx = b->ctx;
+  double radius   = b->radius;
+  for (int64_t s = 0; s < n_strokes; ++s) {
+    const pb_tstroke& in = strokes[s];
+    PB_REQUIRE(in.first_vertex >= 0 && in.n_vertices >= 0 && in.first_vertex + in.n_vertices <= n_vertices,
+               "stroke vertex range out of bounds");
+    if (!(std::fabs(radius - in.radius) < 0.5)) {
+      PB_REQUIRE(pb_tbrush_set_radius(b, in.radius) == 0, pb_last_error());
+      radius = b->radius;
+    }
+    for (int i = 0; i < 3; ++i) {
+      b->paintK[i] = in.K[i];
+      b->paintS[i] = in.S[i];
+    }
+    const host::TextureFrame f = host::build_texture_frame(reinterpret_cast<const host::V2*>(path_xy) + in.first_vertex,
+                                                           in.n_vertices, radius, c->rows, c->cols);
+    if (!f.valid) continue;
+    PB_REQUIRE(f.poly.size() <= static_cast<size_t>(kMaxPoly), "stroke has too many vertices (max 510 per stroke)");
+    SmudgeLaunch L{};
+    for (int p = 0; p < kLayerPlanes; ++p) L.canvas[p] = c->pl.plane(p);
+    L.rows        = c->rows;
+    L.cols        = c->cols;
+    L.store_first = c->store_first;
+    L.store_rows  = c->pl.rows;
+    L.map         = b->d_map;
+    L.map_rows    = b->map_rows;
+    L.map_cols    = b->map_cols;
+    DevTStroke& d = L.stroke;
+    for (int i = 0; i < 3; ++i) {
+      d.K[i] = in.K[i];
+      d.S[i] = in.S[i];
+    }
+    d.thickness_scale = in.thickness_scale;
+    d.x0 = f.x0, d.x1 = f.x1, d.y0 = f.y0, d.y1 = f.y1;
+    d.local_rows = std::max(f.local_rows, 0);
+    d.local_cols = std::max(f.local_cols, 0);
+    d.poly_begin = 0;
+    d.n_poly     = static_cast<int32_t>(f.poly.size());
+    const size_t n_local = static_cast<size_t>(d.local_rows) * d.local_cols;
+    DevBuf<double2> d_poly(ctx, f.poly.size()), d_uv(ctx, f.uv.size());
+    DevBuf<double> d_tmap(ctx, n_local);
+    d_poly.upload(reinterpret_cast<const double2*>(f.poly.data()), f.poly.size());
+    d_uv.upload(reinterpret_cast<const double2*>(f.uv.data()), f.uv.size());
+    d_tmap.zero(n_local);
+    PB_CUDA(cudaMemsetAsync(b->d_counters + 1, 0, sizeof(unsigned long long), ctx->stream));
+    L.poly     = d_poly.p;
+    L.uv       = d_uv.p;
+    L.tmap     = d_tmap.p;
+    L.max_bits = b->d_counters + 1;
+    L.counters = b->d_counters;
+    c->version++;
+    texture_thickness_launch(ctx, L);
+    // Smudge::smudge returns before touching its state when the stroke deposits nothing (:41-47)
+    unsigned long long max_bits = 0;
+    PB_CUDA(cudaMemcpyAsync(&max_bits, b->d_counters + 1, sizeof(max_bits), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    double maxD;
+    std::memcpy(&maxD, &max_bits, sizeof(maxD));
+    std::vector<host::SmudgeStep> steps;
+    if (maxD > 0.0) host::build_smudge_steps(f, b->smudge_size, b->smudge_rotation, steps);
+    static_assert(sizeof(host::SmudgeStep) == sizeof(DevSmudgeStep), "SmudgeStep layout");
+    DevBuf<DevSmudgeStep> d_steps(ctx, steps.size());
+    d_steps.upload(reinterpret_cast<const DevSmudgeStep*>(steps.data()), steps.size());
+    if (!steps.empty() && b->smudge_size > 0) {
+      for (int w = 0; w < 2; ++w)
+        for (int p = 0; p < kLayerPlanes; ++p) L.pick[w][p] = b->smudge_map[w].plane(p);
+      L.size            = b->smudge_size;
+      L.max_size        = b->smudge_max_size;
+      L.first_dst       = b->smudge_dst;
+      L.steps           = d_steps.p;
+      L.n_steps         = static_cast<int>(steps.size());
+      L.bmin_x          = f.bound_min.x;
+      L.bmin_y          = f.bound_min.y;
+      L.pickup_rate     = 0.1;  // Smudge.hxx:156-158
+      L.deposition_rate = 0.1;
+      texture_smudge_launch(ctx, L);
+      b->smudge_dst = (b->smudge_dst + L.n_steps) & 1;
+    }
+    texture_deposit_launch(ctx, L);
+  }
+}
+}  // namespace
+
 int pb_tbrush_create(pb_context* ctx, int map_rows, int map_cols, const double* thickness_map, pb_tbrush** out) {
   PB_API_BEGIN
   DeviceGuard g(ctx);
@@ -1119,8 +1215,8 @@ int pb_tbrush_create(pb_context* ctx, int map_rows, int map_cols, const double* 
   b->map_cols = map_cols;
   PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_map), sizeof(double) * map_rows * map_cols));
   PB_CUDA(cudaMemcpyAsync(b->d_map, thickness_map, sizeof(double) * map_rows * map_cols, cudaMemcpyHostToDevice, ctx->stream));
-  PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_counters), sizeof(unsigned long long)));
-  PB_CUDA(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+  PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_counters), 2 * sizeof(unsigned long long)));
+  PB_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
   PB_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = b.release();
   PB_API_END
@@ -1132,12 +1228,37 @@ int pb_tbrush_destroy(pb_tbrush* b) {
     PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
     cudaFree(b->d_map);
     cudaFree(b->d_counters);
+    planes_free(b->smudge_map[0]);
+    planes_free(b->smudge_map[1]);
     delete b;
   }
   PB_API_END
 }
 int pb_tbrush_set_radius(pb_tbrush* b, double radius) {
-  if (!(std::fabs(b->radius - radius) < 0.5)) b->radius = radius;  // TextureBrush.hxx:33-41
+  PB_API_BEGIN
+  if (!(std::fabs(b->radius - radius) < 0.5)) {  // TextureBrush.hxx:33-41
+    b->radius = radius;
+    if (b->use_smudge) {  // _smudge = Smudge(int(2 * radius)): fresh, clean windows
+      DeviceGuard g(b->ctx);
+      const int size = static_cast<int32_t>(2.0 * radius);
+      PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+      for (auto& m : b->smudge_map) {
+        planes_free(m);
+        if (size > 0) {
+          planes_alloc(b->ctx, m, size, size, kLayerPlanes);
+          for (int p = 0; p < kLayerPlanes; ++p) fill_plane(b->ctx, m.plane(p), m.n(), 0.0);
+        }
+      }
+      b->smudge_size     = size;
+      b->smudge_max_size = (size % 2 == 0) ? size + 1 : size;  // Smudge.hxx:25-27
+      b->smudge_dst      = 0;
+      b->smudge_rotation = 0.0;
+    }
+  }
+  PB_API_END
+}
+int pb_tbrush_enable_smudge(pb_tbrush* b, int enable) {
+  b->use_smudge = enable != 0;
   return 0;
 }
 int pb_tbrush_dip(pb_tbrush* b, const double K[3], const double S[3]) {
@@ -1158,6 +1279,10 @@ int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const 
   DeviceGuard g(ctx);
   PB_REQUIRE(c->pl.ctx == ctx, "canvas and brush belong to different contexts");
   if (n_strokes <= 0) return 0;
+  if (b->use_smudge) {
+    smudge_strokes(b, c, n_strokes, strokes, n_vertices, path_xy);
+    return 0;
+  }
   std::vector<DevTStroke> ds;
   ds.reserve(static_cast<size_t>(n_strokes));
   std::vector<host::V2> poly, uv;

@@ -41,4 +41,31 @@ constexpr int kTextureTile = 64;
 
 void texture_launch(pb_context* ctx, const TextureLaunch& L);
 
+// ---- smudge path (Smudge.hxx): a stroke = thickness pass -> serial smudge walk -> deposit pass -----------------
+struct DevSmudgeStep {
+  double cx, cy, c, s;
+  int32_t roi_x, roi_y;
+};
+struct SmudgeLaunch {
+  void* canvas[kLayerPlanes];
+  int rows, cols, store_first, store_rows;
+  const double* map;  // stroke texture (thickness sample), f64
+  int map_rows, map_cols;
+  DevTStroke stroke;  // one stroke at a time: the smudge state chains strokes serially
+  const double2* poly;
+  const double2* uv;
+  double* tmap;  // the reference's local thicknessMap (local_rows x local_cols, f64, zeroed)
+  unsigned long long* max_bits;  // max over tmap as the bit pattern of a non-negative double (zeroed)
+  unsigned long long* counters;
+  // smudge state
+  void* pick[2][kLayerPlanes];  // ping-pong pickup windows (size x size)
+  int size, max_size, first_dst;
+  const DevSmudgeStep* steps;
+  int n_steps;
+  double bmin_x, bmin_y, pickup_rate, deposition_rate;
+};
+void texture_thickness_launch(pb_context* ctx, const SmudgeLaunch& L);
+void texture_smudge_launch(pb_context* ctx, const SmudgeLaunch& L);
+void texture_deposit_launch(pb_context* ctx, const SmudgeLaunch& L);
+
 }  // namespace pb

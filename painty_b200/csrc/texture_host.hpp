@@ -16,7 +16,43 @@ struct TextureFrame {
   std::vector<V2> poly, uv;  // 2*(n+2) each
   int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
   int local_rows = 0, local_cols = 0;
+  V2 bound_min   = {0.0, 0.0};  // boundMin as handed to Smudge::smudge
+  double length  = 0.0;         // polyline length of the extended vertices (:86-89)
+  std::vector<V2> spine;        // extended vertices (control points of the spine spline)
 };
+
+// One step of Smudge::smudge's walk along the spine (Smudge.hxx:48-60, 161-166): everything that does not depend on
+// pixel data is evaluated on the host in f64.
+struct SmudgeStep {
+  double cx, cy;    // spine position
+  double c, s;      // cos / sin of the window rotation of this step (dtheta)
+  int32_t roi_x, roi_y;
+};
+
+// `rotation` is Smudge::_currentRotation (carried from stroke to stroke); size = map side, as in Smudge.hxx.
+inline void build_smudge_steps(const TextureFrame& f, int size, double& rotation, std::vector<SmudgeStep>& out) {
+  const double pi = 3.141592653589793238462643383279502884197169399375105820974L;
+  const SplineEval spine{f.spine.data(), static_cast<int>(f.spine.size())};
+  for (double u = 0.0; u <= 1.0; u += 1. / f.length) {
+    const V2 center = spine.catmullRom(u);
+    V2 t            = spine.catmullRomDerivativeFirst(u);
+    const double tn = norm(t);
+    t               = {t.x / tn, t.y / tn};
+    const double theta = std::atan2(t.y, t.x);  // updateOrientation :161-166
+    double dtheta      = theta - rotation;
+    while (dtheta <= -0.5 * pi) dtheta += pi;  // normalizeAngle :201-211
+    while (dtheta > 0.5 * pi) dtheta -= pi;
+    rotation = theta;
+    SmudgeStep st;
+    st.cx    = center.x;
+    st.cy    = center.y;
+    st.c     = std::cos(dtheta);
+    st.s     = std::sin(dtheta);
+    st.roi_x = static_cast<int32_t>(center.x - size / 2.0);
+    st.roi_y = static_cast<int32_t>(center.y - size / 2.0);
+    out.push_back(st);
+  }
+}
 
 inline TextureFrame build_texture_frame(const V2* in, int n_in, double radius, int canvas_rows, int canvas_cols) {
   TextureFrame f;
@@ -66,6 +102,9 @@ inline TextureFrame build_texture_frame(const V2* in, int n_in, double radius, i
   f.y1 = static_cast<int32_t>(hi.y);
   f.local_rows = static_cast<int32_t>(hi.y - lo.y + 1);  // :135-136
   f.local_cols = static_cast<int32_t>(hi.x - lo.x + 1);
+  f.bound_min  = lo;
+  for (int i = 1; i < n; ++i) f.length += norm({v[i].x - v[i - 1].x, v[i].y - v[i - 1].y});
+  f.spine      = v;
   f.valid      = true;
   return f;
 }

@@ -8,6 +8,7 @@ The reference's own tests pin no pixel of imprint / texture deposit / whole-imag
 Contents: inputs (seeded), checksums and crops of the outputs for
   gui_*   : painty_gui style 3-point footprint stroke, r=30, 768x1024
   tex_*   : TextureBrushTest stroke (r=40) + a crossing stroke (r=25), smudge off
+  texs_*  : TextureBrushTest exactly as the reference runs it (smudge on, the CPU class's default)
   km_*    : 4096 random pixels through Renderer::compose incl. edge cases (d=0, S=0, K=0 -> NaN)
   brd_*   : footprint stroke overhanging the top-left border with fractional centres (B#11), r=11 (an OOB-free radius)
 """
@@ -52,6 +53,17 @@ def main():
     st = cv.get()
     out.update(tex_sumR=R.sum(), tex_sumV=st["V"].sum(), tex_wet=(st["V"] > 0).sum(), tex_R_crop=R[200:300, 300:400].copy(),
                tex_V_crop=st["V"][200:300, 300:400].copy(), tex_R_rowsum=R.sum(axis=(1, 2)), tex_R_colsum=R.sum(axis=(0, 2)))
+    # --- the reference's TextureBrushTest as written: smudge ON (the CPU class's default), radius 40
+    cv = ref.canvas(768, 1024)
+    tb = ref.texture_brush()
+    tb.enable_smudge(True)
+    tb.dip([.2, .3, .4], [.1, .23, .14])
+    tb.set_radius(40.0)
+    tb.paint_stroke(cv, [(50, 250), (400, 250), (650, 250)])
+    R = cv.compose()
+    st = cv.get()
+    out.update(texs_sumR=R.sum(), texs_sumV=st["V"].sum(), texs_wet=(st["V"] > 0).sum(), texs_R_crop=R[200:300, 300:400].copy(),
+               texs_V_crop=st["V"][200:300, 300:400].copy(), texs_R_colsum=R.sum(axis=(0, 2)))
     # --- compose, random + edge cases
     Kp, Sp, Vp, R0p = km_random_planes(64, 64, seed=7, edge_cases=True)
     out.update(km_K=Kp, km_S=Sp, km_V=Vp, km_R0=R0p, km_R=ref.compose(Kp, Sp, Vp, R0p))

@@ -66,3 +66,70 @@ def test_texture_batch_matches_sequential_oracle(ctx32, ctx64, port, prec):
     import ctypes as C
 
     assert tb.counters() == port.fn("tbrush_pixels", C.c_uint64, [C.c_void_p])(tbo.h)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_smudge_matches_oracle(ctx32, ctx64, port, prec):
+    """renderer/Smudge.hxx on the device: the pickup windows persist across strokes, are re-created by a radius
+    change, smudge can be switched off and on between strokes, strokes run off the canvas."""
+    from painty_b200 import api
+
+    ctx = [ctx32, ctx64][prec]
+    rows, cols = 300, 400
+    cv, cvo = api.Canvas(ctx, rows, cols), port.canvas(rows, cols)
+    bg = np.random.default_rng(6).uniform(0.3, 1.0, (rows, cols, 3))
+    cv.setBackground(bg)
+    cvo.set_background(bg)
+    tb, tbo = api.TextureBrush(ctx), port.texture_brush()
+    tb.enableSmudge(True)
+    tbo.enable_smudge(True)
+
+    def both(fn_dev, fn_cpu):
+        fn_dev(tb)
+        fn_cpu(tbo)
+
+    script = [
+        (20.0, ([.2, .3, .4], [.1, .23, .14]), 0.8, [(30, 150), (200, 140), (350, 180)], True),
+        (20.0, ([.5, .1, .2], [.3, .2, .5]), 0.8, [(150.5, 20.2), (180.1, 120.7), (170.3, 200.9), (220.0, 280.5)], True),
+        (11.0, ([.1, .6, .2], [.3, .2, .1]), 0.4, [(50.5, 220.2), (380.1, 100.7)], True),
+        (11.0, ([.3, .3, .3], [.2, .2, .2]), 0.4, [(10, 10), (100, 60)], False),
+        (11.2, ([.6, .1, .1], [.1, .2, .3]), 1.0, [(390, 290), (300, 200), (320, 100)], True),
+        (7.0, ([.2, .2, .6], [.3, .1, .2]), 0.0, [(100, 100), (200, 100)], True),  # deposits nothing: smudge state untouched
+        (7.0, ([.2, .2, .6], [.3, .1, .2]), 0.9, [(-30, 50), (60, 80), (420, 40)], True),
+    ]
+    for radius, (K, S), scale, path, smudge in script:
+        tb.enableSmudge(smudge)
+        tbo.enable_smudge(smudge)
+        tb.setRadius(radius)
+        tbo.set_radius(radius)
+        tb.dip((K, S))
+        tbo.dip(K, S)
+        tb.setThicknessScale(scale)
+        tbo.set_thickness_scale(scale)
+        tb.paintStroke(path, cv)
+        tbo.paint_stroke(cvo, path)
+    a, b = cv.download("KSV"), cvo.get()
+    if prec:
+        for k in "KSV":
+            assert np.abs(a[k] - b[k]).max() <= 1e-12, k
+    assert np.abs(cv.compose() - cvo.compose()).max() <= TOL[prec]
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_texture_brush_test_with_smudge_fixture(ctx32, ctx64, golden, prec):
+    """The reference's TextureBrushTest as written (smudge on), against the fixture produced by the reference."""
+    from painty_b200 import api
+
+    ctx = [ctx32, ctx64][prec]
+    cv = api.Canvas(ctx, 768, 1024)
+    tb = api.TextureBrush(ctx)
+    tb.enableSmudge(True)
+    tb.dip(([.2, .3, .4], [.1, .23, .14]))
+    tb.setRadius(40.0)
+    tb.paintStroke([(50, 250), (400, 250), (650, 250)], cv)
+    R = cv.compose()
+    st = cv.download("V")
+    assert (st["V"] > 0).sum() == int(golden["texs_wet"])
+    assert np.abs(R[200:300, 300:400] - golden["texs_R_crop"]).max() <= TOL[prec]
+    assert np.abs(R.sum(axis=(0, 2)) - golden["texs_R_colsum"]).max() <= TOL[prec] * 768 * 3
+    assert np.abs(st["V"][200:300, 300:400] - golden["texs_V_crop"]).max() <= (1e-12 if prec else 1e-5)
