@@ -18,6 +18,7 @@
 #include "painty/renderer/FootprintBrush.hxx"
 #include "painty/renderer/PaintLayer.hxx"
 #include "painty/renderer/Renderer.hxx"
+#include "painty/renderer/SbrRenderThreadCuda.hxx"
 #include "painty/renderer/TextureBrush.hxx"
 // reference host code the façade keeps using
 #include "painty/image/src/TextureWarp.cxx"
@@ -162,6 +163,25 @@ int main(int argc, char** argv) {
     double sum2     = 0.0;
     for (const auto& p : rgb2) sum2 += p[0] + p[1] + p[2];
     EXPECT(std::fabs(sum2 - sum) > 1.0 && sum2 == sum2);
+  }
+  {  // sbr_painter's render-thread interface (SbrRenderThread.hxx:19-74): same two strokes, batched, == the brush path
+    painty::SbrRenderThreadCuda rt(painty::Size{1024U, 768U});
+    EXPECT(rt.getSize().width == 1024U && rt.getSize().height == 768U);
+    rt.setBrushThicknessScale(1.0);
+    rt.enableSmudge(false);
+    rt.render({{50, 250}, {400, 250}, {650, 250}}, 40.0, {painty::vec3(.2, .3, .4), painty::vec3(.1, .23, .14)});
+    rt.render({{300.5, 50.2}, {350.1, 200.7}, {330.3, 400.9}, {420.0, 600.5}}, 25.0, {painty::vec3(.5, .1, .2), painty::vec3(.3, .2, .5)})
+      .wait();
+    const painty::Mat3d rgb = rt.getLinearRgbImage().get();
+    double sum              = 0.0;
+    for (const auto& p : rgb) sum += p[0] + p[1] + p[2];
+    std::printf("sbr thread sumR %.6f (want %.6f)\n", sum, want_tex);
+    EXPECT(std::fabs(sum - want_tex) < 3.0);
+    rt.dryCanvas().wait();
+    const painty::Mat3d dried = rt.getLinearRgbImage().get();
+    double sum2               = 0.0;
+    for (const auto& p : dried) sum2 += p[0] + p[1] + p[2];
+    EXPECT(std::fabs(sum2 - sum) < 1.0);  // drying moves the paint into the substrate, the picture stays
   }
   {  // error translation: invalid_argument like KubelkaMunk.hxx:98
     double K[3], S[3];
