@@ -1,7 +1,7 @@
 /**
  * Drop-in for painty/renderer/Renderer.hxx (reference lines 15-158): compose() runs the fused streaming
- * Kubelka-Munk kernel and returns a host Mat by value like the reference. render() (directional-light
- * relighting, reference :60-156) is outside the accelerated path and is not provided.
+ * Kubelka-Munk kernel, render() the same kernel with the directional-light relighting (reference :60-156) fused
+ * behind it; both return a host Mat by value like the reference.
  */
 #pragma once
 
@@ -30,6 +30,13 @@ class Renderer final {
     Mat<vector_type> R1(canvas.getPaintLayer().getRows(), canvas.getPaintLayer().getCols());
     b200::check(pb_canvas_compose(canvas.device(), reinterpret_cast<double*>(R1.data)));
     return R1;
+  }
+
+  /** Render the canvas with directional light (reference :60-156). */
+  Mat<vector_type> render(const Canvas<vector_type>& canvas) const {
+    Mat<vector_type> rgb(canvas.getPaintLayer().getRows(), canvas.getPaintLayer().getCols());
+    b200::check(pb_canvas_render(canvas.device(), reinterpret_cast<double*>(rgb.data)));
+    return rgb;
   }
 };
 }  // namespace painty

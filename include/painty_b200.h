@@ -110,6 +110,10 @@ int pb_canvas_compose_band_device(pb_canvas* c, void* d_out, int64_t plane_strid
  *     out = rows*cols*3 uint8 / uint16 (host). srgb = 0 skips the sRGB conversion (convertTo_sRGB = false). */
 int pb_canvas_compose_qrgb32(pb_canvas* c, uint32_t* out);
 int pb_canvas_compose_bgr(pb_canvas* c, int bits, int srgb, void* out);
+/* Renderer::render(canvas) (renderer/Renderer.hxx:60-156): compose + directional-light relighting (Beckmann /
+ * Cook-Torrance, the wet layer's thickness as height field, 5-tap BORDER_REFLECT normal) fused in one kernel; host
+ * AoS f64 out, clamped to [0,1] like the reference. Full canvases only (the stencil needs the neighbouring rows). */
+int pb_canvas_render(pb_canvas* c, double* out);
 /* Device plane pointers (element type of the context): 0-2 K, 3-5 S, 6 V, 7-9 R0, 10 h. */
 int pb_canvas_device_planes(pb_canvas* c, void* planes[11], int64_t* elems_per_plane);
 int pb_canvas_stored_rows(const pb_canvas* c, int* first_row, int* n_rows);

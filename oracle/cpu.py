@@ -221,6 +221,11 @@ class CpuCanvas:
         self.cpu.fn("canvas_compose", None, [C.c_void_p, _PD])(self.h, _p(out))
         return out
 
+    def render(self):
+        out = np.empty((self.rows, self.cols, 3))
+        self.cpu.fn("canvas_render", None, [C.c_void_p, _PD])(self.h, _p(out))
+        return out
+
 
 class CpuFootprintBrush:
     def __init__(self, cpu, radius):

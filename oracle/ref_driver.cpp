@@ -285,6 +285,13 @@ void ref_canvas_compose(void* cv, double* out) {
     for (size_t ch = 0; ch < 3; ++ch) out[3 * i + static_cast<int32_t>(ch)] = r1(i)[ch];
 }
 
+void ref_canvas_render(void* cv, double* out) {  // Renderer::render (Renderer.hxx:60-156)
+  auto* c                    = static_cast<Canvas*>(cv);
+  const painty::Mat<vec3> r1 = painty::Renderer<vec3>().render(*c);
+  for (int32_t i = 0; i < static_cast<int32_t>(r1.total()); ++i)
+    for (size_t ch = 0; ch < 3; ++ch) out[3 * i + static_cast<int32_t>(ch)] = r1(i)[ch];
+}
+
 // ---- FootprintBrush -----------------------------------------------------------------------------
 // The footprint for ceil(radius) must have been registered with ref_register_resize(width,width)
 // and "./data/footprint/footprint.png" with ref_register_image (any content; it only feeds resize).

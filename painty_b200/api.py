@@ -261,6 +261,12 @@ class Canvas:
         _chk(lib().pb_canvas_compose(self.h, _p(out)))
         return out
 
+    def render(self):
+        """Renderer::render(canvas): compose + directional-light relighting -> host AoS f64 [rows, cols, 3]."""
+        out = np.empty((self.store_rows, self.cols, 3))
+        _chk(lib().pb_canvas_render(self.h, _p(out)))
+        return out
+
     def compose_qrgb32(self):
         """compose + rgb2srgb + 8-bit like DigitalCanvas::updateCanvas: uint32 0xffRRGGBB [rows, cols]."""
         out = np.empty((self.store_rows, self.cols), dtype=np.uint32)
@@ -287,7 +293,10 @@ class Canvas:
 
 
 class Renderer:
-    """painty::Renderer<vec3>::compose (renderer/Renderer.hxx:26-53)."""
+    """painty::Renderer<vec3>: compose (renderer/Renderer.hxx:26-53) and render (:60-156)."""
+
+    def render(self, canvas):
+        return canvas.render()
 
     def compose(self, a, R0=None):
         if isinstance(a, Canvas):

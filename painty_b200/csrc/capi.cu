@@ -763,6 +763,24 @@ void compose_display(pb_canvas* c, int mode, bool srgb, size_t bytes_per_px, voi
   PB_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 }  // namespace
+int pb_canvas_render(pb_canvas* c, double* out) {
+  PB_API_BEGIN
+  pb_context* ctx = c->pl.ctx;
+  DeviceGuard g(ctx);
+  PB_REQUIRE(c->store_first == 0 && c->pl.rows == c->rows, "pb_canvas_render needs a full canvas (not a band)");
+  pb_planes r;
+  planes_alloc(ctx, r, c->pl.rows, c->pl.cols, 3);
+  try {
+    void* o[3] = {r.plane(0), r.plane(1), r.plane(2)};
+    km_render(ctx, c->pl.rows, c->pl.cols, compose_args(c->pl, c->pl, PR, o, 0, ctx->esize()));
+    download_aos(ctx, r, 0, 3, out);
+  } catch (...) {
+    planes_free(r);
+    throw;
+  }
+  planes_free(r);
+  PB_API_END
+}
 int pb_canvas_compose_qrgb32(pb_canvas* c, uint32_t* out) {
   PB_API_BEGIN
   compose_display(c, 0, true, 4, out);

@@ -113,6 +113,8 @@ void km_compose_stacked(pb_context* ctx, int64_t n, const StackArgs& a);
 // compose + rgb2srgb + quantise into `out` (device). mode 0: uint32 0xffRRGGBB (truncating cast); mode 1 / 2:
 // BGR interleaved uint8 / uint16 with round-half-even + saturation; srgb = false skips the transfer curve.
 void km_compose_display(pb_context* ctx, int64_t n, const ComposeArgs& a, int mode, bool srgb, void* out);
+// Renderer::render: R = light(KM(K,S,V over R0), height = V), rows x cols image, R planes out
+void km_render(pb_context* ctx, int rows, int cols, const ComposeArgs& a);
 // Canvas::dryCanvas: h += V; R0 = KM(K,S,R0,V); K=S=V=0
 void km_dry(pb_context* ctx, int64_t n, void* const planes[11]);
 

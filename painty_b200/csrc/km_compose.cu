@@ -250,6 +250,83 @@ __global__ void __launch_bounds__(256) km_compose_display_kernel(ComposePtrs<T> 
   }
 }
 
+// Renderer::render (renderer/Renderer.hxx:60-156) per pixel, after the fused compose. Operation order follows the
+// reference (3-vector reductions left to right). T = float uses the single-precision libm-equivalents.
+template <typename T>
+struct V3 {
+  T x, y, z;
+};
+template <typename T>
+__device__ __forceinline__ T dot3(const V3<T>& a, const V3<T>& b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z;
+}
+template <typename T>
+__device__ __forceinline__ V3<T> normalized(const V3<T>& a) {
+  const T n = sqrt(dot3(a, a));
+  return {a.x / n, a.y / n, a.z / n};
+}
+__device__ __forceinline__ int reflect_idx(int p, int len) {  // cv::borderInterpolate(BORDER_REFLECT)
+  if (static_cast<unsigned>(p) < static_cast<unsigned>(len)) return p;
+  if (len == 1) return 0;
+  do {
+    p = (p < 0) ? (-p - 1) : (len - 1 - (p - len));
+  } while (static_cast<unsigned>(p) >= static_cast<unsigned>(len));
+  return p;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) km_render_kernel(ComposePtrs<T> a, int rows, int cols) {
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (o >= static_cast<int64_t>(rows) * cols) return;
+  const int i = static_cast<int>(o / cols), j = static_cast<int>(o - static_cast<int64_t>(i) * cols);
+  // compose (Kd)
+  T kd[3] = {a.R0[0][o], a.R0[1][o], a.R0[2][o]};
+  const T s11 = a.V[o];
+  km_pixel(a.K[0][o], a.K[1][o], a.K[2][o], a.S[0][o], a.S[1][o], a.S[2][o], s11, kd[0], kd[1], kd[2]);
+  // Interpolate() at integer offsets degenerates to the reflected neighbour (:99-107)
+  auto H = [&](int y, int x) {
+    const int xx = reflect_idx(x, cols), yy = reflect_idx(y, rows);
+    // bilinear with zero fractional part: (v00*(1-0) + v01*0)*(1-0) + (v10*(1-0) + v11*0)*0
+    const int x1 = reflect_idx(x + 1, cols), y1 = reflect_idx(y + 1, rows);
+    const T v00 = a.V[static_cast<int64_t>(yy) * cols + xx], v01 = a.V[static_cast<int64_t>(yy) * cols + x1];
+    const T v10 = a.V[static_cast<int64_t>(y1) * cols + xx], v11 = a.V[static_cast<int64_t>(y1) * cols + x1];
+    const T z = static_cast<T>(0), one = static_cast<T>(1);
+    return (v00 * (one - z) + v01 * z) * (one - z) + (v10 * (one - z) + v11 * z) * z;
+  };
+  const T s01 = H(i, j - 1), s21 = H(i, j + 1), s10 = H(i - 1, j), s12 = H(i + 1, j);
+  const T two = static_cast<T>(2.0), zero = static_cast<T>(0.0), one = static_cast<T>(1.0);
+  const V3<T> va = normalized(V3<T>{two, zero, s21 - s01});
+  const V3<T> vb = normalized(V3<T>{zero, two, s12 - s10});
+  V3<T> n = normalized(V3<T>{va.y * vb.z - va.z * vb.y, va.z * vb.x - va.x * vb.z, va.x * vb.y - va.y * vb.x});
+  n.z *= static_cast<T>(-1.);
+  const V3<T> pix = {static_cast<T>(j), static_cast<T>(i), s11};
+  const V3<T> light_dir = normalized(V3<T>{static_cast<T>(-200) - pix.x, static_cast<T>(-1500) - pix.y, static_cast<T>(-2000.) - pix.z});
+  const V3<T> l = normalized(light_dir);
+  const V3<T> v = normalized(V3<T>{static_cast<T>(cols / 2.0) - pix.x, static_cast<T>(rows / 2.0) - pix.y, static_cast<T>(-100.) - pix.z});
+  const V3<T> h = normalized(V3<T>{v.x + l.x, v.y + l.y, v.z + l.z});
+  const T NdotH = fmax(zero, dot3(n, h)), VdotH = fmax(zero, dot3(v, h));
+  const T NdotV = fmax(zero, dot3(n, v)), NdotL = fmax(zero, dot3(n, l));
+  const T m = static_cast<T>(0.5), sfrac = static_cast<T>(0.2), pi = static_cast<T>(3.141592653589793238462643383279502884);
+  T spec = zero;
+  if (NdotL > zero && NdotV > zero) {
+    const T A  = one / (pow(m, two) + pow(NdotH, static_cast<T>(4.0)) * pi);
+    const T B  = exp(-pow(tan(acos(NdotH)), two) / pow(m, two));
+    const T G1 = two * NdotH * NdotV / VdotH, G2 = two * NdotH * NdotL / VdotH;
+    const T G  = fmin(one, fmin(G1, G2));
+    // R_F = Ks + (1 - Ks) * pow(1 - VdotH, 5) with Ks = 1
+    const T rf = one + (one - one) * pow(one - VdotH, static_cast<T>(5.0));
+    spec       = (A * B * G * rf) / (NdotL * NdotV);
+  }
+  const T ln   = sqrt(dot3(light_dir, light_dir));
+  const T beta = static_cast<T>(15.0) * (one / (static_cast<T>(4.0) * pi * pow(ln, two)));
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const T ambient = kd[c] * sfrac;
+    const T r       = (beta * NdotL) * ((one - sfrac) * kd[c] + sfrac * spec) + ambient * kd[c];
+    a.R[c][o]       = fmin(fmax(r, zero), one);
+  }
+}
+
 template <typename T>
 struct DryPtrs {
   T* p[kCanvasPlanes];
@@ -398,6 +475,30 @@ void km_compose_display(pb_context* ctx, int64_t n, const ComposeArgs& a, int mo
   }
   PB_CUDA(cudaGetLastError());
   ctx->launches++;
+}
+
+template <typename T>
+static void render_t(pb_context* ctx, int rows, int cols, const ComposeArgs& a) {
+  ComposePtrs<T> p;
+  for (int c = 0; c < 3; ++c) {
+    p.K[c]  = static_cast<const T*>(a.K[c]);
+    p.S[c]  = static_cast<const T*>(a.S[c]);
+    p.R0[c] = static_cast<const T*>(a.R0[c]);
+    p.R[c]  = static_cast<T*>(a.R[c]);
+  }
+  p.V             = static_cast<const T*>(a.V);
+  const int64_t n = static_cast<int64_t>(rows) * cols;
+  km_render_kernel<T><<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(p, rows, cols);
+  PB_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+void km_render(pb_context* ctx, int rows, int cols, const ComposeArgs& a) {
+  if (rows <= 0 || cols <= 0) return;
+  if (ctx->precision == PB_F64)
+    render_t<double>(ctx, rows, cols, a);
+  else
+    render_t<float>(ctx, rows, cols, a);
 }
 
 void km_compose_stacked(pb_context* ctx, int64_t n, const StackArgs& a) {

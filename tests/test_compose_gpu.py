@@ -213,3 +213,23 @@ def test_display_epilogue(ctx32, ctx64, port, prec):
         else:
             lsb = 1 if got.max() <= 255 else 8  # 16 bit: 1e-4 of 65535 = 6.5 codes
             assert diff.max() <= lsb and (diff > 0).mean() < (0.01 if lsb == 1 else 1.0)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_render_relighting(ctx32, ctx64, port, prec):
+    """Renderer::render (SURVEY §8f #4): compose + Beckmann/Cook-Torrance relighting with the wet thickness as height
+    field, BORDER_REFLECT stencil at the edges."""
+    from painty_b200 import api
+
+    ctx = [ctx32, ctx64][prec]
+    rows, cols = 67, 91
+    K, S, V, R0 = km_random_planes(rows, cols, seed=21)
+    V = V * 3.0
+    V[10:20, 30:50] = 0.0  # flat dry patch
+    cv, cvo = api.Canvas(ctx, rows, cols), port.canvas(rows, cols)
+    cv.setBackground(R0)
+    cvo.set_background(R0)
+    cv.upload_layer(K, S, V)
+    cvo.set_layer(K, S, V)
+    got, want = api.Renderer().render(cv), cvo.render()
+    assert np.abs(got - want).max() <= (1e-10 if prec else 2e-4)
