@@ -81,19 +81,6 @@ __device__ __forceinline__ void km_pixel(T k0, T k1, T k2, T s0, T s1, T s2, T v
 }
 
 template <typename T>
-struct Vec;
-template <>
-struct Vec<float> {
-  using type              = float4;
-  static constexpr int kN = 4;
-};
-template <>
-struct Vec<double> {
-  using type              = double2;
-  static constexpr int kN = 2;
-};
-
-template <typename T>
 __device__ __forceinline__ void ld4(const T* p, T (&o)[4]);
 template <>
 __device__ __forceinline__ void ld4<float>(const float* p, float (&o)[4]) {
