@@ -294,6 +294,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
   std::vector<int32_t> executor(n, 0), local_index(n, -1), pred_begin(n), pred_end(n), preds;
   std::vector<int32_t> counts(kMaxBands, 0);
   std::vector<char> remote(n, 0);
+  std::vector<Region> allowed(multi ? n : 0);
   DataflowPlanner planner(c->rows, c->cols);
   for (size_t s = 0; s < n; ++s) {
     const HostStroke& h = hs[s];
@@ -309,6 +310,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
       executor[s]  = std::min(y0 / dist->rows_per_band, dist->world - 1);
       const int b0 = executor[s] * dist->rows_per_band, b1 = std::min(b0 + dist->rows_per_band, c->rows) - 1;
       remote[s]    = (r.y1 >= r.y0) && (r.y0 < b0 || r.y1 > b1);
+      allowed[s]   = r;
     }
     local_index[s] = counts[executor[s]]++;
   }
@@ -349,6 +351,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     std::vector<DevStroke> ds(n_run);
     std::vector<int32_t> run_preds;
     int max_active = 1;
+    size_t max_window = 0;
     for (size_t k = 0; k < n_run; ++k) {
       const size_t s      = mine[run_begin + k];
       const HostStroke& h = hs[s];
@@ -365,8 +368,43 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
         d.paintK[q] = h.K[q];
         d.paintS[q] = h.S[q];
       }
-      d.flags    = h.flags | (remote[s] ? 4 : 0);
+      d.flags    = h.flags;
       d.pad      = 0;
+      d.win_band[0] = d.win_band[1] = -1;
+      d.win_row0[0] = d.win_row0[1] = d.win_rows[0] = d.win_rows[1] = 0;
+      d.win_ox = d.win_cols = 0;
+      if (multi && remote[s]) {
+        // the part of the region in a neighbour's band is staged in a local window (<= 2 neighbours, bounded size);
+        // anything larger falls back to direct peer accesses with system-scope fences
+        const Region& r = allowed[s];
+        const int rpb = dist->rows_per_band, ba = r.y0 / rpb, bb = r.y1 / rpb;
+        const int ox = r.x0 & ~3, wc = ((r.x1 - ox + 1) + 3) & ~3;
+        int nw = 0;
+        size_t bytes = 0;
+        bool ok = (bb - ba) <= 2;
+        for (int bnd = ba; bnd <= bb && ok; ++bnd) {
+          if (bnd == dist->rank) continue;
+          if (nw == 2) {
+            ok = false;
+            break;
+          }
+          const int g0 = std::max(r.y0, bnd * rpb), g1 = std::min(r.y1, std::min((bnd + 1) * rpb, c->rows) - 1);
+          d.win_band[nw] = bnd;
+          d.win_row0[nw] = g0 - bnd * rpb;
+          d.win_rows[nw] = g1 - g0 + 1;
+          bytes = std::max(bytes, static_cast<size_t>(d.win_rows[nw]) * wc * (2 * kLayerPlanes * ctx->esize() + 2));
+          ++nw;
+        }
+        if (ok && bytes <= (size_t(192) << 20)) {
+          d.win_ox   = ox;
+          d.win_cols = wc;
+          d.flags |= 8;
+          max_window = std::max(max_window, (bytes + 255) / 256 * 256);
+        } else {
+          d.win_band[0] = d.win_band[1] = -1;
+          d.flags |= 4;
+        }
+      }
       max_active = std::max(max_active, d.n_active);
       d.pred_begin = static_cast<int32_t>(run_preds.size());
       for (int32_t p = pred_begin[s]; p < pred_end[s]; ++p) {
@@ -426,6 +464,9 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     d_preds.upload(run_preds.data(), run_preds.size());
     DevBuf<char> d_scratch(ctx, static_cast<size_t>(L.scratch_stride) * L.grid * ctx->esize());
     const size_t n_groups = static_cast<size_t>(L.grid / (L.cluster * L.group));
+    DevBuf<unsigned char> d_windows(ctx, 2 * max_window * n_groups);
+    L.win_scratch = d_windows.p;
+    L.win_stride  = static_cast<int64_t>(2 * max_window);
     DevBuf<long long> d_group(ctx, L.group > 1 ? 2 * n_groups : 0);  // [0,n): stroke slots, [n,2n): barrier counters
     if (L.group > 1) d_group.zero(2 * n_groups);
     L.group_stroke = d_group.p;

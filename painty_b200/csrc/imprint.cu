@@ -98,19 +98,35 @@ struct OpCtx {
   T paintK[3], paintS[3];
 };
 
-// plane pointers of one row band (constant-bank loads; band is a compile-time 0 on the single-GPU path)
+// View of one row band: plane pointers, dirty map and row pitches, indexed with (band-local row) * pitch + column.
+// Single GPU: built from the launch parameters (band is a compile-time 0, everything folds into constant-bank
+// loads). Multi GPU: one view per band in shared memory, rebuilt per stroke — the executor's own band, peer
+// mappings, or local staging windows (virtual base pointers so that the same index arithmetic works).
 template <typename T>
 struct Band {
   T* can[kLayerPlanes];
   T* src[kLayerPlanes];
+  unsigned char* dirty;
+  unsigned char* touched;  // staging windows only: pixels to push back to their owner
+  int pitch, dpitch;
+  __device__ __forceinline__ Band() {}
   __device__ __forceinline__ Band(const ImprintLaunch& L, int band) {
 #pragma unroll
     for (int k = 0; k < kLayerPlanes; ++k) {
       can[k] = static_cast<T*>(L.canvas[band][k]);
       src[k] = static_cast<T*>(L.snapshot[band][k]);
     }
+    dirty   = L.dirty[band];
+    touched = nullptr;
+    pitch   = L.cols;
+    dpitch  = L.dirty_pitch;
   }
 };
+template <typename T, bool MULTI>
+__device__ __forceinline__ Band<T> band_view(const ImprintLaunch& L, const Band<T>* views, int band) {
+  if (MULTI) return views[band];
+  return Band<T>(L, 0);
+}
 
 // One (canvas pixel, pickup cell) interaction = pickupPaint (:349-384) then depositPaint (:393-431).
 // Split in two so that a thread can put the loads of all its interactions in flight before it computes any.
@@ -194,9 +210,9 @@ struct Hits {
   int band[2];
   int n;
 };
-template <bool MULTI>
-__device__ __forceinline__ Hits find_hits(const ImprintLaunch& L, const DevImprint& im, float fc, float fs, int wr, int mx, int my,
-                                          bool border, int ph, int row_lo, int row_hi) {
+template <typename T, bool MULTI>
+__device__ __forceinline__ Hits find_hits(const ImprintLaunch& L, const Band<T>* views, const DevImprint& im, float fc, float fs,
+                                          int wr, int mx, int my, bool border, int ph, int row_lo, int row_hi) {
   Hits h;
   h.n = 0;
   h.ci[0] = h.ci[1] = h.dof[0] = h.dof[1] = h.band[0] = h.band[1] = 0;
@@ -219,14 +235,16 @@ __device__ __forceinline__ Hits find_hits(const ImprintLaunch& L, const DevImpri
       const int px = static_cast<int>(fx), py = static_cast<int>(fy);  // trunc toward zero (:92-93)
       if (py < 0 || px < 0 || px >= L.cols || py >= L.rows) continue;
       if (border && ((fy >= 0.0 ? 2 : 0) + (fx >= 0.0 ? 1 : 0)) != ph) continue;
-      int band = 0, lrow = py - row_lo;
+      int band = 0, lrow = py - row_lo, pitch = L.cols, dpitch = L.dirty_pitch;
       if (MULTI) {
-        band = py / L.rows_per_band;  // the row's owner GPU
-        lrow = py - band * L.rows_per_band;
+        band   = py / L.rows_per_band;  // the row's owner GPU
+        lrow   = py - band * L.rows_per_band;
+        pitch  = views[band].pitch;
+        dpitch = views[band].dpitch;
       } else if (py < row_lo || py > row_hi) {
         continue;  // band canvas without peers: rows outside the stored window are not ours
       }
-      const int ci = lrow * L.cols + px, dof = lrow * L.dirty_pitch + px;
+      const int ci = lrow * pitch + px, dof = lrow * dpitch + px;
       if (h.n == 0) h.ci[0] = ci, h.dof[0] = dof, h.band[0] = band;
       if (h.n == 1) h.ci[1] = ci, h.dof[1] = dof, h.band[1] = band;
       ++h.n;  // a unit cell cannot hold more than 2 lattice points (min distance 1 < diagonal sqrt 2)
@@ -248,13 +266,14 @@ struct RingGeom {
 };
 
 template <typename T, bool MULTI>
-__device__ __forceinline__ void ring_word(const ImprintLaunch& L, const RingGeom& g, int row, int wi, unsigned word) {
+__device__ __forceinline__ void ring_word(const ImprintLaunch& L, const Band<T>* views, const RingGeom& g, int row, int wi,
+                                          unsigned word) {
   const bool mid = row > g.tly && row < g.bry;
   const int band = MULTI ? row / L.rows_per_band : 0;
   const int lrow = MULTI ? row - band * L.rows_per_band : row - L.store_first;
-  const Band<T> C(L, band);
-  unsigned char* drow = L.dirty[band] + static_cast<int64_t>(lrow) * L.dirty_pitch;
-  const int64_t rbase = static_cast<int64_t>(lrow) * L.cols;
+  const Band<T> C = band_view<T, MULTI>(L, views, band);
+  unsigned char* drow = C.dirty + static_cast<int64_t>(lrow) * C.dpitch;
+  const int64_t rbase = static_cast<int64_t>(lrow) * C.pitch;
   bool need[4];
   T v[4][kLayerPlanes];
 #pragma unroll
@@ -273,12 +292,13 @@ __device__ __forceinline__ void ring_word(const ImprintLaunch& L, const RingGeom
 #pragma unroll
       for (int k = 0; k < kLayerPlanes; ++k) __stcg(C.src[k] + rbase + col, v[b][k]);
       __stcg(drow + col, static_cast<unsigned char>(0));
+      if (MULTI && C.touched) __stcg(C.touched + static_cast<int64_t>(lrow) * C.dpitch + col, static_cast<unsigned char>(1));
     }
   }
 }
 
 template <typename T, bool MULTI>
-__device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const RingGeom& g, int gt, int gstride) {
+__device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const Band<T>* views, const RingGeom& g, int gt, int gstride) {
   if (g.ax1 < g.ax0 || g.ay1 < g.ay0) return;
   const int w0 = g.ax0 >> 2, nw = (g.ax1 >> 2) - w0 + 1, nrows = g.ay1 - g.ay0 + 1;
   const int total = nw * nrows;
@@ -303,13 +323,156 @@ __device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const RingGeom
         if (!(row > g.tly && row < g.bry && wi >= iw0 && wi <= iw1)) {
           const int band = MULTI ? row / L.rows_per_band : 0;
           const int lrow = MULTI ? row - band * L.rows_per_band : row - L.store_first;
-          word[u] = __ldcg(reinterpret_cast<const unsigned*>(L.dirty[band] + static_cast<int64_t>(lrow) * L.dirty_pitch) + wi);
+          const unsigned char* dbase = MULTI ? views[band].dirty : L.dirty[0];
+          const int dpitch           = MULTI ? views[band].dpitch : L.dirty_pitch;
+          word[u] = __ldcg(reinterpret_cast<const unsigned*>(dbase + static_cast<int64_t>(lrow) * dpitch) + wi);
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < kScanBatch; ++u)
-      if (word[u] != 0u) ring_word<T, MULTI>(L, g, rows[u], wis[u], word[u]);
+      if (word[u] != 0u) ring_word<T, MULTI>(L, views, g, rows[u], wis[u], word[u]);
+  }
+}
+
+// ---- multi-GPU staging windows ------------------------------------------------------------------------------------
+// Layout of one window in the stroke slot's scratch: 7 canvas planes | 7 snapshot planes (npx elements each) | dirty
+// bytes | touched bytes, npx = rows * cols (cols a multiple of 4).
+template <typename T>
+struct Window {
+  T* can[kLayerPlanes];
+  T* src[kLayerPlanes];
+  unsigned char *dirty, *touched;
+  int band, row0, rows, ox, cols;
+  __device__ __forceinline__ Window(const ImprintLaunch& L, const DevStroke& st, int group, int w) {
+    band = st.win_band[w], row0 = st.win_row0[w], rows = st.win_rows[w], ox = st.win_ox, cols = st.win_cols;
+    unsigned char* base = L.win_scratch + static_cast<int64_t>(group) * L.win_stride + static_cast<int64_t>(w) * (L.win_stride / 2);
+    const int64_t npx   = static_cast<int64_t>(rows) * cols;
+    T* planes           = reinterpret_cast<T*>(base);
+#pragma unroll
+    for (int k = 0; k < kLayerPlanes; ++k) {
+      can[k] = planes + k * npx;
+      src[k] = planes + (kLayerPlanes + k) * npx;
+    }
+    dirty   = base + 2 * kLayerPlanes * npx * static_cast<int64_t>(sizeof(T));
+    touched = dirty + npx;
+  }
+};
+
+// Build the per-band views of a stroke and pull its windows from the neighbours' HBM (coalesced rows over NVLink).
+template <typename T>
+__device__ __forceinline__ void stage_in(const ImprintLaunch& L, const DevStroke& st, Band<T>* views, int group, int sgt, int gstride,
+                                         int tid) {
+  if (tid < L.n_bands) {
+    Band<T> v(L, tid);
+    if (st.flags & 8) {
+      for (int w = 0; w < 2; ++w) {
+        if (st.win_band[w] != tid) continue;
+        const Window<T> W(L, st, group, w);
+        const int64_t off = static_cast<int64_t>(W.row0) * W.cols + W.ox;  // virtual base: index = lrow * cols + px
+#pragma unroll
+        for (int k = 0; k < kLayerPlanes; ++k) {
+          v.can[k] = W.can[k] - off;
+          v.src[k] = W.src[k] - off;
+        }
+        v.dirty   = W.dirty - off;
+        v.touched = W.touched - off;
+        v.pitch   = W.cols;
+        v.dpitch  = W.cols;
+      }
+    }
+    views[tid] = v;
+  }
+  if (!(st.flags & 8)) return;
+  constexpr int CH = 16 / static_cast<int>(sizeof(T));  // pixels per 16-byte chunk
+  const bool vec   = (L.cols & 3) == 0;                 // row starts of the peer planes are 16 B aligned
+  for (int w = 0; w < 2; ++w) {
+    if (st.win_band[w] < 0) continue;
+    const Window<T> W(L, st, group, w);
+    const int npx = W.rows * W.cols;
+    if (vec) {
+      const int cpr = W.cols / 4;  // 4-pixel groups per window row
+      for (int i = sgt; i < W.rows * cpr; i += gstride) {
+        const int lr = i / cpr, c = (i - lr * cpr) * 4, wi = lr * W.cols + c;
+        const int64_t gi = static_cast<int64_t>(W.row0 + lr) * L.cols + W.ox + c;
+        uint4 a[kLayerPlanes][4 / CH], b[kLayerPlanes][4 / CH];
+#pragma unroll
+        for (int k = 0; k < kLayerPlanes; ++k) {
+#pragma unroll
+          for (int j = 0; j < 4 / CH; ++j) {
+            a[k][j] = __ldcg(reinterpret_cast<const uint4*>(static_cast<const T*>(L.canvas[W.band][k]) + gi) + j);
+            b[k][j] = __ldcg(reinterpret_cast<const uint4*>(static_cast<const T*>(L.snapshot[W.band][k]) + gi) + j);
+          }
+        }
+        const unsigned dflags =
+          __ldcg(reinterpret_cast<const unsigned*>(L.dirty[W.band] + static_cast<int64_t>(W.row0 + lr) * L.dirty_pitch + W.ox + c));
+#pragma unroll
+        for (int k = 0; k < kLayerPlanes; ++k) {
+#pragma unroll
+          for (int j = 0; j < 4 / CH; ++j) {
+            __stcg(reinterpret_cast<uint4*>(W.can[k] + wi) + j, a[k][j]);
+            __stcg(reinterpret_cast<uint4*>(W.src[k] + wi) + j, b[k][j]);
+          }
+        }
+        __stcg(reinterpret_cast<unsigned*>(W.dirty + wi), dflags);
+        __stcg(reinterpret_cast<unsigned*>(W.touched + wi), 0u);
+      }
+      continue;
+    }
+    for (int i = sgt; i < npx; i += gstride) {
+      const int lr = i / W.cols, c = i - lr * W.cols, px = W.ox + c;
+      __stcg(W.touched + i, static_cast<unsigned char>(0));
+      if (px >= L.cols) continue;
+      const int64_t gi = static_cast<int64_t>(W.row0 + lr) * L.cols + px;
+      T a[kLayerPlanes], b[kLayerPlanes];
+#pragma unroll
+      for (int k = 0; k < kLayerPlanes; ++k) {
+        a[k] = __ldcg(static_cast<const T*>(L.canvas[W.band][k]) + gi);
+        b[k] = __ldcg(static_cast<const T*>(L.snapshot[W.band][k]) + gi);
+      }
+      const unsigned char dflag = __ldcg(L.dirty[W.band] + static_cast<int64_t>(W.row0 + lr) * L.dirty_pitch + px);
+#pragma unroll
+      for (int k = 0; k < kLayerPlanes; ++k) {
+        __stcg(W.can[k] + i, a[k]);
+        __stcg(W.src[k] + i, b[k]);
+      }
+      __stcg(W.dirty + i, dflag);
+    }
+  }
+}
+
+// Push back only what this stroke changed: untouched pixels may meanwhile have been refreshed by a commuting stroke's
+// snapshot ring on their owner (an idempotent copy this window must not undo).
+template <typename T>
+__device__ __forceinline__ void stage_out(const ImprintLaunch& L, const DevStroke& st, int group, int sgt, int gstride) {
+  for (int w = 0; w < 2; ++w) {
+    if (st.win_band[w] < 0) continue;
+    const Window<T> W(L, st, group, w);
+    const int nwords = W.rows * W.cols / 4;  // the touched map is scanned 4 pixels at a time
+    const int cpr    = W.cols / 4;
+    for (int i = sgt; i < nwords; i += gstride) {
+      const unsigned t = __ldcg(reinterpret_cast<const unsigned*>(W.touched) + i);
+      if (t == 0u) continue;
+      const int lr = i / cpr, c = (i - lr * cpr) * 4;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (((t >> (8 * b)) & 0xffu) == 0u) continue;
+        const int wi = lr * W.cols + c + b, px = W.ox + c + b;
+        const int64_t gi = static_cast<int64_t>(W.row0 + lr) * L.cols + px;
+        T va[kLayerPlanes], vb[kLayerPlanes];
+#pragma unroll
+        for (int k = 0; k < kLayerPlanes; ++k) {
+          va[k] = __ldcg(W.can[k] + wi);
+          vb[k] = __ldcg(W.src[k] + wi);
+        }
+#pragma unroll
+        for (int k = 0; k < kLayerPlanes; ++k) {
+          __stcg(static_cast<T*>(L.canvas[W.band][k]) + gi, va[k]);
+          __stcg(static_cast<T*>(L.snapshot[W.band][k]) + gi, vb[k]);
+        }
+        __stcg(L.dirty[W.band] + static_cast<int64_t>(W.row0 + lr) * L.dirty_pitch + px, __ldcg(W.dirty + wi));
+      }
+    }
   }
 }
 
@@ -320,6 +483,8 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_stroke;
   __shared__ unsigned long long s_active;
+  __shared__ Band<T> s_view[MULTI ? kMaxBands : 1];
+  const Band<T>* views = MULTI ? s_view : nullptr;
 
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, bd = blockDim.x;
@@ -395,6 +560,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
       C.paintS[k] = static_cast<T>(st.paintS[k]);
     }
     remote       = MULTI && (st.flags & 4) != 0;
+    if (MULTI) stage_in<T>(L, st, s_view, group, sgt, gstride, tid), sync_all();
     const int nA = st.n_active;
     const int wr = (st.side - 1) / 2;  // == hr (square footprint), FootprintBrush.hxx:75-78
     const T* fhs = static_cast<const T*>(st.fh);
@@ -453,7 +619,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
         g.ay0 = max(max(static_cast<int>(im.cy - wr - st.radius), 0), MULTI ? 0 : row_lo);
         g.ax1 = min(static_cast<int>(im.cx + wr + st.radius), L.cols - 1);
         g.ay1 = min(min(static_cast<int>(im.cy + wr + st.radius), L.rows - 1), MULTI ? L.rows - 1 : row_hi);
-        ring_scan<T, MULTI>(L, g, sgt, gstride);
+        ring_scan<T, MULTI>(L, views, g, sgt, gstride);
       }
       // left/top overhang: canvas pixels of column/row 0 can be hit twice (B#11) -> ordered phases
       const bool border = (im.cx - wr < 0.0) || (im.cy - wr < 0.0);
@@ -487,19 +653,20 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
 #pragma unroll
           for (int q = 0; q < CPP; ++q) {
             h[q].n = 0;
-            if (have[q]) h[q] = find_hits<MULTI>(L, im, fc, fs, wr, mx[q], my[q], border, ph, row_lo, row_hi);
+            if (have[q]) h[q] = find_hits<T, MULTI>(L, views, im, fc, fs, wr, mx[q], my[q], border, ph, row_lo, row_hi);
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              if (j < h[q].n) op_load(Band<T>(L, MULTI ? h[q].band[j] : 0), h[q].ci[j], d[q][j]);
+              if (j < h[q].n) op_load(band_view<T, MULTI>(L, views, h[q].band[j]), h[q].ci[j], d[q][j]);
           }
 #pragma unroll
           for (int q = 0; q < CPP; ++q) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               if (j < h[q].n) {
-                const int band = MULTI ? h[q].band[j] : 0;
-                op_finish(C, Band<T>(L, band), h[q].ci[j], fh[q], d[q][j], pick, ps, slot[q]);
-                if (L.dirty[0]) __stcg(L.dirty[band] + h[q].dof[j], static_cast<unsigned char>(1));
+                const Band<T> B = band_view<T, MULTI>(L, views, h[q].band[j]);
+                op_finish(C, B, h[q].ci[j], fh[q], d[q][j], pick, ps, slot[q]);
+                if (B.dirty) __stcg(B.dirty + h[q].dof[j], static_cast<unsigned char>(1));
+                if (MULTI && B.touched) __stcg(B.touched + h[q].dof[j], static_cast<unsigned char>(1));
                 ++my_active;
               }
             }
@@ -519,6 +686,11 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
       }
     }
     sync_all();
+    if (MULTI && (st.flags & 8)) {  // push the touched window pixels back into their owners' HBM
+      stage_out<T>(L, st, group, sgt, gstride);
+      __threadfence_system();
+      sync_all();
+    }
     if (crank == 0 && tid == 0) {
       if (MULTI) {
         __threadfence_system();

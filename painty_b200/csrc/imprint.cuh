@@ -32,8 +32,15 @@ struct DevStroke {
   double paintK[3], paintS[3];
   int32_t pred_begin, pred_end;  // into preds[]
   int32_t flags;                 // bit0: load pick state from the dense map, bit1: store it back,
-                                 // bit2: the stroke touches rows owned by another GPU (system-scope fences)
+                                 // bit2: rows of another GPU are accessed directly through NVLink (system-scope
+                                 //       fences at every barrier), bit3: they are staged in local windows instead
   int32_t pad;
+  // Multi-GPU staging windows: the part of the stroke's region that lies in a neighbour's band is pulled into local
+  // scratch before the stroke and the touched pixels are pushed back afterwards (one bulk NVLink transfer each way
+  // instead of remote round trips on every imprint). Window w covers band-local rows [row0, row0+rows) and canvas
+  // columns [win_ox, win_ox + win_cols) of band win_band[w]; win_band[w] < 0 = unused.
+  int32_t win_band[2], win_row0[2], win_rows[2];
+  int32_t win_ox, win_cols;  // multiples of 4 (the dirty map is scanned in 32-bit words)
 };
 
 struct ImprintLaunch {
@@ -63,6 +70,8 @@ struct ImprintLaunch {
   int flag_offset;               // flag index of this launch's stroke 0 (strokes of earlier launches come first)
   int* queue;                    // single counter (zeroed)
   unsigned long long* counters;  // [0] active stroke-pixels
+  unsigned char* win_scratch;  // staging windows, win_stride bytes per stroke slot (two halves, one per window)
+  int64_t win_stride;
   // per-CTA pick scratch in global memory for footprints that do not fit shared memory
   void* scratch;
   int64_t scratch_stride;  // elements per CTA
