@@ -381,7 +381,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
         const int ox = r.x0 & ~3, wc = ((r.x1 - ox + 1) + 3) & ~3;
         int nw = 0;
         size_t bytes = 0;
-        bool ok = (bb - ba) <= 2;
+        bool ok = (bb - ba) <= 2 && std::getenv("PB_DIST_DIRECT") == nullptr;  // env: force the direct path (tests)
         for (int bnd = ba; bnd <= bb && ok; ++bnd) {
           if (bnd == dist->rank) continue;
           if (nw == 2) {

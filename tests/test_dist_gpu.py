@@ -33,11 +33,13 @@ def _workload(rows, cols, n):
     return rec, np.concatenate(xs), np.concatenate(ys), np.concatenate(ts), sorted(set(float(s["radius"]) for s in strokes))
 
 
-def _worker(rank, world, port, prec, q):
+def _worker(rank, world, port, prec, direct, q):
     import torch
     import torch.distributed as dist
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if direct:
+        os.environ["PB_DIST_DIRECT"] = "1"  # neighbour rows through NVLink loads/stores instead of staging windows
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from painty_b200 import api
@@ -75,21 +77,24 @@ def _worker(rank, world, port, prec, q):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("direct", [False, True])
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("prec", [0, 1])
-def test_two_gpu_band_canvas_equals_single_gpu(built_lib, prec):
+def test_band_canvas_equals_single_gpu(built_lib, prec, world, direct):
+    """600 x 500 canvas in `world` bands (75 rows each at 8 GPUs: strokes span up to 3-4 bands, which also exercises
+    the fallback from staging windows to direct peer access)."""
     import torch
     import torch.multiprocessing as mp
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, prec, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, prec, direct, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=300) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
-    assert res == [(0, True), (1, True)]
+    assert res == [(r, True) for r in range(world)]
