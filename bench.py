@@ -361,6 +361,13 @@ def main():
                      "traffic": 401643264 if world == 1 else None, "algorithmic_bytes_per_launch": COMPOSE_BYTES_PER_PX * n_px,
                      "frac_of_8TBs_nominal": achieved / 8000.0},
     }
+    # the step's dominant kernel is the imprint chain: latency bound (dependent imprints, L2-resident working set), so no
+    # roofline claim — reported with the upper-bound byte model of SURVEY.md §8d (88 B per active stroke-pixel)
+    imp_ms = t_imp / args.steps
+    line["imprint"] = {"kernel": "imprint_kernel<float>", "bound": "latency (dependency chain of imprints, see DESIGN.md §5)",
+                       "ms_per_step": imp_ms, "imprints_per_s": world * len(cx) / max(world, 1) / (imp_ms * 1e-3),
+                       "active_stroke_pixels_per_s": active / (imp_ms * 1e-3),
+                       "model_bytes_per_active_px": 88, "model_GBps": 88 * active / (imp_ms * 1e-3) / 1e9}
     if rank == 0 and not args.no_cpu and world == 1:
         info = cpu_sample(rec, cx, cy, th, ROWS, COLS)
         t = info["t_imprint"] + info["t_compose_full"] * info["n_sample"] / len(rec)
