@@ -654,17 +654,17 @@ int pb_layer_compose(pb_layer* l, const double* R0, double* out) {
   pb_context* ctx = l->pl.ctx;
   DeviceGuard g(ctx);
   pb_planes r;
-  planes_alloc(ctx, r, l->pl.rows, l->pl.cols, 3);
+  planes_alloc_temp(ctx, r, l->pl.rows, l->pl.cols, 3);
   try {
     upload_aos(ctx, r, 0, 3, R0);
     void* o[3] = {r.plane(0), r.plane(1), r.plane(2)};
     km_compose(ctx, l->pl.n(), compose_args(l->pl, r, 0, o, 0, ctx->esize()));
     download_aos(ctx, r, 0, 3, out);
   } catch (...) {
-    planes_free(r);
+    planes_free_temp(r);
     throw;
   }
-  planes_free(r);
+  planes_free_temp(r);
   PB_API_END
 }
 int pb_layer_compose_onto(pb_layer* l, double* R0) { return pb_layer_compose(l, R0, R0); }
@@ -779,16 +779,16 @@ int pb_canvas_compose(pb_canvas* c, double* out) {
   pb_context* ctx = c->pl.ctx;
   DeviceGuard g(ctx);
   pb_planes r;
-  planes_alloc(ctx, r, c->pl.rows, c->pl.cols, 3);
+  planes_alloc_temp(ctx, r, c->pl.rows, c->pl.cols, 3);
   try {
     void* o[3] = {r.plane(0), r.plane(1), r.plane(2)};
     km_compose(ctx, c->pl.n(), compose_args(c->pl, c->pl, PR, o, 0, ctx->esize()));
     download_aos(ctx, r, 0, 3, out);
   } catch (...) {
-    planes_free(r);
+    planes_free_temp(r);
     throw;
   }
-  planes_free(r);
+  planes_free_temp(r);
   PB_API_END
 }
 namespace {
@@ -810,16 +810,16 @@ int pb_canvas_render(pb_canvas* c, double* out) {
   DeviceGuard g(ctx);
   PB_REQUIRE(c->store_first == 0 && c->pl.rows == c->rows, "pb_canvas_render needs a full canvas (not a band)");
   pb_planes r;
-  planes_alloc(ctx, r, c->pl.rows, c->pl.cols, 3);
+  planes_alloc_temp(ctx, r, c->pl.rows, c->pl.cols, 3);
   try {
     void* o[3] = {r.plane(0), r.plane(1), r.plane(2)};
     km_render(ctx, c->pl.rows, c->pl.cols, compose_args(c->pl, c->pl, PR, o, 0, ctx->esize()));
     download_aos(ctx, r, 0, 3, out);
   } catch (...) {
-    planes_free(r);
+    planes_free_temp(r);
     throw;
   }
-  planes_free(r);
+  planes_free_temp(r);
   PB_API_END
 }
 int pb_canvas_compose_qrgb32(pb_canvas* c, uint32_t* out) {

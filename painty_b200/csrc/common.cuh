@@ -85,6 +85,8 @@ namespace pb {
 // ---- layout.cu ----------------------------------------------------------------------------------
 void planes_alloc(pb_context* ctx, pb_planes& pl, int rows, int cols, int nplanes);
 void planes_free(pb_planes& pl);
+void planes_alloc_temp(pb_context* ctx, pb_planes& pl, int rows, int cols, int nplanes);
+void planes_free_temp(pb_planes& pl);
 void fill_plane(pb_context* ctx, void* plane, int64_t n, double value);
 // host AoS f64 (n*ch) <-> `ch` consecutive device planes starting at plane index p0
 void upload_aos(pb_context* ctx, const pb_planes& pl, int p0, int ch, const double* host);

@@ -103,6 +103,21 @@ void planes_alloc(pb_context* ctx, pb_planes& pl, int rows, int cols, int nplane
   PB_CUDA(cudaMalloc(&pl.base, pl.stride * nplanes));
 }
 
+// stream-ordered temporaries (compose results on their way to the host): no device-wide synchronisation
+void planes_alloc_temp(pb_context* ctx, pb_planes& pl, int rows, int cols, int nplanes) {
+  pl.ctx     = ctx;
+  pl.rows    = rows;
+  pl.cols    = cols;
+  pl.nplanes = nplanes;
+  const size_t bytes = static_cast<size_t>(rows) * cols * ctx->esize();
+  pl.stride          = std::max<size_t>((bytes + 255) / 256 * 256, 256);
+  PB_CUDA(cudaMallocAsync(&pl.base, pl.stride * nplanes, ctx->stream));
+}
+void planes_free_temp(pb_planes& pl) {
+  if (pl.base) cudaFreeAsync(pl.base, pl.ctx->stream);
+  pl.base = nullptr;
+}
+
 void planes_free(pb_planes& pl) {
   if (pl.base) cudaFree(pl.base);
   pl.base = nullptr;
