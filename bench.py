@@ -334,6 +334,19 @@ def main():
 
     # roofline of the KM compose kernel, measured live with events around each launch
     cmp_ms = t_cmp / args.steps
+    roofline_how = "events around the compose launch of every timed step"
+    if world > 1:
+        # at N > 1 the in-step launch follows a host-side process-group barrier (idle GPU + launch latency inside the
+        # event pair); the kernel itself is timed with back-to-back launches right after the timed steps
+        ce0, ce1 = ev(), ev()
+        cv.compose_device(d_R.data_ptr(), n_px)
+        ce0.record(stream)
+        for _ in range(5):
+            cv.compose_device(d_R.data_ptr(), n_px)
+        ce1.record(stream)
+        ctx.synchronize()
+        cmp_ms = ce0.elapsed_time(ce1) / 5
+        roofline_how = "5 back-to-back launches after the timed steps (the in-step launch follows a host barrier)"
     achieved = COMPOSE_BYTES_PER_PX * n_px / (cmp_ms * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback"
     try:
@@ -348,7 +361,8 @@ def main():
                    "parallelism": "single GPU" if world == 1 else
                    "one %dx%d canvas in %d row bands (one per GPU), strokes cross bands through NVLink peer memory, NCCL all_gather of "
                    "reflectance" % (rows_total, COLS, world),
-                   "stroke_pixels_per_step": int(visited), "active_stroke_pixels_per_step": int(active),
+                   "stroke_pixels_per_step": int(visited_all), "stroke_pixels_per_step_this_rank": int(visited),
+                   "active_stroke_pixels_per_step_this_rank": int(active),
                    "l2": "canvas working set 8.3 Mpx x 14 planes x 4 B = 464 MB > 126 MB L2; canvas cleared every step",
                    "imprint_ms": t_imp / args.steps, "compose_ms": cmp_ms},
         "clocks": clocks,
@@ -356,7 +370,7 @@ def main():
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "km_compose_kernel<float>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "peak_source": peak_src,
+                     "frac": achieved / peak, "peak_source": peak_src, "measured": roofline_how,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one 4K launch, ncu --set full (profiles/r01_compose_f32_raw.csv)
                      "traffic": 401643264 if world == 1 else None, "algorithmic_bytes_per_launch": COMPOSE_BYTES_PER_PX * n_px,
                      "frac_of_8TBs_nominal": achieved / 8000.0},
