@@ -72,3 +72,46 @@ def test_errors_are_reported_not_swallowed(ctx32):
         br.stroke_batch(cv, rec, [1.0], [1.0], [0.0])
     with pytest.raises(api.PaintyError):
         api.Canvas(ctx32, 70000, 70000)  # >= 2^31 pixels (the reference's int32 index limit)
+
+
+def test_remaining_api_surface(ctx64, port):
+    """PaintLayer::copyTo / set, brush rate accessors, clean(), public updateSnapshot(canvas), snapshot toggling."""
+    import ctypes as C
+
+    from painty_b200 import api
+
+    rows, cols = 48, 64
+    rng = np.random.default_rng(3)
+    K, S, V = rng.uniform(0, 1, (rows, cols, 3)), rng.uniform(0, 1, (rows, cols, 3)), rng.uniform(0, 0.5, (rows, cols))
+    a, b = api.PaintLayer(ctx64, rows, cols), api.PaintLayer(ctx64, 2, 2)
+    a.upload(K, S, V)
+    a.copyTo(b)  # reallocates the destination like PaintLayer.hxx:104-107
+    assert (b.getRows(), b.getCols()) == (rows, cols)
+    for x, y in zip(b.download(), (K, S, V)):
+        assert np.array_equal(x, y)
+    a.clear()
+    assert all((x == 0).all() for x in a.download())
+
+    br, bro = api.FootprintBrush(ctx64, 6.0), port.footprint_brush(6.0)
+    assert (br.getPickupRate(), br.getDepositionRate(), br.getUseSnapshotBuffer()) == (0.9, 0.05, True)  # :477-495
+    br.setPickupRate(0.5)
+    br.setDepositionRate(0.2)
+    bro.set_rates(0.5, 0.2)
+    assert (br.getPickupRate(), br.getDepositionRate()) == (0.5, 0.2)
+    cv, cvo = api.Canvas(ctx64, rows, cols), port.canvas(rows, cols)
+    cv.upload_layer(K, S, V)
+    cvo.set_layer(K, S, V)
+    br.updateSnapshot(cv)  # FootprintBrush::updateSnapshot(canvas) :168-172 == what the first imprint would do
+    cx, cy, th = np.linspace(10, 50, 30), np.linspace(12, 30, 30), np.linspace(0, 1.5, 30)
+    for obj, canvas in ((br, cv), (bro, cvo)):
+        obj.dip(([.3, .2, .1], [.2, .4, .3])) if obj is br else obj.dip([.3, .2, .1], [.2, .4, .3])
+        obj.imprint_batch(canvas, cx, cy, th)
+    br.clean()  # :160-166, keeps the paint
+    assert all((x == 0).all() for x in br.getPickupMap())
+    port.fn("fbrush_dip", None, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)])  # (clean on the port = dip with the same paint)
+    bro.dip([.3, .2, .1], [.2, .4, .3])
+    br.imprint_batch(cv, cx[::-1].copy(), cy[::-1].copy(), th)
+    bro.imprint_batch(cvo, cx[::-1].copy(), cy[::-1].copy(), th)
+    got, want = cv.download("KSV"), cvo.get()
+    for k in "KSV":
+        assert np.array_equal(got[k], want[k]), k
