@@ -254,11 +254,11 @@ struct DistInfo {
 };
 constexpr int64_t kDistFlagCapacity = int64_t(1) << 22;
 
-// margin 0: the BOX the stroke modifies (footprint square around every centre); margin = radius: everything it
-// reads or writes, i.e. the union of the snapshot "allowed" boxes (:298-305). Both padded by 2 px.
-Region stroke_region(const HostStroke& h, const double* cx, const double* cy, int rows, int cols, double margin) {
-  Region r{1, 1, 0, 0};
-  if (h.n <= 0) return r;
+// The BOX a stroke modifies (footprint square around every centre) and everything it reads or writes (the union of
+// the snapshot "allowed" boxes, :298-305: the box grown by the radius). Both padded by 2 px, clipped to the canvas.
+void stroke_regions(const HostStroke& h, const double* cx, const double* cy, int rows, int cols, Region& box, Region& allowed) {
+  box = allowed = Region{1, 1, 0, 0};
+  if (h.n <= 0) return;
   double lx = cx[h.first], hx = lx, ly = cy[h.first], hy = ly;
   for (int64_t i = h.first; i < h.first + h.n; ++i) {
     lx = std::min(lx, cx[i]);
@@ -266,12 +266,17 @@ Region stroke_region(const HostStroke& h, const double* cx, const double* cy, in
     ly = std::min(ly, cy[i]);
     hy = std::max(hy, cy[i]);
   }
-  const double m = (h.g->side - 1) / 2 + margin + 2.0;
-  r.x0 = static_cast<int>(std::max(0.0, std::floor(lx - m)));
-  r.y0 = static_cast<int>(std::max(0.0, std::floor(ly - m)));
-  r.x1 = static_cast<int>(std::min<double>(cols - 1, std::ceil(hx + m)));
-  r.y1 = static_cast<int>(std::min<double>(rows - 1, std::ceil(hy + m)));
-  return r;
+  auto grow = [&](double margin) {
+    const double m = (h.g->side - 1) / 2 + margin + 2.0;
+    Region r;
+    r.x0 = static_cast<int>(std::max(0.0, std::floor(lx - m)));
+    r.y0 = static_cast<int>(std::max(0.0, std::floor(ly - m)));
+    r.x1 = static_cast<int>(std::min<double>(cols - 1, std::ceil(hx + m)));
+    r.y1 = static_cast<int>(std::min<double>(rows - 1, std::ceil(hy + m)));
+    return r;
+  };
+  box     = grow(0.0);
+  allowed = grow(h.radius);
 }
 
 // Plans and launches the persistent imprint kernel for a submission-ordered stroke list: one launch per run of
@@ -298,12 +303,12 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
   DataflowPlanner planner(c->rows, c->cols);
   for (size_t s = 0; s < n; ++s) {
     const HostStroke& h = hs[s];
-    const Region r      = stroke_region(h, cx, cy, c->rows, c->cols, h.radius);
+    Region box, r;
+    stroke_regions(h, cx, cy, c->rows, c->cols, box, r);
     if (b->use_snapshot) {
-      planner.add_footprint(static_cast<int32_t>(s), stroke_region(h, cx, cy, c->rows, c->cols, 0.0), r, preds, pred_begin[s],
-                            pred_end[s]);
+      planner.add_footprint(static_cast<int32_t>(s), box, r, preds, pred_begin[s], pred_end[s]);
     } else {
-      planner.add(static_cast<int32_t>(s), stroke_region(h, cx, cy, c->rows, c->cols, 0.0), preds, pred_begin[s], pred_end[s]);
+      planner.add(static_cast<int32_t>(s), box, preds, pred_begin[s], pred_end[s]);
     }
     if (multi && h.n > 0) {
       const int y0 = std::min(std::max(static_cast<int>(cy[h.first]), 0), c->rows - 1);
@@ -319,14 +324,23 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     if (executor[s] == (multi ? dist->rank : 0)) mine.push_back(s);
   PB_REQUIRE(static_cast<int64_t>(mine.size()) <= kDistFlagCapacity, "too many strokes in one batch");
 
-  std::vector<DevImprint> im(static_cast<size_t>(n_imprints));
-  for (size_t k = 0; k < mine.size(); ++k) {  // only the imprints this rank executes
-    const HostStroke& h = hs[mine[k]];
-    for (int64_t i = h.first; i < h.first + h.n; ++i) {
-      im[i].cx = cx[i];
-      im[i].cy = cy[i];
-      im[i].c  = std::cos(-theta[i]);  // FootprintBrush.hxx:95-96, per-imprint constants
-      im[i].s  = std::sin(-theta[i]);
+  // per-imprint constants of the strokes this rank executes, compacted in execution order
+  std::vector<DevImprint> im;
+  std::vector<int64_t> local_first(mine.size());
+  {
+    size_t total = 0;
+    for (size_t k = 0; k < mine.size(); ++k) total += static_cast<size_t>(hs[mine[k]].n);
+    im.resize(total);
+    size_t o = 0;
+    for (size_t k = 0; k < mine.size(); ++k) {
+      const HostStroke& h = hs[mine[k]];
+      local_first[k]      = static_cast<int64_t>(o);
+      for (int64_t i = h.first; i < h.first + h.n; ++i, ++o) {
+        im[o].cx = cx[i];
+        im[o].cy = cy[i];
+        im[o].c  = std::cos(-theta[i]);  // FootprintBrush.hxx:95-96, per-imprint constants
+        im[o].s  = std::sin(-theta[i]);
+      }
     }
   }
   DevBuf<DevImprint> d_im(ctx, im.size());
@@ -356,7 +370,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
       const size_t s      = mine[run_begin + k];
       const HostStroke& h = hs[s];
       DevStroke& d        = ds[k];
-      d.first_imprint     = h.first;
+      d.first_imprint     = local_first[run_begin + k];
       d.n_imprints        = static_cast<int32_t>(h.n);
       d.n_active          = h.g->n_active;
       d.xy                = h.g->d_xy;
