@@ -66,6 +66,16 @@ int pb_paint_mix_single(int n, const double* baseK, const double* baseS, int n_w
 int pb_expand_stroke(int mode, int n, const double* path_xy, int64_t capacity, double* cx, double* cy, double* theta,
                      int64_t* n_imprints);
 
+/* Host-side dataflow planner used by the stroke batches (no device needed; exposed for testing and for hosts that
+ * want to inspect the schedule). Strokes are given in submission order by two inclusive pixel rectangles
+ * (x0,y0,x1,y1): `box` = what the stroke modifies, `allowed` = what it may read or refresh (for a texture stroke pass
+ * the same rectangle twice). Two strokes must keep their order iff the box of one meets the allowed rectangle of the
+ * other (at 64 px tile granularity). Writes the predecessor lists as CSR: offsets[n+1] and up to `capacity` entries of
+ * preds; *n_preds receives the total count. Waiting for the listed predecessors is sufficient (ordering is
+ * transitive through them). */
+int pb_plan_dependencies(int rows, int cols, int64_t n, const int32_t* box, const int32_t* allowed, int64_t* offsets,
+                         int64_t capacity, int32_t* preds, int64_t* n_preds);
+
 /* ---- PaintLayer ------------------------------------------------------------------------------ */
 int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out);
 int pb_layer_destroy(pb_layer* l);

@@ -114,6 +114,21 @@ def expand_stroke(path, mode=0):
     return cx, cy, th
 
 
+def plan_dependencies(rows, cols, box, allowed):
+    """Host-side dataflow plan: (offsets[n+1], preds) CSR of the strokes each stroke has to wait for."""
+    box = np.ascontiguousarray(box, dtype=np.int32).reshape(-1, 4)
+    allowed = np.ascontiguousarray(allowed, dtype=np.int32).reshape(-1, 4)
+    n = len(box)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    total = C.c_int64(0)
+    _chk(lib().pb_plan_dependencies(rows, cols, C.c_int64(n), box.ctypes.data_as(_VP), allowed.ctypes.data_as(_VP),
+                                    offsets.ctypes.data_as(_VP), C.c_int64(0), None, C.byref(total)))
+    preds = np.zeros(max(total.value, 1), dtype=np.int32)
+    _chk(lib().pb_plan_dependencies(rows, cols, C.c_int64(n), box.ctypes.data_as(_VP), allowed.ctypes.data_as(_VP),
+                                    offsets.ctypes.data_as(_VP), C.c_int64(total.value), preds.ctypes.data_as(_VP), C.byref(total)))
+    return offsets, preds[:total.value]
+
+
 # ---- device objects -----------------------------------------------------------------------------
 class Context:
     def __init__(self, device=0, precision=F32):

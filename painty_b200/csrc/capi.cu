@@ -601,6 +601,27 @@ int pb_expand_stroke(int mode, int n, const double* path_xy, int64_t capacity, d
   PB_API_END
 }
 
+int pb_plan_dependencies(int rows, int cols, int64_t n, const int32_t* box, const int32_t* allowed, int64_t* offsets,
+                         int64_t capacity, int32_t* preds, int64_t* n_preds) {
+  PB_API_BEGIN
+  PB_REQUIRE(rows > 0 && cols > 0 && n >= 0 && n < (int64_t(1) << 31), "pb_plan_dependencies: bad sizes");
+  DataflowPlanner planner(rows, cols);
+  std::vector<int32_t> all;
+  for (int64_t s = 0; s < n; ++s) {
+    auto clip = [&](const int32_t* r) {
+      return Region{std::max(r[0], 0), std::max(r[1], 0), std::min(r[2], cols - 1), std::min(r[3], rows - 1)};
+    };
+    int32_t b = 0, e = 0;
+    planner.add_footprint(static_cast<int32_t>(s), clip(box + 4 * s), clip(allowed + 4 * s), all, b, e);
+    offsets[s]     = b;
+    offsets[s + 1] = e;
+  }
+  if (n == 0) offsets[0] = 0;
+  for (int64_t i = 0; i < std::min<int64_t>(capacity, static_cast<int64_t>(all.size())); ++i) preds[i] = all[static_cast<size_t>(i)];
+  if (n_preds) *n_preds = static_cast<int64_t>(all.size());
+  PB_API_END
+}
+
 // ---- PaintLayer --------------------------------------------------------------------------------------
 int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out) {
   PB_API_BEGIN

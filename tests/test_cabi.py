@@ -104,3 +104,44 @@ def test_no_cpu_fallback(built_lib):
         pytest.skip("a GPU is present")
     with pytest.raises(api.PaintyError):
         api.Context(0, api.F32)
+
+
+def test_dataflow_planner_orders_every_conflicting_pair(built_lib):
+    """The host planner behind the stroke batches: for random box / ring rectangles, every pair whose box meets the
+    other's allowed region must be ordered through the (transitive) predecessor lists; rings that only overlap each
+    other need not be. Pure host code — runs without a GPU."""
+    from painty_b200 import api
+
+    rng = np.random.default_rng(17)
+    rows, cols, n = 1500, 2000, 400
+    box, allowed = [], []
+    for _ in range(n):
+        x, y = int(rng.integers(-50, cols)), int(rng.integers(-50, rows))
+        w, h, m = int(rng.integers(5, 300)), int(rng.integers(5, 300)), int(rng.integers(0, 150))
+        box.append((x, y, x + w, y + h))
+        allowed.append((x - m, y - m, x + w + m, y + h + m))
+    off, preds = api.plan_dependencies(rows, cols, box, allowed)
+    assert off[0] == 0 and off[-1] == len(preds) and all(0 <= p < i for i in range(n) for p in preds[off[i]:off[i + 1]])
+    # transitive closure of "must finish before"
+    before = [set() for _ in range(n)]
+    for i in range(n):
+        for p in preds[off[i]:off[i + 1]]:
+            before[i].add(int(p))
+            before[i] |= before[int(p)]
+
+    def clip(r):
+        return (max(r[0], 0), max(r[1], 0), min(r[2], cols - 1), min(r[3], rows - 1))
+
+    def meets(a, b):
+        a, b = clip(a), clip(b)
+        return a[0] <= a[2] and a[1] <= a[3] and b[0] <= b[2] and b[1] <= b[3] and a[0] <= b[2] and b[0] <= a[2] and a[1] <= b[3] and b[1] <= a[3]
+
+    conflicts = independent = 0
+    for i in range(n):
+        for j in range(i):
+            if meets(box[i], allowed[j]) or meets(allowed[i], box[j]):
+                conflicts += 1
+                assert j in before[i], (j, i)
+            elif j not in before[i]:
+                independent += 1
+    assert conflicts > 1000 and independent > 1000  # the plan really leaves parallelism
