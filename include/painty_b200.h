@@ -76,6 +76,19 @@ int pb_expand_stroke(int mode, int n, const double* path_xy, int64_t capacity, d
 int pb_plan_dependencies(int rows, int cols, int64_t n, const int32_t* box, const int32_t* allowed, int64_t* offsets,
                          int64_t capacity, int32_t* preds, int64_t* n_preds);
 
+/* The footprint brush's dataflow graph at SEGMENT granularity, as pb_fbrush_stroke_batch builds it (host only;
+ * exposed for testing and schedule inspection). Stroke s owns the imprints [first[s], first[s]+count[s]) of cx/cy,
+ * has a footprint of side[s] cells and the given radius. A stroke is cut into segments of seg_len[s] consecutive
+ * imprints (segment_length, enlarged for very long strokes; 0 = whole strokes). Outputs: seg_first[n+1] (first
+ * global segment of each stroke), seg_len[n], and a CSR list per global segment — seg_off[segments+1] (up to
+ * seg_capacity+1 entries written) into pred_stroke/pred_need (up to pred_capacity entries, total in *n_preds):
+ * the segment may start once stroke pred_stroke[i] (always an earlier stroke) has completed pred_need[i] segments.
+ * Call once with zero capacities to size the outputs (seg_first[n] and *n_preds). */
+int pb_plan_segments(int rows, int cols, int64_t n, const int64_t* first, const int64_t* count, const int32_t* side,
+                     const double* radius, const double* cx, const double* cy, int segment_length, int use_snapshot,
+                     int32_t* seg_first, int32_t* seg_len, int64_t seg_capacity, int32_t* seg_off, int64_t pred_capacity,
+                     int32_t* pred_stroke, int32_t* pred_need, int64_t* n_preds);
+
 /* ---- PaintLayer ------------------------------------------------------------------------------ */
 int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out);
 int pb_layer_destroy(pb_layer* l);

@@ -129,6 +129,39 @@ def plan_dependencies(rows, cols, box, allowed):
     return offsets, preds[:total.value]
 
 
+def plan_segments(rows, cols, first, count, side, radius, cx, cy, segment_length=32, use_snapshot=True):
+    """Segment-level dataflow plan of a footprint stroke list (see pb_plan_segments).
+
+    Returns (seg_first[n+1], seg_len[n], seg_off[segments+1], pred_stroke, pred_need)."""
+    first = np.ascontiguousarray(first, dtype=np.int64)
+    count = np.ascontiguousarray(count, dtype=np.int64)
+    side = np.ascontiguousarray(side, dtype=np.int32)
+    radius = np.ascontiguousarray(radius, dtype=np.float64)
+    cx = np.ascontiguousarray(cx, dtype=np.float64)
+    cy = np.ascontiguousarray(cy, dtype=np.float64)
+    n = len(first)
+    seg_first = np.zeros(n + 1, dtype=np.int32)
+    seg_len = np.zeros(max(n, 1), dtype=np.int32)
+    total = C.c_int64(0)
+
+    def call(seg_cap, seg_off, pred_cap, ps, pn):
+        _chk(lib().pb_plan_segments(rows, cols, C.c_int64(n), first.ctypes.data_as(_VP), count.ctypes.data_as(_VP),
+                                    side.ctypes.data_as(_VP), radius.ctypes.data_as(_VP), cx.ctypes.data_as(_VP),
+                                    cy.ctypes.data_as(_VP), int(segment_length), int(bool(use_snapshot)),
+                                    seg_first.ctypes.data_as(_VP), seg_len.ctypes.data_as(_VP), C.c_int64(seg_cap),
+                                    seg_off.ctypes.data_as(_VP), C.c_int64(pred_cap), ps.ctypes.data_as(_VP),
+                                    pn.ctypes.data_as(_VP), C.byref(total)))
+
+    dummy = np.zeros(1, dtype=np.int32)
+    call(0, dummy, 0, dummy, dummy)
+    n_seg, n_pred = int(seg_first[n]), int(total.value)
+    seg_off = np.zeros(n_seg + 1, dtype=np.int32)
+    ps = np.zeros(max(n_pred, 1), dtype=np.int32)
+    pn = np.zeros(max(n_pred, 1), dtype=np.int32)
+    call(n_seg, seg_off, n_pred, ps, pn)
+    return seg_first, seg_len[:n], seg_off, ps[:n_pred], pn[:n_pred]
+
+
 # ---- device objects -----------------------------------------------------------------------------
 class Context:
     def __init__(self, device=0, precision=F32):

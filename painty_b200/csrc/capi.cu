@@ -106,7 +106,7 @@ struct pb_fbrush {
   int dirty_pitch      = 0;
   uint64_t snap_canvas_id = 0, snap_canvas_version = 0;  // canvas state the dirty map is valid for
   // multi-GPU: completion flags other GPUs poll (kDistFlagCapacity ints + 1024 queue counters), batch epoch
-  int* dist_flags       = nullptr;
+  long long* dist_flags = nullptr;
   int dist_epoch        = 0;
   int dist_queue_slot   = 0;
   bool use_snapshot = true;
@@ -250,34 +250,9 @@ struct DistInfo {
   void* snapshot_base[kMaxBands] = {};
   int64_t snapshot_stride[kMaxBands] = {};
   unsigned char* dirty_base[kMaxBands] = {};
-  int* flags_base[kMaxBands] = {};
+  long long* flags_base[kMaxBands] = {};
 };
 constexpr int64_t kDistFlagCapacity = int64_t(1) << 22;
-
-// The BOX a stroke modifies (footprint square around every centre) and everything it reads or writes (the union of
-// the snapshot "allowed" boxes, :298-305: the box grown by the radius). Both padded by 2 px, clipped to the canvas.
-void stroke_regions(const HostStroke& h, const double* cx, const double* cy, int rows, int cols, Region& box, Region& allowed) {
-  box = allowed = Region{1, 1, 0, 0};
-  if (h.n <= 0) return;
-  double lx = cx[h.first], hx = lx, ly = cy[h.first], hy = ly;
-  for (int64_t i = h.first; i < h.first + h.n; ++i) {
-    lx = std::min(lx, cx[i]);
-    hx = std::max(hx, cx[i]);
-    ly = std::min(ly, cy[i]);
-    hy = std::max(hy, cy[i]);
-  }
-  auto grow = [&](double margin) {
-    const double m = (h.g->side - 1) / 2 + margin + 2.0;
-    Region r;
-    r.x0 = static_cast<int>(std::max(0.0, std::floor(lx - m)));
-    r.y0 = static_cast<int>(std::max(0.0, std::floor(ly - m)));
-    r.x1 = static_cast<int>(std::min<double>(cols - 1, std::ceil(hx + m)));
-    r.y1 = static_cast<int>(std::min<double>(rows - 1, std::ceil(hy + m)));
-    return r;
-  };
-  box     = grow(0.0);
-  allowed = grow(h.radius);
-}
 
 // Plans and launches the persistent imprint kernel for a submission-ordered stroke list: one launch per run of
 // consecutive (local) strokes that share a launch class; dependencies are tracked across runs and — with `dist` —
@@ -294,22 +269,33 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
   const bool have_dirty = b->dirty != nullptr && b->snapshot.rows == c->pl.rows && b->snapshot.cols == c->pl.cols;
   PB_REQUIRE(!multi || (have_dirty && b->use_snapshot), "distributed strokes need the snapshot buffer enabled");
 
-  // global plan: executor rank, predecessors (global indices), local numbering
+  // Global plan: executor rank, local numbering, and the dataflow graph at segment granularity (schedule.hpp).
+  // Strokes that stage neighbour rows in windows read them once at the start, so they keep a single segment.
   const size_t n = hs.size();
-  std::vector<int32_t> executor(n, 0), local_index(n, -1), pred_begin(n), pred_end(n), preds;
+  static const int kSegmentLength = [] {
+    const char* e = std::getenv("PB_IMPRINT_SEGMENT");  // imprints per dataflow segment; 0 = whole strokes
+    return e ? std::max(0, std::atoi(e)) : 64;  // measured 16 / 32 / 64: 8.13 / 8.14 / 8.11 s, whole strokes 9.78 s
+  }();
+  std::vector<int32_t> executor(n, 0), local_index(n, -1);
   std::vector<int32_t> counts(kMaxBands, 0);
   std::vector<char> remote(n, 0);
   std::vector<Region> allowed(multi ? n : 0);
-  DataflowPlanner planner(c->rows, c->cols);
-  for (size_t s = 0; s < n; ++s) {
+  auto span_of = [&](size_t s) {
     const HostStroke& h = hs[s];
-    Region box, r;
-    stroke_regions(h, cx, cy, c->rows, c->cols, box, r);
-    if (b->use_snapshot) {
-      planner.add_footprint(static_cast<int32_t>(s), box, r, preds, pred_begin[s], pred_end[s]);
-    } else {
-      planner.add(static_cast<int32_t>(s), box, preds, pred_begin[s], pred_end[s]);
+    bool single         = false;
+    if (multi && h.n > 0) {  // decided from the whole-stroke region, i.e. before the planner asks for segments
+      Region box, r;
+      imprint_regions(h.first, h.n, (h.g->side - 1) / 2, h.radius, cx, cy, c->rows, c->cols, box, r);
+      const int y0 = std::min(std::max(static_cast<int>(cy[h.first]), 0), c->rows - 1);
+      const int ex = std::min(y0 / dist->rows_per_band, dist->world - 1);
+      const int b0 = ex * dist->rows_per_band, b1 = std::min(b0 + dist->rows_per_band, c->rows) - 1;
+      single       = (r.y1 >= r.y0) && (r.y0 < b0 || r.y1 > b1);
     }
+    return StrokeSpan{h.first, h.n, (h.g->side - 1) / 2, h.radius, single};
+  };
+  const SegmentPlan plan = plan_segments(c->rows, c->cols, n, span_of, cx, cy, kSegmentLength, b->use_snapshot,
+                                         [&](size_t s, const Region&, const Region& r) {
+    const HostStroke& h = hs[s];
     if (multi && h.n > 0) {
       const int y0 = std::min(std::max(static_cast<int>(cy[h.first]), 0), c->rows - 1);
       executor[s]  = std::min(y0 / dist->rows_per_band, dist->world - 1);
@@ -318,7 +304,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
       allowed[s]   = r;
     }
     local_index[s] = counts[executor[s]]++;
-  }
+  });
   std::vector<size_t> mine;
   for (size_t s = 0; s < n; ++s)
     if (executor[s] == (multi ? dist->rank : 0)) mine.push_back(s);
@@ -347,7 +333,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
   d_im.upload(im.data(), im.size());
 
   // completion flags: a per-batch buffer on one GPU, the brush's exported buffer + a fresh epoch across GPUs
-  DevBuf<int> d_flags(ctx, multi ? 0 : mine.size() + 1);
+  DevBuf<long long> d_flags(ctx, multi ? 0 : mine.size() + 1);
   int epoch = 1;
   if (multi) {
     epoch = ++b->dist_epoch;
@@ -363,7 +349,8 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     const size_t n_run = run_end - run_begin;
 
     std::vector<DevStroke> ds(n_run);
-    std::vector<int32_t> run_preds;
+    std::vector<int2> run_preds;
+    std::vector<int32_t> run_seg_off(1, 0);
     int max_active = 1;
     size_t max_window = 0;
     for (size_t k = 0; k < n_run; ++k) {
@@ -420,12 +407,15 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
         }
       }
       max_active = std::max(max_active, d.n_active);
-      d.pred_begin = static_cast<int32_t>(run_preds.size());
-      for (int32_t p = pred_begin[s]; p < pred_end[s]; ++p) {
-        const int32_t g = preds[p];
-        run_preds.push_back(multi ? ((executor[g] << 27) | local_index[g]) : local_index[g]);
+      d.seg_begin = static_cast<int32_t>(run_seg_off.size()) - 1;
+      d.seg_len   = plan.seg_len[s];
+      for (int32_t gseg = plan.seg_first[s]; gseg < plan.seg_first[s + 1]; ++gseg) {
+        for (int32_t p = plan.seg_off[gseg]; p < plan.seg_off[gseg + 1]; ++p) {
+          const int32_t g = plan.pred_stroke[p];
+          run_preds.push_back(make_int2(multi ? ((executor[g] << 27) | local_index[g]) : local_index[g], plan.pred_need[p]));
+        }
+        run_seg_off.push_back(static_cast<int32_t>(run_preds.size()));
       }
-      d.pred_end = static_cast<int32_t>(run_preds.size());
     }
 
     ImprintLaunch L{};
@@ -444,7 +434,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
       }
       L.rows_per_band = dist->rows_per_band;
       L.my_band       = dist->rank;
-      L.queue         = b->dist_flags + kDistFlagCapacity + (b->dist_queue_slot++ % 1024);
+      L.queue         = reinterpret_cast<int*>(b->dist_flags + kDistFlagCapacity + (b->dist_queue_slot++ % 1024));
       PB_CUDA(cudaMemsetAsync(L.queue, 0, sizeof(int), ctx->stream));
     } else {
       for (int p = 0; p < kLayerPlanes; ++p) {
@@ -455,7 +445,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
       L.done[0]       = d_flags.p;
       L.rows_per_band = std::max(c->pl.rows, 1);
       L.my_band       = 0;
-      L.queue         = d_flags.p + mine.size();
+      L.queue         = reinterpret_cast<int*>(d_flags.p + mine.size());
       if (run_begin > 0) PB_CUDA(cudaMemsetAsync(L.queue, 0, sizeof(int), ctx->stream));
     }
     for (int p = 0; p < kLayerPlanes; ++p) L.pick_dense[p] = b->pick.base ? b->pick.plane(p) : nullptr;
@@ -473,9 +463,11 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     L.n_strokes       = static_cast<int64_t>(n_run);
 
     DevBuf<DevStroke> d_strokes(ctx, ds.size());
-    DevBuf<int32_t> d_preds(ctx, run_preds.size());
+    DevBuf<int2> d_preds(ctx, run_preds.size());
+    DevBuf<int32_t> d_seg_off(ctx, run_seg_off.size());
     d_strokes.upload(ds.data(), ds.size());
     d_preds.upload(run_preds.data(), run_preds.size());
+    d_seg_off.upload(run_seg_off.data(), run_seg_off.size());
     DevBuf<char> d_scratch(ctx, static_cast<size_t>(L.scratch_stride) * L.grid * ctx->esize());
     const size_t n_groups = static_cast<size_t>(L.grid / (L.cluster * L.group));
     DevBuf<unsigned char> d_windows(ctx, 2 * max_window * n_groups);
@@ -489,6 +481,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     L.strokes  = d_strokes.p;
     L.imprints = d_im.p;
     L.preds    = d_preds.p;
+    L.seg_off  = d_seg_off.p;
     L.counters = b->d_counters;
     imprint_launch(ctx, L, smem);
     if (b->count_visited) imprint_count_visited(ctx, d_strokes.p, L.n_strokes, d_im.p, c->rows, c->cols, b->d_counters + 1);
@@ -619,6 +612,32 @@ int pb_plan_dependencies(int rows, int cols, int64_t n, const int32_t* box, cons
   if (n == 0) offsets[0] = 0;
   for (int64_t i = 0; i < std::min<int64_t>(capacity, static_cast<int64_t>(all.size())); ++i) preds[i] = all[static_cast<size_t>(i)];
   if (n_preds) *n_preds = static_cast<int64_t>(all.size());
+  PB_API_END
+}
+
+int pb_plan_segments(int rows, int cols, int64_t n, const int64_t* first, const int64_t* count, const int32_t* side,
+                     const double* radius, const double* cx, const double* cy, int segment_length, int use_snapshot,
+                     int32_t* seg_first, int32_t* seg_len, int64_t seg_capacity, int32_t* seg_off, int64_t pred_capacity,
+                     int32_t* pred_stroke, int32_t* pred_need, int64_t* n_preds) {
+  PB_API_BEGIN
+  PB_REQUIRE(rows > 0 && cols > 0 && n >= 0 && n < (int64_t(1) << 31), "pb_plan_segments: bad sizes");
+  const SegmentPlan plan = plan_segments(
+      rows, cols, static_cast<size_t>(n),
+      [&](size_t s) { return StrokeSpan{first[s], count[s], (side[s] - 1) / 2, radius[s], false}; }, cx, cy, segment_length,
+      use_snapshot != 0, [](size_t, const Region&, const Region&) {});
+  for (int64_t s = 0; s < n; ++s) {
+    seg_first[s] = plan.seg_first[static_cast<size_t>(s)];
+    seg_len[s]   = plan.seg_len[static_cast<size_t>(s)];
+  }
+  seg_first[n] = plan.seg_first[static_cast<size_t>(n)];
+  for (int64_t i = 0; i < std::min<int64_t>(seg_capacity + 1, static_cast<int64_t>(plan.seg_off.size())); ++i)
+    seg_off[i] = plan.seg_off[static_cast<size_t>(i)];
+  const int64_t np = static_cast<int64_t>(plan.pred_stroke.size());
+  for (int64_t i = 0; i < std::min(pred_capacity, np); ++i) {
+    pred_stroke[i] = plan.pred_stroke[static_cast<size_t>(i)];
+    pred_need[i]   = plan.pred_need[static_cast<size_t>(i)];
+  }
+  if (n_preds) *n_preds = np;
   PB_API_END
 }
 
@@ -1160,8 +1179,8 @@ int pb_fbrush_dist_storage(pb_fbrush* b, pb_canvas* c, void** snapshot_base, int
   DeviceGuard g(b->ctx);
   ensure_snapshot(b, c);
   if (b->dist_flags == nullptr) {
-    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->dist_flags), sizeof(int) * (kDistFlagCapacity + 1024)));
-    PB_CUDA(cudaMemsetAsync(b->dist_flags, 0, sizeof(int) * (kDistFlagCapacity + 1024), b->ctx->stream));
+    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->dist_flags), sizeof(long long) * (kDistFlagCapacity + 1024)));
+    PB_CUDA(cudaMemsetAsync(b->dist_flags, 0, sizeof(long long) * (kDistFlagCapacity + 1024), b->ctx->stream));
   }
   PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
   if (snapshot_base) *snapshot_base = b->snapshot.base;
@@ -1189,7 +1208,7 @@ int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* 
     di.snapshot_base[r]   = d->snapshot_base[r];
     di.snapshot_stride[r] = d->snapshot_stride[r];
     di.dirty_base[r]      = static_cast<unsigned char*>(d->dirty_base[r]);
-    di.flags_base[r]      = static_cast<int*>(d->flags_base[r]);
+    di.flags_base[r]      = static_cast<long long*>(d->flags_base[r]);
   }
   stroke_batch_impl(b, c, n_strokes, strokes, n_imprints, cx, cy, theta, &di);
   PB_API_END

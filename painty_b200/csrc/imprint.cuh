@@ -20,6 +20,7 @@ struct DevImprint {  // per-imprint constants, computed on the host in f64 (Foot
 };
 
 constexpr int kMaxBands = 8;  // GPUs of one NVSwitch node
+constexpr int kStrokeDone = 0x7fffffff;  // progress value of a finished stroke
 
 struct DevStroke {
   int64_t first_imprint;
@@ -30,7 +31,8 @@ struct DevStroke {
   int32_t size_map, side;
   double radius;  // FootprintBrush::_radius as used by updateSnapshot (:298-305)
   double paintK[3], paintS[3];
-  int32_t pred_begin, pred_end;  // into preds[]
+  int32_t seg_begin;             // first entry of this stroke in seg_off[] (one entry per segment, + 1)
+  int32_t seg_len;               // imprints per dataflow segment (>= 1)
   int32_t flags;                 // bit0: load pick state from the dense map, bit1: store it back,
                                  // bit2: rows of another GPU are accessed directly through NVLink (system-scope
                                  //       fences at every barrier), bit3: they are staged in local windows instead
@@ -64,8 +66,11 @@ struct ImprintLaunch {
   const DevStroke* strokes;
   int64_t n_strokes;
   const DevImprint* imprints;
-  const int32_t* preds;          // single GPU: stroke index; multi GPU: (rank << 27) | index on that rank
-  int* done[kMaxBands];          // per-rank completion flags ([my_band] is local); a stroke is done when == epoch
+  // Dataflow: segment j of the launch waits for preds[seg_off[j] .. seg_off[j+1]) = (stroke, segments needed);
+  // stroke = flag index (single GPU) or (rank << 27) | flag index on that rank (multi GPU).
+  const int2* preds;
+  const int32_t* seg_off;
+  long long* done[kMaxBands];    // per-rank progress words ([my_band] is local): (epoch << 32) | segments completed
   int epoch;
   int flag_offset;               // flag index of this launch's stroke 0 (strokes of earlier launches come first)
   int* queue;                    // single counter (zeroed)

@@ -8,6 +8,7 @@
 // sufficient: each of them in turn waited for the previous toucher of the shared tile (induction).
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <vector>
 
@@ -82,5 +83,114 @@ class DataflowPlanner {
   std::vector<int32_t> last_;
   std::vector<std::vector<int32_t>> ring_;
 };
+
+// The BOX a run of footprint imprints modifies (footprint square of half side `half_side` around every centre) and
+// everything it reads or writes (the union of the snapshot "allowed" boxes, FootprintBrush.hxx:298-305: the box
+// grown by the radius). Both padded by 2 px, clipped to the canvas.
+inline void imprint_regions(int64_t first, int64_t count, int half_side, double radius, const double* cx, const double* cy,
+                            int rows, int cols, Region& box, Region& allowed) {
+  box = allowed = Region{1, 1, 0, 0};
+  if (count <= 0) return;
+  double lx = cx[first], hx = lx, ly = cy[first], hy = ly;
+  for (int64_t i = first; i < first + count; ++i) {
+    lx = std::min(lx, cx[i]);
+    hx = std::max(hx, cx[i]);
+    ly = std::min(ly, cy[i]);
+    hy = std::max(hy, cy[i]);
+  }
+  auto grow = [&](double margin) {
+    const double m = half_side + margin + 2.0;
+    Region r;
+    r.x0 = static_cast<int>(std::max(0.0, std::floor(lx - m)));
+    r.y0 = static_cast<int>(std::max(0.0, std::floor(ly - m)));
+    r.x1 = static_cast<int>(std::min<double>(cols - 1, std::ceil(hx + m)));
+    r.y1 = static_cast<int>(std::min<double>(rows - 1, std::ceil(hy + m)));
+    return r;
+  };
+  box     = grow(0.0);
+  allowed = grow(radius);
+}
+
+// Dataflow graph of a footprint stroke list at SEGMENT granularity. A stroke is cut into segments of seg_len
+// consecutive imprints; segment k of a stroke may start once every EARLIER stroke g listed for it has completed
+// `need` segments. The executor publishes a stroke's progress at segment boundaries, so a later stroke starts (or
+// continues) as soon as the earlier ones have moved past the part of the canvas its next segment needs — the
+// critical path of densely overlapping stroke lists shrinks accordingly.
+// The planner sees the segments in submission order. A dependency on segment m of stroke g becomes "g has
+// completed m + 1 segments" (largest requirement per g kept); dependencies on the own stroke are dropped: its
+// segments run in order anyway, and each of them registered the predecessors it displaced in the tile tables, so
+// the induction argument of DataflowPlanner still holds.
+struct StrokeSpan {
+  int64_t first, count;  // imprints [first, first + count) of the cx/cy arrays
+  int half_side;         // (footprint side - 1) / 2
+  double radius;
+  bool single;           // keep the stroke in one segment (it reads its whole region up front)
+};
+struct SegmentPlan {
+  std::vector<int32_t> seg_first;  // [n + 1] first segment of each stroke
+  std::vector<int32_t> seg_len;    // [n] imprints per segment
+  std::vector<int32_t> seg_off;    // [segments + 1] CSR offsets into pred_stroke / pred_need
+  std::vector<int32_t> pred_stroke, pred_need;
+};
+constexpr int kMaxSegmentsPerStroke = 4000;
+
+template <typename SpanFn, typename VisitFn>
+SegmentPlan plan_segments(int rows, int cols, size_t n, SpanFn&& span_of, const double* cx, const double* cy, int segment_length,
+                          bool use_snapshot, VisitFn&& visit_stroke) {
+  SegmentPlan plan;
+  plan.seg_first.assign(n + 1, 0);
+  plan.seg_len.assign(n, 1);
+  plan.seg_off.assign(1, 0);
+  std::vector<int32_t> owner, raw;
+  DataflowPlanner planner(rows, cols);
+  for (size_t s = 0; s < n; ++s) {
+    const StrokeSpan sp = span_of(s);
+    Region box, allowed;
+    imprint_regions(sp.first, sp.count, sp.half_side, sp.radius, cx, cy, rows, cols, box, allowed);
+    visit_stroke(s, box, allowed);
+    const int64_t whole = std::max<int64_t>(sp.count, 1);
+    int64_t len = (segment_length <= 0 || sp.single)
+                      ? whole
+                      : std::max<int64_t>(segment_length, (whole + kMaxSegmentsPerStroke - 1) / kMaxSegmentsPerStroke);
+    len                  = std::min(len, whole);
+    const int nseg       = static_cast<int>((whole + len - 1) / len);
+    plan.seg_len[s]      = static_cast<int32_t>(len);
+    plan.seg_first[s + 1] = plan.seg_first[s] + nseg;
+    for (int k = 0; k < nseg; ++k) {
+      const int32_t gseg = plan.seg_first[s] + k;
+      Region sbox = box, sall = allowed;
+      if (nseg > 1)
+        imprint_regions(sp.first + k * len, std::min<int64_t>(len, sp.count - k * len), sp.half_side, sp.radius, cx, cy, rows,
+                        cols, sbox, sall);
+      raw.clear();
+      int32_t rb = 0, re = 0;
+      if (use_snapshot) {
+        planner.add_footprint(gseg, sbox, sall, raw, rb, re);
+      } else {
+        planner.add(gseg, sbox, raw, rb, re);
+      }
+      const size_t begin = plan.pred_stroke.size();
+      for (int32_t p : raw) {
+        const int32_t g = owner[p];
+        if (g == static_cast<int32_t>(s)) continue;
+        const int32_t need = p - plan.seg_first[g] + 1;
+        bool merged        = false;
+        for (size_t q = begin; q < plan.pred_stroke.size() && !merged; ++q) {
+          if (plan.pred_stroke[q] == g) {
+            plan.pred_need[q] = std::max(plan.pred_need[q], need);
+            merged            = true;
+          }
+        }
+        if (!merged) {
+          plan.pred_stroke.push_back(g);
+          plan.pred_need.push_back(need);
+        }
+      }
+      owner.push_back(static_cast<int32_t>(s));
+      plan.seg_off.push_back(static_cast<int32_t>(plan.pred_stroke.size()));
+    }
+  }
+  return plan;
+}
 
 }  // namespace pb

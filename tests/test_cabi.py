@@ -145,3 +145,84 @@ def test_dataflow_planner_orders_every_conflicting_pair(built_lib):
             elif j not in before[i]:
                 independent += 1
     assert conflicts > 1000 and independent > 1000  # the plan really leaves parallelism
+
+
+def test_segment_plan_orders_every_conflicting_segment_pair(built_lib):
+    """The footprint brush tracks dependencies per SEGMENT of a stroke (progress counters instead of one completion
+    flag). For a random overlapping stroke list: every pair of segments of two different strokes whose regions
+    conflict (box of one meets the allowed region of the other) must be ordered, earlier stroke first, through the
+    waits (stroke, segments needed) + the in-order execution of a stroke's own segments. Pure host code."""
+    from painty_b200 import api, assets
+
+    rng = np.random.default_rng(5)
+    rows, cols, n, seg = 1200, 1600, 90, 16
+    first, count, side, radius, cx, cy = [], [], [], [], [], []
+    for _ in range(n):
+        m = int(rng.integers(1, 300))
+        r = float(rng.uniform(8, 40))
+        x, y, a = rng.uniform(-20, cols + 20), rng.uniform(-20, rows + 20), rng.uniform(0, 2 * np.pi)
+        first.append(len(cx)); count.append(m); radius.append(r); side.append(assets.footprint_geometry(r)[3])
+        for _ in range(m):
+            cx.append(x); cy.append(y)
+            a += rng.normal(0, 0.05); x += np.cos(a); y += np.sin(a)
+    first.append(len(cx)); count.append(0); radius.append(10.0); side.append(assets.footprint_geometry(10.0)[3])  # empty stroke
+    n += 1
+    seg_first, seg_len, seg_off, ps, pn = api.plan_segments(rows, cols, first, count, side, radius, cx, cy, seg, True)
+    n_seg = int(seg_first[-1])
+    assert len(seg_off) == n_seg + 1 and seg_off[0] == 0 and seg_off[-1] == len(ps)
+    owner = np.repeat(np.arange(n), np.diff(seg_first))
+    for s in range(n):
+        assert seg_first[s + 1] - seg_first[s] == max(1, -(-count[s] // seg_len[s]))
+    # whole strokes (segment_length 0) give one segment each
+    sf0 = api.plan_segments(rows, cols, first, count, side, radius, cx, cy, 0, True)[0]
+    assert list(sf0) == list(range(n + 1))
+
+    cxa, cya = np.asarray(cx), np.asarray(cy)
+
+    def regions(s, k):
+        a = first[s] + k * seg_len[s]
+        m = min(seg_len[s], count[s] - k * seg_len[s])
+        if m <= 0:
+            return None, None
+        half = (side[s] - 1) // 2
+        out = []
+        for margin in (0.0, radius[s]):
+            mm = half + margin + 2.0
+            out.append((max(0, int(np.floor(cxa[a:a + m].min() - mm))), max(0, int(np.floor(cya[a:a + m].min() - mm))),
+                        min(cols - 1, int(np.ceil(cxa[a:a + m].max() + mm))), min(rows - 1, int(np.ceil(cya[a:a + m].max() + mm)))))
+        return out
+
+    def meets(a, b):
+        return (a is not None and b is not None and a[0] <= a[2] and a[1] <= a[3] and b[0] <= b[2] and b[1] <= b[3]
+                and a[0] <= b[2] and b[0] <= a[2] and a[1] <= b[3] and b[1] <= a[3])
+
+    box, alw = zip(*[regions(int(owner[g]), g - int(seg_first[owner[g]])) for g in range(n_seg)])
+    # reach[g] = bitset of the segments that are guaranteed complete before segment g starts
+    reach = [0] * n_seg
+    for g in range(n_seg):
+        s = int(owner[g])
+        r = 0
+        if g > seg_first[s]:
+            r |= reach[g - 1] | (1 << (g - 1))
+        for i in range(seg_off[g], seg_off[g + 1]):
+            p, need = int(ps[i]), int(pn[i])
+            assert p < s and 1 <= need <= seg_first[p + 1] - seg_first[p]
+            q = int(seg_first[p]) + need - 1
+            r |= reach[q] | (1 << q)
+        reach[g] = r
+    conflicts = free = 0
+    for g in range(n_seg):
+        for q in range(int(seg_first[owner[g]])):  # segments of earlier strokes
+            if meets(box[g], alw[q]) or meets(alw[g], box[q]):
+                conflicts += 1
+                assert (reach[g] >> q) & 1, (q, g)
+            elif not (reach[g] >> q) & 1:
+                free += 1
+    assert conflicts > 1000 and free > 1000
+    # finer than stroke level: some stroke starts before an earlier stroke it depends on has finished
+    partial = 0
+    for s in range(n):
+        g0 = int(seg_first[s])
+        for i in range(seg_off[g0], seg_off[g0 + 1]):
+            partial += int(pn[i]) < seg_first[ps[i] + 1] - seg_first[ps[i]]
+    assert partial > 0
