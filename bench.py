@@ -379,7 +379,8 @@ def main():
     # roofline claim — reported with the upper-bound byte model of SURVEY.md §8d (88 B per active stroke-pixel)
     imp_ms = t_imp / args.steps
     line["imprint"] = {"kernel": "imprint_kernel<float>", "bound": "latency (dependency chain of imprints, see DESIGN.md §5)",
-                       "ms_per_step": imp_ms, "imprints_per_s": world * len(cx) / max(world, 1) / (imp_ms * 1e-3),
+                       "ms_per_step": imp_ms, "ms_each_step": [round(t[0].elapsed_time(t[1]), 1) for t in timers],
+                       "imprints_per_s": world * len(cx) / max(world, 1) / (imp_ms * 1e-3),
                        "active_stroke_pixels_per_s": active / (imp_ms * 1e-3),
                        "model_bytes_per_active_px": 88, "model_GBps": 88 * active / (imp_ms * 1e-3) / 1e9}
     if rank == 0 and not args.no_cpu and world == 1:

@@ -89,6 +89,16 @@ int pb_plan_segments(int rows, int cols, int64_t n, const int64_t* first, const 
                      int32_t* seg_first, int32_t* seg_len, int64_t seg_capacity, int32_t* seg_off, int64_t pred_capacity,
                      int32_t* pred_stroke, int32_t* pred_need, int64_t* n_preds);
 
+/* Claim order of the device stroke queues (host only; exposed for testing). The strokes are list-scheduled with a
+ * cost model: stroke s runs on slot pool pool[s] (its GPU) in launch run[s] of that pool and costs cost[s] per
+ * imprint; pool p has runs_per_pool[p] launches with slots[...] concurrent strokes each (flattened pool-major).
+ * order[n] receives the global claim sequence: a topological order of the segment-level dependency graph (every
+ * stroke after all strokes any of its segments waits for) that keeps the runs of a pool in sequence. */
+int pb_plan_claim_order(int rows, int cols, int64_t n, const int64_t* first, const int64_t* count, const int32_t* side,
+                        const double* radius, const double* cx, const double* cy, int segment_length, int use_snapshot,
+                        const int32_t* pool, const int32_t* run, const double* cost, int n_pools, const int32_t* runs_per_pool,
+                        const int32_t* slots, int32_t* order);
+
 /* ---- PaintLayer ------------------------------------------------------------------------------ */
 int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out);
 int pb_layer_destroy(pb_layer* l);

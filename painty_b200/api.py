@@ -162,6 +162,24 @@ def plan_segments(rows, cols, first, count, side, radius, cx, cy, segment_length
     return seg_first, seg_len[:n], seg_off, ps[:n_pred], pn[:n_pred]
 
 
+def plan_claim_order(rows, cols, first, count, side, radius, cx, cy, pool, run, cost, slots, segment_length=64,
+                     use_snapshot=True):
+    """Host list-scheduling of a footprint stroke list (see pb_plan_claim_order). `slots` = per pool, the list of
+    concurrent strokes of each of its runs. Returns the global claim sequence (stroke indices)."""
+    n = len(first)
+    arr = lambda a, t: np.ascontiguousarray(a, dtype=t)
+    first, count, side, radius = arr(first, np.int64), arr(count, np.int64), arr(side, np.int32), arr(radius, np.float64)
+    cx, cy, pool, run, cost = arr(cx, np.float64), arr(cy, np.float64), arr(pool, np.int32), arr(run, np.int32), arr(cost, np.float64)
+    rpp = arr([len(x) for x in slots], np.int32)
+    flat = arr([v for x in slots for v in x], np.int32)
+    order = np.zeros(max(n, 1), dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(_VP)
+    _chk(lib().pb_plan_claim_order(rows, cols, C.c_int64(n), p(first), p(count), p(side), p(radius), p(cx), p(cy),
+                                   int(segment_length), int(bool(use_snapshot)), p(pool), p(run), p(cost), len(slots),
+                                   p(rpp), p(flat), p(order)))
+    return order[:n]
+
+
 # ---- device objects -----------------------------------------------------------------------------
 class Context:
     def __init__(self, device=0, precision=F32):

@@ -539,7 +539,8 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
   for (;;) {
     sync_all();
     if (crank == 0 && tid == 0) {
-      s_stroke = atomicAdd(L.queue, 1);
+      const long long ticket = atomicAdd(L.queue, 1);
+      s_stroke = (ticket < L.n_strokes && L.order != nullptr) ? static_cast<long long>(L.order[ticket]) : ticket;
       if (G > 1) __stcg(L.group_stroke + group, s_stroke);
     }
     sync_all();

@@ -73,7 +73,8 @@ struct ImprintLaunch {
   long long* done[kMaxBands];    // per-rank progress words ([my_band] is local): (epoch << 32) | segments completed
   int epoch;
   int flag_offset;               // flag index of this launch's stroke 0 (strokes of earlier launches come first)
-  int* queue;                    // single counter (zeroed)
+  int* queue;                    // single counter (zeroed): tickets
+  const int32_t* order;          // ticket -> stroke of this launch (host-planned claim order); nullptr = identity
   unsigned long long* counters;  // [0] active stroke-pixels
   unsigned char* win_scratch;  // staging windows, win_stride bytes per stroke slot (two halves, one per window)
   int64_t win_stride;

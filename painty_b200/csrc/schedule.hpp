@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <functional>
+#include <utility>
 #include <vector>
 
 namespace pb {
@@ -191,6 +193,205 @@ SegmentPlan plan_segments(int rows, int cols, size_t n, SpanFn&& span_of, const 
     }
   }
   return plan;
+}
+
+// Claim order of the device queues. The imprint kernel's clusters pop strokes from a queue strictly in order and
+// block on the dataflow waits, so a stroke that is not ready yet holds a cluster while later strokes that could
+// run stay in the queue (head-of-line blocking). The host therefore list-schedules the batch once with a cost
+// model and hands the device the resulting CLAIM ORDER: the device still pops in order, but the order is the one
+// in which an ideal ready-first scheduler would have started the strokes.
+//
+// Model: every stroke belongs to a slot POOL (the GPU that executes it) and to a RUN (kernel launch) of that pool;
+// a pool works on one run at a time, with slots[pool][run] concurrent strokes. A free slot claims the first
+// stroke among the next `window` unclaimed ones of the current run (submission order) whose predecessor strokes
+// are all CLAIMED and whose first segment is ready. Claiming only after all predecessors makes the global claim
+// sequence T a topological order of the dependency graph, and per-pool orders are T restricted to the pool —
+// which is what keeps in-order popping deadlock free: the T-earliest unfinished stroke is always claimed and all
+// its predecessors are finished. Deterministic: every rank computes the same T from the same inputs.
+struct ClaimSpec {
+  int32_t pool, run;
+  double cost;  // estimated duration of one imprint (any consistent unit)
+};
+
+inline std::vector<int32_t> plan_claim_order(const SegmentPlan& plan, const std::vector<int64_t>& count,
+                                             const std::vector<ClaimSpec>& spec, const std::vector<std::vector<int>>& slots,
+                                             int window = 64) {
+  const int32_t n = static_cast<int32_t>(count.size());
+  std::vector<int32_t> order;
+  order.reserve(static_cast<size_t>(n));
+  if (n == 0) return order;
+  // stroke-level predecessor sets (unique) and their transpose
+  std::vector<int32_t> unclaimed_preds(static_cast<size_t>(n), 0), succ_off(static_cast<size_t>(n) + 1, 0), succ;
+  {
+    std::vector<std::pair<int32_t, int32_t>> edges;  // (pred, stroke)
+    std::vector<int32_t> tmp;
+    for (int32_t s = 0; s < n; ++s) {
+      tmp.assign(plan.pred_stroke.begin() + plan.seg_off[plan.seg_first[s]], plan.pred_stroke.begin() + plan.seg_off[plan.seg_first[s + 1]]);
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      unclaimed_preds[s] = static_cast<int32_t>(tmp.size());
+      for (int32_t g : tmp) {
+        edges.emplace_back(g, s);
+        ++succ_off[static_cast<size_t>(g) + 1];
+      }
+    }
+    for (int32_t g = 0; g < n; ++g) succ_off[g + 1] += succ_off[g];
+    succ.resize(edges.size());
+    std::vector<int32_t> fill(succ_off.begin(), succ_off.end() - 1);
+    for (const auto& e : edges) succ[fill[e.first]++] = e.second;
+  }
+  struct Pool {
+    std::vector<std::vector<int32_t>> pending;  // per run: strokes in submission order
+    std::vector<size_t> head;                   // per run: first possibly unclaimed entry
+    std::vector<int32_t> left;                  // per run: strokes not finished yet
+    int run = 0;
+    std::vector<int32_t> slot_stroke, slot_seg;  // -1 = idle
+    std::vector<char> slot_running;
+  };
+  std::vector<Pool> pools(slots.size());
+  for (size_t p = 0; p < pools.size(); ++p) {
+    pools[p].pending.resize(slots[p].size());
+    pools[p].head.assign(slots[p].size(), 0);
+    pools[p].left.assign(slots[p].size(), 0);
+  }
+  for (int32_t s = 0; s < n; ++s) {
+    pools[spec[s].pool].pending[spec[s].run].push_back(s);
+    ++pools[spec[s].pool].left[spec[s].run];
+  }
+  auto open_run = [&](Pool& P) {
+    while (P.run < static_cast<int>(P.pending.size()) && P.left[P.run] == 0) ++P.run;
+    if (P.run < static_cast<int>(P.pending.size())) {
+      const int k = std::max(1, slots[&P - pools.data()][P.run]);
+      P.slot_stroke.assign(k, -1);
+      P.slot_seg.assign(k, 0);
+      P.slot_running.assign(k, 0);
+    } else {
+      P.slot_stroke.clear();
+    }
+  };
+  for (Pool& P : pools) open_run(P);
+
+  std::vector<int32_t> progress(static_cast<size_t>(n), 0);
+  std::vector<char> claimed(static_cast<size_t>(n), 0);
+  // wake lists: pools to rescan / (pool, slot) to recheck when a stroke makes progress
+  std::vector<std::vector<int32_t>> wake_pool(static_cast<size_t>(n)), wake_slot(static_cast<size_t>(n));
+  struct Event {
+    double t;
+    int32_t pool, slot;
+    bool operator>(const Event& o) const { return t != o.t ? t > o.t : (pool != o.pool ? pool > o.pool : slot > o.slot); }
+  };
+  std::vector<Event> heap;
+  auto push = [&](Event e) {
+    heap.push_back(e);
+    std::push_heap(heap.begin(), heap.end(), std::greater<Event>());
+  };
+  double now = 0.0;
+  // first unsatisfied predecessor of segment k of stroke s, or -1
+  auto blocker = [&](int32_t s, int32_t k) {
+    const int32_t g = plan.seg_first[s] + k;
+    for (int32_t i = plan.seg_off[g]; i < plan.seg_off[g + 1]; ++i)
+      if (progress[plan.pred_stroke[i]] < plan.pred_need[i]) return plan.pred_stroke[i];
+    return -1;
+  };
+  auto seg_count = [&](int32_t s) { return plan.seg_first[s + 1] - plan.seg_first[s]; };
+  auto start_segment = [&](int32_t p, int32_t i) {  // slot holds a stroke that is not running: run its segment if ready
+    Pool& P          = pools[p];
+    const int32_t s = P.slot_stroke[i], k = P.slot_seg[i];
+    const int32_t b = blocker(s, k);
+    if (b >= 0) {
+      wake_slot[b].push_back(p);
+      wake_slot[b].push_back(i);
+      return;
+    }
+    const int64_t m   = std::max<int64_t>(0, std::min<int64_t>(plan.seg_len[s], count[s] - static_cast<int64_t>(k) * plan.seg_len[s]));
+    P.slot_running[i] = 1;
+    push(Event{now + static_cast<double>(m) * spec[s].cost, p, i});
+  };
+  auto scan_pool = [&](int32_t p) {
+    Pool& P = pools[p];
+    if (P.run >= static_cast<int>(P.pending.size())) return;
+    std::vector<int32_t>& pend = P.pending[P.run];
+    size_t& head               = P.head[P.run];
+    for (size_t i = 0; i < P.slot_stroke.size(); ++i) {
+      if (P.slot_stroke[i] >= 0) continue;
+      while (head < pend.size() && claimed[pend[head]]) ++head;
+      int32_t pick = -1;
+      int seen     = 0;
+      for (size_t q = head; q < pend.size() && seen < window; ++q) {
+        const int32_t s = pend[q];
+        if (claimed[s]) continue;
+        ++seen;
+        if (unclaimed_preds[s] > 0) continue;  // wakes up through the claim of its predecessor (same scan loop)
+        const int32_t b = blocker(s, 0);
+        if (b < 0) {
+          pick = s;
+          break;
+        }
+        if (wake_pool[b].empty() || wake_pool[b].back() != p) wake_pool[b].push_back(p);
+      }
+      if (pick < 0) return;  // no candidate for this slot => none for the other idle slots either
+      claimed[pick] = 1;
+      order.push_back(pick);
+      for (int32_t j = succ_off[pick]; j < succ_off[pick + 1]; ++j) --unclaimed_preds[succ[j]];
+      P.slot_stroke[i] = pick;
+      P.slot_seg[i]    = 0;
+      start_segment(p, static_cast<int32_t>(i));
+    }
+  };
+  auto scan_all = [&]() {
+    // a claim can unblock candidates of other pools (their predecessors are now all claimed): iterate to a fixpoint
+    size_t before;
+    do {
+      before = order.size();
+      for (size_t p = 0; p < pools.size(); ++p) scan_pool(static_cast<int32_t>(p));
+    } while (order.size() != before);
+  };
+  scan_all();
+  std::vector<int32_t> wp, ws;
+  while (!heap.empty()) {
+    std::pop_heap(heap.begin(), heap.end(), std::greater<Event>());
+    const Event e = heap.back();
+    heap.pop_back();
+    now       = e.t;
+    Pool& P   = pools[e.pool];
+    const int32_t s = P.slot_stroke[e.slot];
+    const int32_t k = P.slot_seg[e.slot] + 1;
+    P.slot_running[e.slot] = 0;
+    bool freed = false;
+    if (k >= seg_count(s)) {
+      progress[s]           = 0x7fffffff;
+      P.slot_stroke[e.slot] = -1;
+      freed                 = true;
+      if (--P.left[P.run] == 0) open_run(P);
+    } else {
+      progress[s]        = k;
+      P.slot_seg[e.slot] = k;
+    }
+    wp.swap(wake_pool[s]);
+    ws.swap(wake_slot[s]);
+    wake_pool[s].clear();
+    wake_slot[s].clear();
+    if (!freed) start_segment(e.pool, e.slot);
+    for (size_t i = 0; i + 1 < ws.size(); i += 2) {
+      Pool& Q = pools[ws[i]];
+      const int32_t sl = ws[i + 1];
+      if (sl < static_cast<int32_t>(Q.slot_stroke.size()) && Q.slot_stroke[sl] >= 0 && !Q.slot_running[sl]) start_segment(ws[i], sl);
+    }
+    const size_t before = order.size();
+    std::sort(wp.begin(), wp.end());
+    wp.erase(std::unique(wp.begin(), wp.end()), wp.end());
+    if (freed && !std::binary_search(wp.begin(), wp.end(), e.pool)) scan_pool(e.pool);
+    for (int32_t p : wp) scan_pool(p);
+    if (order.size() != before) scan_all();
+    wp.clear();
+    ws.clear();
+  }
+  // Anything the model left unclaimed (cannot happen for a consistent plan) keeps its submission order.
+  if (order.size() != static_cast<size_t>(n)) {
+    order.clear();
+    for (int32_t s = 0; s < n; ++s) order.push_back(s);
+  }
+  return order;
 }
 
 }  // namespace pb
