@@ -768,7 +768,9 @@ __global__ void __launch_bounds__(256) count_visited_kernel(const DevStroke* str
 
 // variants by maximum block size: smaller CTAs get a larger register budget (no spills on the critical path).
 // A 1024-thread variant (64 registers, ~1.5 KB of spill traffic per thread) was measured and is slower: 24.3 vs
-// 21.1 us per imprint at r = 129, 8.71 vs 8.14 s on the 10k-stroke workload.
+// 21.1 us per imprint at r = 129, 8.71 vs 8.14 s on the 10k-stroke workload. So is a 384-thread variant with two
+// cells in flight per thread (168 registers): 23.1 us at r = 129, 18.5 vs 16.6 us at r = 112 — for the large
+// footprints more resident warps beat more independent work per thread.
 template <typename T, bool CL, bool MULTI>
 const void* kernel_ptr_b(int block) {
   if (block <= 256) return reinterpret_cast<const void*>(imprint_kernel<T, CL, 256, MULTI>);
