@@ -83,9 +83,11 @@ int pb_plan_dependencies(int rows, int cols, int64_t n, const int32_t* box, cons
  * global segment of each stroke), seg_len[n], and a CSR list per global segment — seg_off[segments+1] (up to
  * seg_capacity+1 entries written) into pred_stroke/pred_need (up to pred_capacity entries, total in *n_preds):
  * the segment may start once stroke pred_stroke[i] (always an earlier stroke) has completed pred_need[i] segments.
- * Call once with zero capacities to size the outputs (seg_first[n] and *n_preds). */
+ * single (may be NULL): non-zero keeps that stroke in one segment (what the multi-GPU path does for strokes that stage
+ * neighbour rows). Call once with zero capacities to size the outputs (seg_first[n] and *n_preds). */
 int pb_plan_segments(int rows, int cols, int64_t n, const int64_t* first, const int64_t* count, const int32_t* side,
-                     const double* radius, const double* cx, const double* cy, int segment_length, int use_snapshot,
+                     const double* radius, const unsigned char* single, const double* cx, const double* cy, int segment_length,
+                     int use_snapshot,
                      int32_t* seg_first, int32_t* seg_len, int64_t seg_capacity, int32_t* seg_off, int64_t pred_capacity,
                      int32_t* pred_stroke, int32_t* pred_need, int64_t* n_preds);
 
@@ -93,11 +95,12 @@ int pb_plan_segments(int rows, int cols, int64_t n, const int64_t* first, const 
  * cost model: stroke s runs on slot pool pool[s] (its GPU) in launch run[s] of that pool and costs cost[s] per
  * imprint; pool p has runs_per_pool[p] launches with slots[...] concurrent strokes each (flattened pool-major).
  * order[n] receives the global claim sequence: a topological order of the segment-level dependency graph (every
- * stroke after all strokes any of its segments waits for) that keeps the runs of a pool in sequence. */
+ * stroke after all strokes any of its segments waits for) that keeps the runs of a pool in sequence. *makespan (may be
+ * NULL) receives the model's completion time of the batch in units of cost. */
 int pb_plan_claim_order(int rows, int cols, int64_t n, const int64_t* first, const int64_t* count, const int32_t* side,
-                        const double* radius, const double* cx, const double* cy, int segment_length, int use_snapshot,
-                        const int32_t* pool, const int32_t* run, const double* cost, int n_pools, const int32_t* runs_per_pool,
-                        const int32_t* slots, int32_t* order);
+                        const double* radius, const unsigned char* single, const double* cx, const double* cy,
+                        int segment_length, int use_snapshot, const int32_t* pool, const int32_t* run, const double* cost,
+                        int n_pools, const int32_t* runs_per_pool, const int32_t* slots, int32_t* order, double* makespan);
 
 /* ---- PaintLayer ------------------------------------------------------------------------------ */
 int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out);

@@ -129,7 +129,7 @@ def plan_dependencies(rows, cols, box, allowed):
     return offsets, preds[:total.value]
 
 
-def plan_segments(rows, cols, first, count, side, radius, cx, cy, segment_length=32, use_snapshot=True):
+def plan_segments(rows, cols, first, count, side, radius, cx, cy, segment_length=64, use_snapshot=True, single=None):
     """Segment-level dataflow plan of a footprint stroke list (see pb_plan_segments).
 
     Returns (seg_first[n+1], seg_len[n], seg_off[segments+1], pred_stroke, pred_need)."""
@@ -139,6 +139,7 @@ def plan_segments(rows, cols, first, count, side, radius, cx, cy, segment_length
     radius = np.ascontiguousarray(radius, dtype=np.float64)
     cx = np.ascontiguousarray(cx, dtype=np.float64)
     cy = np.ascontiguousarray(cy, dtype=np.float64)
+    single = None if single is None else np.ascontiguousarray(single, dtype=np.uint8)
     n = len(first)
     seg_first = np.zeros(n + 1, dtype=np.int32)
     seg_len = np.zeros(max(n, 1), dtype=np.int32)
@@ -146,7 +147,8 @@ def plan_segments(rows, cols, first, count, side, radius, cx, cy, segment_length
 
     def call(seg_cap, seg_off, pred_cap, ps, pn):
         _chk(lib().pb_plan_segments(rows, cols, C.c_int64(n), first.ctypes.data_as(_VP), count.ctypes.data_as(_VP),
-                                    side.ctypes.data_as(_VP), radius.ctypes.data_as(_VP), cx.ctypes.data_as(_VP),
+                                    side.ctypes.data_as(_VP), radius.ctypes.data_as(_VP),
+                                    None if single is None else single.ctypes.data_as(_VP), cx.ctypes.data_as(_VP),
                                     cy.ctypes.data_as(_VP), int(segment_length), int(bool(use_snapshot)),
                                     seg_first.ctypes.data_as(_VP), seg_len.ctypes.data_as(_VP), C.c_int64(seg_cap),
                                     seg_off.ctypes.data_as(_VP), C.c_int64(pred_cap), ps.ctypes.data_as(_VP),
@@ -163,7 +165,7 @@ def plan_segments(rows, cols, first, count, side, radius, cx, cy, segment_length
 
 
 def plan_claim_order(rows, cols, first, count, side, radius, cx, cy, pool, run, cost, slots, segment_length=64,
-                     use_snapshot=True):
+                     use_snapshot=True, single=None, return_makespan=False):
     """Host list-scheduling of a footprint stroke list (see pb_plan_claim_order). `slots` = per pool, the list of
     concurrent strokes of each of its runs. Returns the global claim sequence (stroke indices)."""
     n = len(first)
@@ -173,11 +175,13 @@ def plan_claim_order(rows, cols, first, count, side, radius, cx, cy, pool, run, 
     rpp = arr([len(x) for x in slots], np.int32)
     flat = arr([v for x in slots for v in x], np.int32)
     order = np.zeros(max(n, 1), dtype=np.int32)
-    p = lambda a: a.ctypes.data_as(_VP)
-    _chk(lib().pb_plan_claim_order(rows, cols, C.c_int64(n), p(first), p(count), p(side), p(radius), p(cx), p(cy),
+    single = None if single is None else arr(single, np.uint8)
+    makespan = C.c_double(0.0)
+    p = lambda a: None if a is None else a.ctypes.data_as(_VP)
+    _chk(lib().pb_plan_claim_order(rows, cols, C.c_int64(n), p(first), p(count), p(side), p(radius), p(single), p(cx), p(cy),
                                    int(segment_length), int(bool(use_snapshot)), p(pool), p(run), p(cost), len(slots),
-                                   p(rpp), p(flat), p(order)))
-    return order[:n]
+                                   p(rpp), p(flat), p(order), C.byref(makespan)))
+    return (order[:n], makespan.value) if return_makespan else order[:n]
 
 
 # ---- device objects -----------------------------------------------------------------------------

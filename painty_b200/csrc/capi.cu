@@ -685,15 +685,16 @@ int pb_plan_dependencies(int rows, int cols, int64_t n, const int32_t* box, cons
 }
 
 int pb_plan_segments(int rows, int cols, int64_t n, const int64_t* first, const int64_t* count, const int32_t* side,
-                     const double* radius, const double* cx, const double* cy, int segment_length, int use_snapshot,
+                     const double* radius, const unsigned char* single, const double* cx, const double* cy, int segment_length,
+                     int use_snapshot,
                      int32_t* seg_first, int32_t* seg_len, int64_t seg_capacity, int32_t* seg_off, int64_t pred_capacity,
                      int32_t* pred_stroke, int32_t* pred_need, int64_t* n_preds) {
   PB_API_BEGIN
   PB_REQUIRE(rows > 0 && cols > 0 && n >= 0 && n < (int64_t(1) << 31), "pb_plan_segments: bad sizes");
   const SegmentPlan plan = plan_segments(
       rows, cols, static_cast<size_t>(n),
-      [&](size_t s) { return StrokeSpan{first[s], count[s], (side[s] - 1) / 2, radius[s], false}; }, cx, cy, segment_length,
-      use_snapshot != 0, [](size_t, const Region&, const Region&) {});
+      [&](size_t s) { return StrokeSpan{first[s], count[s], (side[s] - 1) / 2, radius[s], single != nullptr && single[s] != 0}; },
+      cx, cy, segment_length, use_snapshot != 0, [](size_t, const Region&, const Region&) {});
   for (int64_t s = 0; s < n; ++s) {
     seg_first[s] = plan.seg_first[static_cast<size_t>(s)];
     seg_len[s]   = plan.seg_len[static_cast<size_t>(s)];
@@ -711,15 +712,15 @@ int pb_plan_segments(int rows, int cols, int64_t n, const int64_t* first, const 
 }
 
 int pb_plan_claim_order(int rows, int cols, int64_t n, const int64_t* first, const int64_t* count, const int32_t* side,
-                        const double* radius, const double* cx, const double* cy, int segment_length, int use_snapshot,
-                        const int32_t* pool, const int32_t* run, const double* cost, int n_pools, const int32_t* runs_per_pool,
-                        const int32_t* slots, int32_t* order) {
+                        const double* radius, const unsigned char* single, const double* cx, const double* cy,
+                        int segment_length, int use_snapshot, const int32_t* pool, const int32_t* run, const double* cost,
+                        int n_pools, const int32_t* runs_per_pool, const int32_t* slots, int32_t* order, double* makespan) {
   PB_API_BEGIN
   PB_REQUIRE(rows > 0 && cols > 0 && n >= 0 && n < (int64_t(1) << 31) && n_pools >= 1, "pb_plan_claim_order: bad sizes");
   const SegmentPlan plan = plan_segments(
       rows, cols, static_cast<size_t>(n),
-      [&](size_t s) { return StrokeSpan{first[s], count[s], (side[s] - 1) / 2, radius[s], false}; }, cx, cy, segment_length,
-      use_snapshot != 0, [](size_t, const Region&, const Region&) {});
+      [&](size_t s) { return StrokeSpan{first[s], count[s], (side[s] - 1) / 2, radius[s], single != nullptr && single[s] != 0}; },
+      cx, cy, segment_length, use_snapshot != 0, [](size_t, const Region&, const Region&) {});
   std::vector<std::vector<int>> sl(static_cast<size_t>(n_pools));
   for (int p = 0, o = 0; p < n_pools; ++p)
     for (int j = 0; j < runs_per_pool[p]; ++j) sl[p].push_back(slots[o++]);
@@ -730,7 +731,7 @@ int pb_plan_claim_order(int rows, int cols, int64_t n, const int64_t* first, con
     spec[s]   = ClaimSpec{pool[s], run[s], cost[s]};
     counts[s] = count[s];
   }
-  const std::vector<int32_t> seq = plan_claim_order(plan, counts, spec, sl);
+  const std::vector<int32_t> seq = plan_claim_order(plan, counts, spec, sl, 64, makespan);
   for (int64_t s = 0; s < n; ++s) order[s] = seq[static_cast<size_t>(s)];
   PB_API_END
 }

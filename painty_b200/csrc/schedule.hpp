@@ -138,13 +138,25 @@ constexpr int kMaxSegmentsPerStroke = 4000;
 
 template <typename SpanFn, typename VisitFn>
 SegmentPlan plan_segments(int rows, int cols, size_t n, SpanFn&& span_of, const double* cx, const double* cy, int segment_length,
-                          bool use_snapshot, VisitFn&& visit_stroke) {
+                          bool use_snapshot, VisitFn&& visit_stroke, int tile = 64) {
   SegmentPlan plan;
   plan.seg_first.assign(n + 1, 0);
   plan.seg_len.assign(n, 1);
   plan.seg_off.assign(1, 0);
-  std::vector<int32_t> owner, raw;
-  DataflowPlanner planner(rows, cols);
+  // Same tile tables and rules as DataflowPlanner (last box per tile, rings since then), specialised for segments:
+  // entries are global segment ids, consecutive ring entries of one stroke collapse into the latest (a dependency
+  // on a later segment implies the earlier ones), and the per-segment lists are deduplicated per STROKE with stamps.
+  const int tx = (cols + tile - 1) / tile, ty = (rows + tile - 1) / tile;
+  std::vector<int32_t> last(static_cast<size_t>(tx) * ty, -1), owner;
+  std::vector<std::vector<int32_t>> ring(use_snapshot ? last.size() : 0);
+  std::vector<int32_t> stamp(n, -1), slot(n, 0);
+  auto tiles = [&](const Region& r, auto&& fn) {
+    if (r.x1 < r.x0 || r.y1 < r.y0) return;
+    const int tx0 = r.x0 / tile, tx1 = std::min(r.x1 / tile, tx - 1);
+    const int ty0 = r.y0 / tile, ty1 = std::min(r.y1 / tile, ty - 1);
+    for (int y = ty0; y <= ty1; ++y)
+      for (int x = tx0; x <= tx1; ++x) fn(static_cast<size_t>(y) * tx + x);
+  };
   for (size_t s = 0; s < n; ++s) {
     const StrokeSpan sp = span_of(s);
     Region box, allowed;
@@ -158,37 +170,51 @@ SegmentPlan plan_segments(int rows, int cols, size_t n, SpanFn&& span_of, const 
     const int nseg       = static_cast<int>((whole + len - 1) / len);
     plan.seg_len[s]      = static_cast<int32_t>(len);
     plan.seg_first[s + 1] = plan.seg_first[s] + nseg;
+    const int32_t self   = static_cast<int32_t>(s);
     for (int k = 0; k < nseg; ++k) {
       const int32_t gseg = plan.seg_first[s] + k;
       Region sbox = box, sall = allowed;
       if (nseg > 1)
         imprint_regions(sp.first + k * len, std::min<int64_t>(len, sp.count - k * len), sp.half_side, sp.radius, cx, cy, rows,
                         cols, sbox, sall);
-      raw.clear();
-      int32_t rb = 0, re = 0;
-      if (use_snapshot) {
-        planner.add_footprint(gseg, sbox, sall, raw, rb, re);
-      } else {
-        planner.add(gseg, sbox, raw, rb, re);
-      }
-      const size_t begin = plan.pred_stroke.size();
-      for (int32_t p : raw) {
-        const int32_t g = owner[p];
-        if (g == static_cast<int32_t>(s)) continue;
-        const int32_t need = p - plan.seg_first[g] + 1;
-        bool merged        = false;
-        for (size_t q = begin; q < plan.pred_stroke.size() && !merged; ++q) {
-          if (plan.pred_stroke[q] == g) {
-            plan.pred_need[q] = std::max(plan.pred_need[q], need);
-            merged            = true;
-          }
-        }
-        if (!merged) {
+      auto note = [&](int32_t l) {  // segment l of an earlier stroke must be complete
+        if (l < 0) return;
+        const int32_t g = owner[l];
+        if (g == self) return;
+        const int32_t need = l - plan.seg_first[g] + 1;
+        if (stamp[g] != gseg) {
+          stamp[g] = gseg;
+          slot[g]  = static_cast<int32_t>(plan.pred_stroke.size());
           plan.pred_stroke.push_back(g);
           plan.pred_need.push_back(need);
+        } else if (plan.pred_need[slot[g]] < need) {
+          plan.pred_need[slot[g]] = need;
         }
+      };
+      if (use_snapshot) {
+        tiles(sall, [&](size_t t) { note(last[t]); });  // earlier boxes under our ring or box
+        tiles(sbox, [&](size_t t) {                     // earlier rings over our box
+          for (int32_t l : ring[t]) note(l);
+        });
+        tiles(sall, [&](size_t t) {
+          std::vector<int32_t>& r = ring[t];
+          if (!r.empty() && owner[r.back()] == self) {
+            r.back() = gseg;
+          } else {
+            r.push_back(gseg);
+          }
+        });
+        tiles(sbox, [&](size_t t) {
+          last[t] = gseg;
+          ring[t].clear();
+        });
+      } else {
+        tiles(sbox, [&](size_t t) {
+          note(last[t]);
+          last[t] = gseg;
+        });
       }
-      owner.push_back(static_cast<int32_t>(s));
+      owner.push_back(self);
       plan.seg_off.push_back(static_cast<int32_t>(plan.pred_stroke.size()));
     }
   }
@@ -215,7 +241,7 @@ struct ClaimSpec {
 
 inline std::vector<int32_t> plan_claim_order(const SegmentPlan& plan, const std::vector<int64_t>& count,
                                              const std::vector<ClaimSpec>& spec, const std::vector<std::vector<int>>& slots,
-                                             int window = 64) {
+                                             int window = 64, double* makespan = nullptr) {
   const int32_t n = static_cast<int32_t>(count.size());
   std::vector<int32_t> order;
   order.reserve(static_cast<size_t>(n));
@@ -386,6 +412,7 @@ inline std::vector<int32_t> plan_claim_order(const SegmentPlan& plan, const std:
     wp.clear();
     ws.clear();
   }
+  if (makespan) *makespan = now;  // the model's completion time of the batch, in units of ClaimSpec::cost
   // Anything the model left unclaimed (cannot happen for a consistent plan) keeps its submission order.
   if (order.size() != static_cast<size_t>(n)) {
     order.clear();
