@@ -508,7 +508,12 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
       L.queue         = reinterpret_cast<int*>(d_flags.p + mine.size());
       if (run_begin > 0) PB_CUDA(cudaMemsetAsync(L.queue, 0, sizeof(int), ctx->stream));
     }
-    for (int p = 0; p < kLayerPlanes; ++p) L.pick_dense[p] = b->pick.base ? b->pick.plane(p) : nullptr;
+    for (int p = 0; p < kLayerPlanes; ++p) {
+      L.own_canvas[p]   = L.canvas[L.my_band][p];
+      L.own_snapshot[p] = L.snapshot[L.my_band][p];
+      L.pick_dense[p]   = b->pick.base ? b->pick.plane(p) : nullptr;
+    }
+    L.own_dirty = L.dirty[L.my_band];
     L.epoch           = epoch;
     L.flag_offset     = static_cast<int>(run_begin);
     L.dirty_pitch     = b->dirty_pitch;

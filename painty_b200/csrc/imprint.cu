@@ -37,6 +37,7 @@
 #include <cstdlib>
 #include <map>
 #include <tuple>
+#include <type_traits>
 
 #include "imprint.cuh"
 
@@ -129,11 +130,30 @@ struct Band {
     pitch   = L.cols;
     dpitch  = L.dirty_pitch;
   }
+  // the executor's own band, from dedicated launch fields (compile-time offsets into the constant bank)
+  __device__ __forceinline__ explicit Band(const ImprintLaunch& L) {
+#pragma unroll
+    for (int k = 0; k < kLayerPlanes; ++k) {
+      can[k] = static_cast<T*>(L.own_canvas[k]);
+      src[k] = static_cast<T*>(L.own_snapshot[k]);
+    }
+    dirty   = L.own_dirty;
+    touched = nullptr;
+    pitch   = L.cols;
+    dpitch  = L.dirty_pitch;
+  }
 };
-template <typename T, bool MULTI>
+// VIEWS = the stroke may touch rows of other bands (multi GPU, straddling strokes): pixels are addressed through the
+// per-band views. Otherwise everything lies in the executor's own band and folds into constant-bank operands.
+template <typename T, bool VIEWS>
 __device__ __forceinline__ Band<T> band_view(const ImprintLaunch& L, const Band<T>* views, int band) {
-  if (MULTI) return views[band];
-  return Band<T>(L, 0);
+  if (VIEWS) return views[band];
+  return Band<T>(L);
+}
+// Owner band of a canvas row. Almost every row a straddling stroke touches still lies in the executor's own band.
+__device__ __forceinline__ int band_of(const ImprintLaunch& L, int row) {
+  const int b0 = L.my_band * L.rows_per_band;
+  return (row >= b0 && row < b0 + L.rows_per_band) ? L.my_band : row / L.rows_per_band;
 }
 
 // One (canvas pixel, pickup cell) interaction = pickupPaint (:349-384) then depositPaint (:393-431).
@@ -245,7 +265,7 @@ __device__ __forceinline__ Hits find_hits(const ImprintLaunch& L, const Band<T>*
       if (border && ((fy >= 0.0 ? 2 : 0) + (fx >= 0.0 ? 1 : 0)) != ph) continue;
       int band = 0, lrow = py - row_lo, pitch = L.cols, dpitch = L.dirty_pitch;
       if (MULTI) {
-        band   = py / L.rows_per_band;  // the row's owner GPU
+        band   = band_of(L, py);  // the row's owner GPU
         lrow   = py - band * L.rows_per_band;
         pitch  = views[band].pitch;
         dpitch = views[band].dpitch;
@@ -277,7 +297,7 @@ template <typename T, bool MULTI>
 __device__ __forceinline__ void ring_word(const ImprintLaunch& L, const Band<T>* views, const RingGeom& g, int row, int wi,
                                           unsigned word) {
   const bool mid = row > g.tly && row < g.bry;
-  const int band = MULTI ? row / L.rows_per_band : 0;
+  const int band = MULTI ? band_of(L, row) : 0;
   const int lrow = MULTI ? row - band * L.rows_per_band : row - L.store_first;
   const Band<T> C = band_view<T, MULTI>(L, views, band);
   unsigned char* drow = C.dirty + static_cast<int64_t>(lrow) * C.dpitch;
@@ -329,9 +349,9 @@ __device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const Band<T>*
         rows[u] = row;
         wis[u]  = wi;
         if (!(row > g.tly && row < g.bry && wi >= iw0 && wi <= iw1)) {
-          const int band = MULTI ? row / L.rows_per_band : 0;
+          const int band = MULTI ? band_of(L, row) : 0;
           const int lrow = MULTI ? row - band * L.rows_per_band : row - L.store_first;
-          const unsigned char* dbase = MULTI ? views[band].dirty : L.dirty[0];
+          const unsigned char* dbase = MULTI ? views[band].dirty : L.own_dirty;
           const int dpitch           = MULTI ? views[band].dpitch : L.dirty_pitch;
           word[u] = __ldcg(reinterpret_cast<const unsigned*>(dbase + static_cast<int64_t>(lrow) * dpitch) + wi);
         }
@@ -590,7 +610,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
       C.paintS[k] = static_cast<T>(st.paintS[k]);
     }
     remote       = MULTI && (st.flags & 4) != 0;
-    if (MULTI) stage_in<T>(L, st, s_view, group, sgt, gstride, tid), sync_all();
+    if (MULTI && (st.flags & 12)) stage_in<T>(L, st, s_view, group, sgt, gstride, tid), sync_all();
     const int nA = st.n_active;
     const int wr = (st.side - 1) / 2;  // == hr (square footprint), FootprintBrush.hxx:75-78
     const T* fhs = static_cast<const T*>(st.fh);
@@ -635,82 +655,98 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
       }
     }
 
-    DevImprint nxt = st.n_imprints > 0 ? L.imprints[st.first_imprint] : DevImprint{0, 0, 1, 0};
-    int seg_k = 0, seg_next = st.seg_len;  // next segment boundary (imprint index)
-    for (int ii = 0; ii < st.n_imprints; ++ii) {
-      if (ii == seg_next) {
-        ++seg_k;
-        seg_next += st.seg_len;
-        seg_publish(seg_k);
-        seg_wait(seg_k);
-      }
-      const DevImprint im = nxt;
-      if (ii + 1 < st.n_imprints) nxt = L.imprints[st.first_imprint + ii + 1];  // prefetch (hidden behind this imprint)
+    // The imprint chain, instantiated twice in the multi-GPU kernel: strokes that stay inside the executor's band
+    // (the large majority) address it directly like the single-GPU kernel; only straddling strokes pay for the
+    // per-band views.
+    auto imprint_chain = [&](auto views_tag) {
+      constexpr bool VIEWS = decltype(views_tag)::value;
+      DevImprint nxt = st.n_imprints > 0 ? L.imprints[st.first_imprint] : DevImprint{0, 0, 1, 0};
+      int seg_k = 0, seg_next = st.seg_len;  // next segment boundary (imprint index)
+      for (int ii = 0; ii < st.n_imprints; ++ii) {
+        if (ii == seg_next) {
+          ++seg_k;
+          seg_next += st.seg_len;
+          seg_publish(seg_k);
+          seg_wait(seg_k);
+        }
+        const DevImprint im = nxt;
+        if (ii + 1 < st.n_imprints) nxt = L.imprints[st.first_imprint + ii + 1];  // prefetch (hidden behind this imprint)
 
-      if (L.use_snapshot) {
-        // updateSnapshot(canvas, centre) (:278-319): refresh the ring allowed-box \ open interior
-        RingGeom g;
-        g.tlx = static_cast<int>(im.cx - wr), g.tly = static_cast<int>(im.cy - wr);
-        g.brx = static_cast<int>(im.cx + wr), g.bry = static_cast<int>(im.cy + wr);
-        g.ax0 = max(static_cast<int>(im.cx - wr - st.radius), 0);
-        g.ay0 = max(max(static_cast<int>(im.cy - wr - st.radius), 0), MULTI ? 0 : row_lo);
-        g.ax1 = min(static_cast<int>(im.cx + wr + st.radius), L.cols - 1);
-        g.ay1 = min(min(static_cast<int>(im.cy + wr + st.radius), L.rows - 1), MULTI ? L.rows - 1 : row_hi);
-        ring_scan<T, MULTI>(L, views, g, sgt, gstride);
-      }
-      // left/top overhang: canvas pixels of column/row 0 can be hit twice (B#11) -> ordered phases
-      const bool border = (im.cx - wr < 0.0) || (im.cy - wr < 0.0);
-      const float fc = static_cast<float>(im.c), fs = static_cast<float>(im.s);
-      sync_all();
+        if (L.use_snapshot) {
+          // updateSnapshot(canvas, centre) (:278-319): refresh the ring allowed-box \ open interior
+          RingGeom g;
+          g.tlx = static_cast<int>(im.cx - wr), g.tly = static_cast<int>(im.cy - wr);
+          g.brx = static_cast<int>(im.cx + wr), g.bry = static_cast<int>(im.cy + wr);
+          g.ax0 = max(static_cast<int>(im.cx - wr - st.radius), 0);
+          g.ay0 = max(max(static_cast<int>(im.cy - wr - st.radius), 0), VIEWS ? 0 : row_lo);
+          g.ax1 = min(static_cast<int>(im.cx + wr + st.radius), L.cols - 1);
+          g.ay1 = min(min(static_cast<int>(im.cy + wr + st.radius), L.rows - 1), VIEWS ? L.rows - 1 : row_hi);
+          ring_scan<T, VIEWS>(L, views, g, sgt, gstride);
+        }
+        // left/top overhang: canvas pixels of column/row 0 can be hit twice (B#11) -> ordered phases
+        const bool border = (im.cx - wr < 0.0) || (im.cy - wr < 0.0);
+        const float fc = static_cast<float>(im.c), fs = static_cast<float>(im.s);
+        sync_all();
 
-      const int n_phase = border ? 4 : 1;
-      for (int ph = 0; ph < n_phase; ++ph) {
-        // CPP cells per pass: all loads of up to 2*CPP interactions are in flight before any is computed
-        constexpr int CPP = MAXB <= 256 ? 2 : 1;
-        for (int k = 0; k < my_cells; k += CPP) {
-          int mx[CPP], my[CPP], slot[CPP];
-          T fh[CPP];
-          bool have[CPP];
-#pragma unroll
-          for (int q = 0; q < CPP; ++q) {
-            have[q] = k + q < my_cells;
-            slot[q] = tid + (k + q) * bd;
-            if (k + q < kRegCells) {
-              mx[q] = cmx[(k + q) & 1], my[q] = cmy[(k + q) & 1], fh[q] = cfh[(k + q) & 1];
-            } else if (have[q]) {
-              const int cell    = cell0 + (k + q) * bd;
-              const uint32_t xy = st.xy[cell];
-              mx[q] = static_cast<int>(xy & 0xffffu), my[q] = static_cast<int>(xy >> 16), fh[q] = fhs[cell];
-            } else {
-              mx[q] = my[q] = 0, fh[q] = static_cast<T>(0);
+        const int n_phase = border ? 4 : 1;
+        for (int ph = 0; ph < n_phase; ++ph) {
+          // CPP cells per pass: all loads of up to 2*CPP interactions are in flight before any is computed
+          constexpr int CPP = MAXB <= 256 ? 2 : 1;
+          for (int k = 0; k < my_cells; k += CPP) {
+            int mx[CPP], my[CPP], slot[CPP];
+            T fh[CPP];
+            bool have[CPP];
+  #pragma unroll
+            for (int q = 0; q < CPP; ++q) {
+              have[q] = k + q < my_cells;
+              slot[q] = tid + (k + q) * bd;
+              if (k + q < kRegCells) {
+                mx[q] = cmx[(k + q) & 1], my[q] = cmy[(k + q) & 1], fh[q] = cfh[(k + q) & 1];
+              } else if (have[q]) {
+                const int cell    = cell0 + (k + q) * bd;
+                const uint32_t xy = st.xy[cell];
+                mx[q] = static_cast<int>(xy & 0xffffu), my[q] = static_cast<int>(xy >> 16), fh[q] = fhs[cell];
+              } else {
+                mx[q] = my[q] = 0, fh[q] = static_cast<T>(0);
+              }
             }
-          }
-          Hits h[CPP];
-          OpData<T> d[CPP][2];
-#pragma unroll
-          for (int q = 0; q < CPP; ++q) {
-            h[q].n = 0;
-            if (have[q]) h[q] = find_hits<T, MULTI>(L, views, im, fc, fs, wr, mx[q], my[q], border, ph, row_lo, row_hi);
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              if (j < h[q].n) op_load(band_view<T, MULTI>(L, views, h[q].band[j]), h[q].ci[j], d[q][j]);
-          }
-#pragma unroll
-          for (int q = 0; q < CPP; ++q) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              if (j < h[q].n) {
-                const Band<T> B = band_view<T, MULTI>(L, views, h[q].band[j]);
-                op_finish(C, B, h[q].ci[j], fh[q], d[q][j], pick, ps, slot[q]);
-                if (B.dirty) __stcg(B.dirty + h[q].dof[j], static_cast<unsigned char>(1));
-                if (MULTI && B.touched) __stcg(B.touched + h[q].dof[j], static_cast<unsigned char>(1));
-                ++my_active;
+            Hits h[CPP];
+            OpData<T> d[CPP][2];
+  #pragma unroll
+            for (int q = 0; q < CPP; ++q) {
+              h[q].n = 0;
+              if (have[q]) h[q] = find_hits<T, VIEWS>(L, views, im, fc, fs, wr, mx[q], my[q], border, ph, row_lo, row_hi);
+  #pragma unroll
+              for (int j = 0; j < 2; ++j)
+                if (j < h[q].n) op_load(band_view<T, VIEWS>(L, views, h[q].band[j]), h[q].ci[j], d[q][j]);
+            }
+  #pragma unroll
+            for (int q = 0; q < CPP; ++q) {
+  #pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                if (j < h[q].n) {
+                  const Band<T> B = band_view<T, VIEWS>(L, views, h[q].band[j]);
+                  op_finish(C, B, h[q].ci[j], fh[q], d[q][j], pick, ps, slot[q]);
+                  if (B.dirty) __stcg(B.dirty + h[q].dof[j], static_cast<unsigned char>(1));
+                  if (VIEWS && B.touched) __stcg(B.touched + h[q].dof[j], static_cast<unsigned char>(1));
+                  ++my_active;
+                }
               }
             }
           }
+          sync_all();
         }
-        sync_all();
       }
+
+    };
+    if constexpr (MULTI) {
+      if (st.flags & 12) {
+        imprint_chain(std::true_type{});
+      } else {
+        imprint_chain(std::false_type{});
+      }
+    } else {
+      imprint_chain(std::false_type{});
     }
 
     if (st.flags & 2) {

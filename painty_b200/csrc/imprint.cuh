@@ -53,6 +53,10 @@ struct ImprintLaunch {
   void* canvas[kMaxBands][kLayerPlanes];
   void* snapshot[kMaxBands][kLayerPlanes];  // == canvas planes when the snapshot buffer is disabled
   unsigned char* dirty[kMaxBands];          // 1 byte per pixel: snapshot(p) may differ from canvas(p)
+  // the executor's own band once more (== index my_band above): strokes that stay inside it use these fields
+  void* own_canvas[kLayerPlanes];
+  void* own_snapshot[kLayerPlanes];
+  unsigned char* own_dirty;
   int n_bands, rows_per_band, my_band;
   int dirty_pitch;
   int use_snapshot;
