@@ -2,6 +2,7 @@
 // brush state, host-side stroke planning, kernel launches. No CPU fallback anywhere: every entry point
 // that computes pixels needs a CUDA device and fails loudly otherwise.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -35,6 +36,13 @@ void set_error(const std::string& msg) { g_error = msg; }
   catch (...) {                              \
     pb::set_error("unknown C++ exception");  \
     return 1;                                \
+  }
+
+// entry points that only touch host state: reject a null handle with an error code instead of crashing
+#define PB_CHECK_HANDLE(h, name)                      \
+  if ((h) == nullptr) {                               \
+    pb::set_error(name ": null handle");              \
+    return 1;                                         \
   }
 
 using namespace pb;
@@ -105,7 +113,7 @@ struct pb_fbrush {
   unsigned char* dirty = nullptr;
   int dirty_pitch      = 0;
   uint64_t snap_canvas_id = 0, snap_canvas_version = 0;  // canvas state the dirty map is valid for
-  // multi-GPU: completion flags other GPUs poll (kDistFlagCapacity ints + 1024 queue counters), batch epoch
+  // multi-GPU: 64-bit progress words other GPUs poll (kDistFlagCapacity words + 1024 queue counters), batch epoch
   long long* dist_flags = nullptr;
   int dist_epoch        = 0;
   int dist_queue_slot   = 0;
@@ -608,6 +616,7 @@ int pb_context_destroy(pb_context* ctx) {
 }
 int pb_context_synchronize(pb_context* ctx) {
   PB_API_BEGIN
+  PB_REQUIRE(ctx != nullptr, "pb_context_synchronize: null handle");
   DeviceGuard g(ctx);
   PB_CUDA(cudaStreamSynchronize(ctx->stream));
   PB_API_END
@@ -744,6 +753,7 @@ int pb_plan_claim_order(int rows, int cols, int64_t n, const int64_t* first, con
 // ---- PaintLayer --------------------------------------------------------------------------------------
 int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out) {
   PB_API_BEGIN
+  PB_REQUIRE(ctx != nullptr, "pb_layer_create: null handle");
   DeviceGuard g(ctx);
   auto l = std::make_unique<pb_layer>();
   planes_alloc(ctx, l->pl, rows, cols, kLayerPlanes);
@@ -768,6 +778,7 @@ int pb_layer_rows(const pb_layer* l) { return l->pl.rows; }
 int pb_layer_cols(const pb_layer* l) { return l->pl.cols; }
 int pb_layer_clear(pb_layer* l) {
   PB_API_BEGIN
+  PB_REQUIRE(l != nullptr, "pb_layer_clear: null handle");
   DeviceGuard g(l->pl.ctx);
   if (l->canvas) l->canvas->version++;
   for (int p = 0; p < kLayerPlanes; ++p) fill_plane(l->pl.ctx, l->pl.plane(p), l->pl.n(), 0.0);
@@ -775,6 +786,7 @@ int pb_layer_clear(pb_layer* l) {
 }
 int pb_layer_upload(pb_layer* l, const double* K, const double* S, const double* V) {
   PB_API_BEGIN
+  PB_REQUIRE(l != nullptr, "pb_layer_upload: null handle");
   DeviceGuard g(l->pl.ctx);
   if (l->canvas) l->canvas->version++;
   if (K) upload_aos(l->pl.ctx, l->pl, PK, 3, K);
@@ -784,6 +796,7 @@ int pb_layer_upload(pb_layer* l, const double* K, const double* S, const double*
 }
 int pb_layer_download(pb_layer* l, double* K, double* S, double* V) {
   PB_API_BEGIN
+  PB_REQUIRE(l != nullptr, "pb_layer_download: null handle");
   DeviceGuard g(l->pl.ctx);
   if (K) download_aos(l->pl.ctx, l->pl, PK, 3, K);
   if (S) download_aos(l->pl.ctx, l->pl, PS, 3, S);
@@ -792,6 +805,8 @@ int pb_layer_download(pb_layer* l, double* K, double* S, double* V) {
 }
 int pb_layer_copy(const pb_layer* src, pb_layer* dst) {
   PB_API_BEGIN
+  PB_REQUIRE(src != nullptr, "pb_layer_copy: null handle");
+  PB_REQUIRE(dst != nullptr, "pb_layer_copy: null handle");
   DeviceGuard g(src->pl.ctx);
   if (dst->canvas) dst->canvas->version++;
   if (dst->pl.rows != src->pl.rows || dst->pl.cols != src->pl.cols) {  // PaintLayer.hxx:104-107
@@ -805,6 +820,7 @@ int pb_layer_copy(const pb_layer* src, pb_layer* dst) {
 }
 int pb_layer_compose(pb_layer* l, const double* R0, double* out) {
   PB_API_BEGIN
+  PB_REQUIRE(l != nullptr, "pb_layer_compose: null handle");
   pb_context* ctx = l->pl.ctx;
   DeviceGuard g(ctx);
   pb_planes r;
@@ -826,6 +842,7 @@ int pb_layer_compose_onto(pb_layer* l, double* R0) { return pb_layer_compose(l, 
 // ---- Canvas ------------------------------------------------------------------------------------------
 int pb_canvas_create_band(pb_context* ctx, int rows, int cols, int row_begin, int row_end, int halo, pb_canvas** out) {
   PB_API_BEGIN
+  PB_REQUIRE(ctx != nullptr, "pb_canvas_create_band: null handle");
   DeviceGuard g(ctx);
   PB_REQUIRE(rows >= 0 && cols >= 0, "canvas size must be non-negative");
   PB_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= rows && halo >= 0, "invalid band");
@@ -836,8 +853,8 @@ int pb_canvas_create_band(pb_context* ctx, int rows, int cols, int row_begin, in
   c->row_begin   = row_begin;
   c->row_end     = row_end;
   c->halo        = halo;
-  static uint64_t next_id = 1;
-  c->id          = next_id++;
+  static std::atomic<uint64_t> next_id{1};
+  c->id          = next_id.fetch_add(1);
   c->store_first = std::max(0, row_begin - halo);
   const int last = std::min(rows, row_end + halo);
   planes_alloc(ctx, c->pl, last - c->store_first, cols, kCanvasPlanes);
@@ -861,12 +878,14 @@ int pb_canvas_destroy(pb_canvas* c) {
 int pb_canvas_rows(const pb_canvas* c) { return c->rows; }
 int pb_canvas_cols(const pb_canvas* c) { return c->cols; }
 int pb_canvas_stored_rows(const pb_canvas* c, int* first_row, int* n_rows) {
+  PB_CHECK_HANDLE(c, "pb_canvas_stored_rows");
   if (first_row) *first_row = c->store_first;
   if (n_rows) *n_rows = c->pl.rows;
   return 0;
 }
 int pb_canvas_clear(pb_canvas* c) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_clear: null handle");
   DeviceGuard g(c->pl.ctx);
   c->version++;
   canvas_clear(c);
@@ -874,6 +893,7 @@ int pb_canvas_clear(pb_canvas* c) {
 }
 int pb_canvas_set_background(pb_canvas* c, const double* R0) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_set_background: null handle");
   DeviceGuard g(c->pl.ctx);
   c->version++;
   canvas_clear(c);
@@ -882,6 +902,7 @@ int pb_canvas_set_background(pb_canvas* c, const double* R0) {
 }
 int pb_canvas_dry(pb_canvas* c) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_dry: null handle");
   DeviceGuard g(c->pl.ctx);
   c->version++;
   void* planes[kCanvasPlanes];
@@ -891,6 +912,7 @@ int pb_canvas_dry(pb_canvas* c) {
 }
 int pb_canvas_upload_layer(pb_canvas* c, const double* K, const double* S, const double* V) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_upload_layer: null handle");
   DeviceGuard g(c->pl.ctx);
   c->version++;
   if (K) upload_aos(c->pl.ctx, c->pl, PK, 3, K);
@@ -900,6 +922,7 @@ int pb_canvas_upload_layer(pb_canvas* c, const double* K, const double* S, const
 }
 int pb_canvas_download(pb_canvas* c, double* K, double* S, double* V, double* R0, double* h) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_download: null handle");
   DeviceGuard g(c->pl.ctx);
   if (K) download_aos(c->pl.ctx, c->pl, PK, 3, K);
   if (S) download_aos(c->pl.ctx, c->pl, PS, 3, S);
@@ -910,6 +933,7 @@ int pb_canvas_download(pb_canvas* c, double* K, double* S, double* V, double* R0
 }
 int pb_canvas_compose_device(pb_canvas* c, void* d_out, int64_t plane_stride) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_compose_device: null handle");
   pb_context* ctx = c->pl.ctx;
   DeviceGuard g(ctx);
   void* o[3];
@@ -919,6 +943,7 @@ int pb_canvas_compose_device(pb_canvas* c, void* d_out, int64_t plane_stride) {
 }
 int pb_canvas_compose_band_device(pb_canvas* c, void* d_out, int64_t plane_stride) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_compose_band_device: null handle");
   pb_context* ctx = c->pl.ctx;
   DeviceGuard g(ctx);
   void* o[3];
@@ -930,6 +955,7 @@ int pb_canvas_compose_band_device(pb_canvas* c, void* d_out, int64_t plane_strid
 }
 int pb_canvas_compose(pb_canvas* c, double* out) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_compose: null handle");
   pb_context* ctx = c->pl.ctx;
   DeviceGuard g(ctx);
   pb_planes r;
@@ -960,6 +986,7 @@ void compose_display(pb_canvas* c, int mode, bool srgb, size_t bytes_per_px, voi
 }  // namespace
 int pb_canvas_render(pb_canvas* c, double* out) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_render: null handle");
   pb_context* ctx = c->pl.ctx;
   DeviceGuard g(ctx);
   PB_REQUIRE(c->store_first == 0 && c->pl.rows == c->rows, "pb_canvas_render needs a full canvas (not a band)");
@@ -978,17 +1005,20 @@ int pb_canvas_render(pb_canvas* c, double* out) {
 }
 int pb_canvas_compose_qrgb32(pb_canvas* c, uint32_t* out) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_compose_qrgb32: null handle");
   compose_display(c, 0, true, 4, out);
   PB_API_END
 }
 int pb_canvas_compose_bgr(pb_canvas* c, int bits, int srgb, void* out) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_compose_bgr: null handle");
   PB_REQUIRE(bits == 8 || bits == 16, "pb_canvas_compose_bgr: bits must be 8 or 16");
   compose_display(c, bits == 8 ? 1 : 2, srgb != 0, bits == 8 ? 3 : 6, out);
   PB_API_END
 }
 int pb_canvas_paint_layer(pb_canvas* c, pb_layer** out) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_paint_layer: null handle");
   auto l        = std::make_unique<pb_layer>();
   l->pl         = c->pl;
   l->pl.nplanes = kLayerPlanes;
@@ -999,12 +1029,14 @@ int pb_canvas_paint_layer(pb_canvas* c, pb_layer** out) {
 }
 int pb_canvas_upload_substrate(pb_canvas* c, const double* R0, const double* h) {
   PB_API_BEGIN
+  PB_REQUIRE(c != nullptr, "pb_canvas_upload_substrate: null handle");
   DeviceGuard g(c->pl.ctx);
   if (R0) upload_aos(c->pl.ctx, c->pl, PR, 3, R0);
   if (h) upload_aos(c->pl.ctx, c->pl, PH, 1, h);
   PB_API_END
 }
 int pb_canvas_device_planes(pb_canvas* c, void* planes[11], int64_t* elems_per_plane) {
+  PB_CHECK_HANDLE(c, "pb_canvas_device_planes");
   for (int p = 0; p < kCanvasPlanes; ++p) planes[p] = c->pl.plane(p);
   if (elems_per_plane) *elems_per_plane = c->pl.n();
   return 0;
@@ -1014,6 +1046,7 @@ int pb_canvas_device_planes(pb_canvas* c, void* planes[11], int64_t* elems_per_p
 int pb_km_compose_planes(pb_context* ctx, int64_t n, const void* const K[3], const void* const S[3], const void* V,
                          const void* const R0[3], void* const R[3]) {
   PB_API_BEGIN
+  PB_REQUIRE(ctx != nullptr, "pb_km_compose_planes: null handle");
   DeviceGuard g(ctx);
   ComposeArgs a;
   for (int k = 0; k < 3; ++k) {
@@ -1029,6 +1062,7 @@ int pb_km_compose_planes(pb_context* ctx, int64_t n, const void* const K[3], con
 int pb_km_compose_stacked_planes(pb_context* ctx, int64_t n, int n_layers, const void* const* K, const void* const* S,
                                  const void* const* V, const void* const R0[3], void* const R[3]) {
   PB_API_BEGIN
+  PB_REQUIRE(ctx != nullptr, "pb_km_compose_stacked_planes: null handle");
   DeviceGuard g(ctx);
   PB_REQUIRE(n_layers >= 1, "compose_stacked: need at least one layer");
   // more than kMaxStack layers: chain passes of <= kMaxStack, intermediate R stays on the device in R
@@ -1057,6 +1091,7 @@ int pb_km_compose_stacked_planes(pb_context* ctx, int64_t n, int n_layers, const
 // ---- FootprintBrush --------------------------------------------------------------------------------------
 int pb_fbrush_create(pb_context* ctx, pb_fbrush** out) {
   PB_API_BEGIN
+  PB_REQUIRE(ctx != nullptr, "pb_fbrush_create: null handle");
   DeviceGuard g(ctx);
   auto b = std::make_unique<pb_fbrush>();
   b->ctx = ctx;
@@ -1085,6 +1120,7 @@ int pb_fbrush_destroy(pb_fbrush* b) {
 }
 int pb_fbrush_register_footprint(pb_fbrush* b, double radius, int side, const double* footprint) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_register_footprint: null handle");
   DeviceGuard g(b->ctx);
   PB_REQUIRE(footprint != nullptr, "footprint is null");
   register_footprint(b, radius, side, footprint);
@@ -1092,6 +1128,7 @@ int pb_fbrush_register_footprint(pb_fbrush* b, double radius, int side, const do
 }
 int pb_fbrush_set_radius(pb_fbrush* b, double radius, int side, const double* footprint, int* acted) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_set_radius: null handle");
   DeviceGuard g(b->ctx);
   const bool act = !(std::fabs(b->radius - radius) < 0.5);  // fuzzyCompare, FootprintBrush.hxx:47-48
   if (acted) *acted = act ? 1 : 0;
@@ -1100,12 +1137,14 @@ int pb_fbrush_set_radius(pb_fbrush* b, double radius, int side, const double* fo
 }
 int pb_fbrush_clean(pb_fbrush* b) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_clean: null handle");
   DeviceGuard g(b->ctx);
   if (b->pick.base)
     for (int p = 0; p < kLayerPlanes; ++p) fill_plane(b->ctx, b->pick.plane(p), b->pick.n(), 0.0);
   PB_API_END
 }
 int pb_fbrush_dip(pb_fbrush* b, const double K[3], const double S[3]) {
+  PB_CHECK_HANDLE(b, "pb_fbrush_dip");
   const int rc = pb_fbrush_clean(b);
   if (rc) return rc;
   for (int i = 0; i < 3; ++i) {
@@ -1115,16 +1154,19 @@ int pb_fbrush_dip(pb_fbrush* b, const double K[3], const double S[3]) {
   return 0;
 }
 int pb_fbrush_set_pickup_rate(pb_fbrush* b, double rate) {
+  PB_CHECK_HANDLE(b, "pb_fbrush_set_pickup_rate");
   b->pickup_rate = rate;
   return 0;
 }
 int pb_fbrush_set_deposition_rate(pb_fbrush* b, double rate) {
+  PB_CHECK_HANDLE(b, "pb_fbrush_set_deposition_rate");
   b->deposition_rate = rate;
   return 0;
 }
 double pb_fbrush_get_pickup_rate(const pb_fbrush* b) { return b->pickup_rate; }
 double pb_fbrush_get_deposition_rate(const pb_fbrush* b) { return b->deposition_rate; }
 int pb_fbrush_set_use_snapshot(pb_fbrush* b, int use) {
+  PB_CHECK_HANDLE(b, "pb_fbrush_set_use_snapshot");
   b->use_snapshot = use != 0;
   return 0;
 }
@@ -1132,6 +1174,7 @@ int pb_fbrush_get_use_snapshot(const pb_fbrush* b) { return b->use_snapshot ? 1 
 int pb_fbrush_size_map(const pb_fbrush* b) { return b->cur ? b->cur->size_map : 0; }
 int pb_fbrush_pickup_map(pb_fbrush* b, double* K, double* S, double* V) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_pickup_map: null handle");
   DeviceGuard g(b->ctx);
   PB_REQUIRE(b->pick.base != nullptr, "brush has no pickup map yet (setRadius was never applied)");
   if (K) download_aos(b->ctx, b->pick, PK, 3, K);
@@ -1141,6 +1184,7 @@ int pb_fbrush_pickup_map(pb_fbrush* b, double* K, double* S, double* V) {
 }
 int pb_fbrush_pickup_layer(pb_fbrush* b, pb_layer** out) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_pickup_layer: null handle");
   PB_REQUIRE(b->pick.base != nullptr, "brush has no pickup map yet (setRadius was never applied)");
   auto l  = std::make_unique<pb_layer>();
   l->pl   = b->pick;
@@ -1150,6 +1194,8 @@ int pb_fbrush_pickup_layer(pb_fbrush* b, pb_layer** out) {
 }
 int pb_fbrush_update_snapshot(pb_fbrush* b, pb_canvas* c) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_update_snapshot: null handle");
+  PB_REQUIRE(c != nullptr, "pb_fbrush_update_snapshot: null handle");
   DeviceGuard g(b->ctx);
   if (b->snapshot.base == nullptr || b->snapshot.rows != c->pl.rows || b->snapshot.cols != c->pl.cols) {
     ensure_snapshot(b, c);
@@ -1165,6 +1211,7 @@ int pb_fbrush_update_snapshot(pb_fbrush* b, pb_canvas* c) {
 }
 int pb_fbrush_snapshot_download(pb_fbrush* b, double* K, double* S, double* V) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_snapshot_download: null handle");
   DeviceGuard g(b->ctx);
   PB_REQUIRE(b->snapshot.base != nullptr, "brush has no snapshot buffer yet");
   if (K) download_aos(b->ctx, b->snapshot, PK, 3, K);
@@ -1175,6 +1222,8 @@ int pb_fbrush_snapshot_download(pb_fbrush* b, double* K, double* S, double* V) {
 int pb_fbrush_imprint_batch(pb_fbrush* b, pb_canvas* c, int64_t n, const double* cx, const double* cy,
                             const double* theta) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_imprint_batch: null handle");
+  PB_REQUIRE(c != nullptr, "pb_fbrush_imprint_batch: null handle");
   DeviceGuard g(b->ctx);
   PB_REQUIRE(b->cur != nullptr, "imprint before setRadius: the brush has no footprint");
   if (n <= 0) return 0;
@@ -1239,6 +1288,8 @@ void stroke_batch_impl(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_s
 int pb_fbrush_stroke_batch(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_stroke* strokes, int64_t n_imprints,
                            const double* cx, const double* cy, const double* theta) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_stroke_batch: null handle");
+  PB_REQUIRE(c != nullptr, "pb_fbrush_stroke_batch: null handle");
   DeviceGuard g(b->ctx);
   stroke_batch_impl(b, c, n_strokes, strokes, n_imprints, cx, cy, theta, nullptr);
   PB_API_END
@@ -1247,6 +1298,7 @@ int pb_fbrush_stroke_batch(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const 
 // ---- multi-GPU ---------------------------------------------------------------------------------------------
 int pb_ipc_export(pb_context* ctx, void* dev_ptr, unsigned char handle[PB_IPC_HANDLE_BYTES]) {
   PB_API_BEGIN
+  PB_REQUIRE(ctx != nullptr, "pb_ipc_export: null handle");
   DeviceGuard g(ctx);
   static_assert(sizeof(cudaIpcMemHandle_t) == PB_IPC_HANDLE_BYTES, "IPC handle size");
   cudaIpcMemHandle_t h;
@@ -1256,6 +1308,7 @@ int pb_ipc_export(pb_context* ctx, void* dev_ptr, unsigned char handle[PB_IPC_HA
 }
 int pb_ipc_import(pb_context* ctx, const unsigned char handle[PB_IPC_HANDLE_BYTES], void** dev_ptr) {
   PB_API_BEGIN
+  PB_REQUIRE(ctx != nullptr, "pb_ipc_import: null handle");
   DeviceGuard g(ctx);
   cudaIpcMemHandle_t h;
   std::memcpy(&h, handle, sizeof(h));
@@ -1264,11 +1317,13 @@ int pb_ipc_import(pb_context* ctx, const unsigned char handle[PB_IPC_HANDLE_BYTE
 }
 int pb_ipc_close(pb_context* ctx, void* dev_ptr) {
   PB_API_BEGIN
+  PB_REQUIRE(ctx != nullptr, "pb_ipc_close: null handle");
   DeviceGuard g(ctx);
   PB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
   PB_API_END
 }
 int pb_canvas_storage(pb_canvas* c, void** base, int64_t* plane_stride_bytes) {
+  PB_CHECK_HANDLE(c, "pb_canvas_storage");
   if (base) *base = c->pl.base;
   if (plane_stride_bytes) *plane_stride_bytes = static_cast<int64_t>(c->pl.stride);
   return 0;
@@ -1276,6 +1331,8 @@ int pb_canvas_storage(pb_canvas* c, void** base, int64_t* plane_stride_bytes) {
 int pb_fbrush_dist_storage(pb_fbrush* b, pb_canvas* c, void** snapshot_base, int64_t* snapshot_stride_bytes, void** dirty_base,
                            void** flags_base) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_dist_storage: null handle");
+  PB_REQUIRE(c != nullptr, "pb_fbrush_dist_storage: null handle");
   DeviceGuard g(b->ctx);
   ensure_snapshot(b, c);
   if (b->dist_flags == nullptr) {
@@ -1292,6 +1349,8 @@ int pb_fbrush_dist_storage(pb_fbrush* b, pb_canvas* c, void** snapshot_base, int
 int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* d, int64_t n_strokes, const pb_stroke* strokes,
                                 int64_t n_imprints, const double* cx, const double* cy, const double* theta) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_stroke_batch_dist: null handle");
+  PB_REQUIRE(c != nullptr, "pb_fbrush_stroke_batch_dist: null handle");
   DeviceGuard g(b->ctx);
   PB_REQUIRE(d != nullptr && d->world >= 1 && d->world <= kMaxBands && d->rank >= 0 && d->rank < d->world, "invalid pb_dist_desc");
   PB_REQUIRE(d->rows_per_band > 0 && c->halo == 0 && c->row_begin == d->rank * d->rows_per_band &&
@@ -1314,11 +1373,13 @@ int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* 
   PB_API_END
 }
 int pb_fbrush_enable_visited_count(pb_fbrush* b, int enable) {
+  PB_CHECK_HANDLE(b, "pb_fbrush_enable_visited_count");
   b->count_visited = enable != 0;
   return 0;
 }
 int pb_fbrush_counters(pb_fbrush* b, uint64_t* visited, uint64_t* active) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_counters: null handle");
   DeviceGuard g(b->ctx);
   unsigned long long h[2];
   PB_CUDA(cudaMemcpyAsync(h, b->d_counters, sizeof(h), cudaMemcpyDeviceToHost, b->ctx->stream));
@@ -1420,6 +1481,7 @@ void smudge_strokes(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const pb_tstr
 
 int pb_tbrush_create(pb_context* ctx, int map_rows, int map_cols, const double* thickness_map, pb_tbrush** out) {
   PB_API_BEGIN
+  PB_REQUIRE(ctx != nullptr, "pb_tbrush_create: null handle");
   DeviceGuard g(ctx);
   PB_REQUIRE(map_rows > 0 && map_cols > 0 && thickness_map != nullptr, "texture brush needs a thickness map");
   auto b      = std::make_unique<pb_tbrush>();
@@ -1449,6 +1511,7 @@ int pb_tbrush_destroy(pb_tbrush* b) {
 }
 int pb_tbrush_set_radius(pb_tbrush* b, double radius) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_tbrush_set_radius: null handle");
   if (!(std::fabs(b->radius - radius) < 0.5)) {  // TextureBrush.hxx:33-41
     b->radius = radius;
     if (b->use_smudge) {  // _smudge = Smudge(int(2 * radius)): fresh, clean windows
@@ -1471,10 +1534,12 @@ int pb_tbrush_set_radius(pb_tbrush* b, double radius) {
   PB_API_END
 }
 int pb_tbrush_enable_smudge(pb_tbrush* b, int enable) {
+  PB_CHECK_HANDLE(b, "pb_tbrush_enable_smudge");
   b->use_smudge = enable != 0;
   return 0;
 }
 int pb_tbrush_dip(pb_tbrush* b, const double K[3], const double S[3]) {
+  PB_CHECK_HANDLE(b, "pb_tbrush_dip");
   for (int i = 0; i < 3; ++i) {
     b->paintK[i] = K[i];
     b->paintS[i] = S[i];
@@ -1482,12 +1547,15 @@ int pb_tbrush_dip(pb_tbrush* b, const double K[3], const double S[3]) {
   return 0;
 }
 int pb_tbrush_set_thickness_scale(pb_tbrush* b, double scale) {
+  PB_CHECK_HANDLE(b, "pb_tbrush_set_thickness_scale");
   b->thickness_scale = scale;
   return 0;
 }
 int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const pb_tstroke* strokes, int64_t n_vertices,
                            const double* path_xy) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_tbrush_stroke_batch: null handle");
+  PB_REQUIRE(c != nullptr, "pb_tbrush_stroke_batch: null handle");
   pb_context* ctx = b->ctx;
   DeviceGuard g(ctx);
   PB_REQUIRE(c->pl.ctx == ctx, "canvas and brush belong to different contexts");
@@ -1581,6 +1649,7 @@ int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const 
   PB_API_END
 }
 int pb_tbrush_paint_stroke(pb_tbrush* b, pb_canvas* c, int n, const double* path_xy) {
+  PB_CHECK_HANDLE(b, "pb_tbrush_paint_stroke");
   pb_tstroke s{};
   s.radius = b->radius;
   for (int i = 0; i < 3; ++i) {
@@ -1594,6 +1663,7 @@ int pb_tbrush_paint_stroke(pb_tbrush* b, pb_canvas* c, int n, const double* path
 }
 int pb_tbrush_counters(pb_tbrush* b, uint64_t* pixels) {
   PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_tbrush_counters: null handle");
   DeviceGuard g(b->ctx);
   unsigned long long h = 0;
   PB_CUDA(cudaMemcpyAsync(&h, b->d_counters, sizeof(h), cudaMemcpyDeviceToHost, b->ctx->stream));

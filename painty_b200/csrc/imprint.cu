@@ -36,6 +36,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <tuple>
 #include <type_traits>
 
@@ -867,6 +868,8 @@ void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& sme
   L.cluster  = cluster;
   L.group    = group;
   // occupancy queries and attribute changes cost milliseconds: do them once per launch shape
+  static std::mutex cache_mutex;  // contexts of different devices may plan from different host threads
+  std::lock_guard<std::mutex> lock(cache_mutex);
   static std::map<std::tuple<int, int, int, int, size_t>, int> cache;
   const bool multi = L.n_bands > 1;
   const auto key   = std::make_tuple(ctx->device, ctx->precision * 2 + (multi ? 1 : 0), cluster * 100 + group, block, smem_bytes);

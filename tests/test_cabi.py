@@ -270,3 +270,35 @@ def test_claim_order_is_topological_and_keeps_runs(built_lib):
     for p in (0, 1):
         seq = [int(run[s]) for s in order if pool[s] == p]
         assert seq == sorted(seq)
+
+
+def test_null_handles_are_errors_not_crashes(built_lib):
+    """A binding that passes a NULL handle gets status 1 and a message from pb_last_error(), never a segfault."""
+    import ctypes as C
+
+    from painty_b200 import api
+
+    lib = api.lib()
+    lib.pb_last_error.restype = C.c_char_p
+    null = C.c_void_p(None)
+    out = (C.c_double * 3)()
+    calls = [
+        ("pb_canvas_clear", (null,)),
+        ("pb_canvas_dry", (null,)),
+        ("pb_canvas_compose", (null, out)),
+        ("pb_layer_clear", (null,)),
+        ("pb_fbrush_set_pickup_rate", (null, C.c_double(0.5))),
+        ("pb_fbrush_set_use_snapshot", (null, 1)),
+        ("pb_fbrush_clean", (null,)),
+        ("pb_fbrush_dip", (null, out, out)),
+        ("pb_tbrush_dip", (null, out, out)),
+        ("pb_tbrush_enable_smudge", (null, 1)),
+        ("pb_canvas_stored_rows", (null, None, None)),
+    ]
+    for name, args in calls:
+        rc = getattr(lib, name)(*args)
+        assert rc == 1, name
+        assert b"null handle" in lib.pb_last_error(), name
+    # destroying NULL is a no-op, like free()
+    for name in ("pb_canvas_destroy", "pb_layer_destroy", "pb_fbrush_destroy", "pb_tbrush_destroy", "pb_context_destroy"):
+        assert getattr(lib, name)(null) == 0, name
