@@ -1227,6 +1227,7 @@ int pb_fbrush_imprint_batch(pb_fbrush* b, pb_canvas* c, int64_t n, const double*
   DeviceGuard g(b->ctx);
   PB_REQUIRE(b->cur != nullptr, "imprint before setRadius: the brush has no footprint");
   if (n <= 0) return 0;
+  PB_REQUIRE(cx != nullptr && cy != nullptr && theta != nullptr, "imprint_batch: null imprint arrays");
   PB_REQUIRE(n < (int64_t(1) << 31), "too many imprints in one batch");
   HostStroke h;
   h.g      = b->cur;
@@ -1246,6 +1247,8 @@ void stroke_batch_impl(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_s
                        const double* cx, const double* cy, const double* theta, const DistInfo* dist) {
   if (n_strokes <= 0) return;
   PB_REQUIRE(n_strokes < (int64_t(1) << 27), "too many strokes in one batch");
+  PB_REQUIRE(strokes != nullptr && n_imprints >= 0 && (n_imprints == 0 || (cx != nullptr && cy != nullptr && theta != nullptr)),
+             "stroke_batch: null stroke or imprint arrays");
   std::vector<HostStroke> hs(static_cast<size_t>(n_strokes));
   double radius            = b->radius;
   const FootprintGeom* cur = b->cur;
