@@ -102,6 +102,15 @@ int pb_plan_claim_order(int rows, int cols, int64_t n, const int64_t* first, con
                         int segment_length, int use_snapshot, const int32_t* pool, const int32_t* run, const double* cost,
                         int n_pools, const int32_t* runs_per_pool, const int32_t* slots, int32_t* order, double* makespan);
 
+/* Test hook (host only): the dirty-map words (4 pixels each) the imprint kernel reads for one snapshot ring pass
+ * (FootprintBrush.hxx:278-319), enumerated by the same code the device runs. box = (tlx, tly, brx, bry), the
+ * footprint box whose open interior is excluded; allowed = (ax0, ay0, ax1, ay1), the clipped allowed box, inclusive.
+ * Writes up to `capacity` (row, word index) pairs and the total count. */
+int pb_ring_words(const int32_t box[4], const int32_t allowed[4], int64_t capacity, int32_t* rows, int32_t* words, int64_t* n_words);
+
+/* Test hook (host only): the device's exact test "(int)round(x) == m" for a pickup-cell index m >= 0. */
+int pb_rounds_to(double x, int m);
+
 /* ---- PaintLayer ------------------------------------------------------------------------------ */
 int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out);
 int pb_layer_destroy(pb_layer* l);

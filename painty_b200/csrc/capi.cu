@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "host_math.hpp"
 #include "imprint.cuh"
+#include "ring_words.hpp"
 #include "schedule.hpp"
 #include "texture.cuh"
 #include "texture_host.hpp"
@@ -749,6 +750,23 @@ int pb_plan_claim_order(int rows, int cols, int64_t n, const int64_t* first, con
   for (int64_t s = 0; s < n; ++s) order[s] = seq[static_cast<size_t>(s)];
   PB_API_END
 }
+
+int pb_ring_words(const int32_t box[4], const int32_t allowed[4], int64_t capacity, int32_t* rows, int32_t* words, int64_t* n_words) {
+  PB_API_BEGIN
+  PB_REQUIRE(box != nullptr && allowed != nullptr && n_words != nullptr, "pb_ring_words: null argument");
+  const RingGeom g{box[0], box[1], box[2], box[3], allowed[0], allowed[1], allowed[2], allowed[3]};
+  const RingWords rw(g);
+  for (int64_t i = 0; i < std::min<int64_t>(capacity, rw.total); ++i) {
+    int row = 0, wi = 0;
+    rw.at(static_cast<int>(i), row, wi);
+    rows[i]  = row;
+    words[i] = wi;
+  }
+  *n_words = rw.total;
+  PB_API_END
+}
+
+int pb_rounds_to(double x, int m) { return rounds_to(x, m) ? 1 : 0; }
 
 // ---- PaintLayer --------------------------------------------------------------------------------------
 int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out) {

@@ -41,6 +41,7 @@
 #include <type_traits>
 
 #include "imprint.cuh"
+#include "ring_words.hpp"
 
 namespace cg = cooperative_groups;
 
@@ -289,11 +290,6 @@ __device__ __forceinline__ Hits find_hits(const ImprintLaunch& L, const Band<T>*
 // word loads (kScanBatch independent L2 requests in flight), then all pixel loads of a dirty word, then stores.
 constexpr int kScanBatch = 8;
 
-struct RingGeom {
-  int tlx, tly, brx, bry;  // footprint box corners (exclusive interior bounds)
-  int ax0, ay0, ax1, ay1;  // allowed box, clipped to canvas and stored rows
-};
-
 template <typename T, bool MULTI>
 __device__ __forceinline__ void ring_word(const ImprintLaunch& L, const Band<T>* views, const RingGeom& g, int row, int wi,
                                           unsigned word) {
@@ -328,12 +324,8 @@ __device__ __forceinline__ void ring_word(const ImprintLaunch& L, const Band<T>*
 
 template <typename T, bool MULTI>
 __device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const Band<T>* views, const RingGeom& g, int gt, int gstride) {
-  if (g.ax1 < g.ax0 || g.ay1 < g.ay0) return;
-  const int w0 = g.ax0 >> 2, nw = (g.ax1 >> 2) - w0 + 1, nrows = g.ay1 - g.ay0 + 1;
-  const int total = nw * nrows;
-  const float inv = 1.0f / static_cast<float>(nw);
-  // words lying completely inside the open interior (on interior rows) are never read
-  const int iw0 = (g.tlx >> 2) + 1, iw1 = (g.brx - 4) >> 2;
+  const RingWords rw(g);  // exactly the words outside the open interior (ring_words.hpp)
+  const int total = rw.total;
   for (int base = gt; base < total; base += gstride * kScanBatch) {
     unsigned word[kScanBatch];
     int rows[kScanBatch], wis[kScanBatch];
@@ -342,20 +334,15 @@ __device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const Band<T>*
       const int i = base + u * gstride;
       word[u]     = 0u;
       if (i < total) {
-        int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv);  // i / nw without integer division
-        r     = min(r, nrows - 1);
-        if (r * nw > i) --r;
-        if ((r + 1) * nw <= i) ++r;
-        const int wi = w0 + (i - r * nw), row = g.ay0 + r;
+        int row, wi;
+        rw.at(i, row, wi);
         rows[u] = row;
         wis[u]  = wi;
-        if (!(row > g.tly && row < g.bry && wi >= iw0 && wi <= iw1)) {
-          const int band = MULTI ? band_of(L, row) : 0;
-          const int lrow = MULTI ? row - band * L.rows_per_band : row - L.store_first;
-          const unsigned char* dbase = MULTI ? views[band].dirty : L.own_dirty;
-          const int dpitch           = MULTI ? views[band].dpitch : L.dirty_pitch;
-          word[u] = __ldcg(reinterpret_cast<const unsigned*>(dbase + static_cast<int64_t>(lrow) * dpitch) + wi);
-        }
+        const int band = MULTI ? band_of(L, row) : 0;
+        const int lrow = MULTI ? row - band * L.rows_per_band : row - L.store_first;
+        const unsigned char* dbase = MULTI ? views[band].dirty : L.own_dirty;
+        const int dpitch           = MULTI ? views[band].dpitch : L.dirty_pitch;
+        word[u] = __ldcg(reinterpret_cast<const unsigned*>(dbase + static_cast<int64_t>(lrow) * dpitch) + wi);
       }
     }
 #pragma unroll

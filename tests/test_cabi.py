@@ -302,3 +302,61 @@ def test_null_handles_are_errors_not_crashes(built_lib):
     # destroying NULL is a no-op, like free()
     for name in ("pb_canvas_destroy", "pb_layer_destroy", "pb_fbrush_destroy", "pb_tbrush_destroy", "pb_context_destroy"):
         assert getattr(lib, name)(null) == 0, name
+
+
+def test_ring_word_enumeration_matches_the_reference_ring(built_lib):
+    """The snapshot ring pass reads the dirty map in 4-pixel words. The device enumerates only the words that hold a
+    ring pixel candidate: every word of the allowed rows outside the footprint box rows, and on box rows the words not
+    completely inside the open interior (FootprintBrush.hxx:298-316: allowed box minus open interior). The same code
+    runs here on the host (pb_ring_words) against a brute-force enumeration, for random and degenerate geometries."""
+    import ctypes as C
+
+    from painty_b200 import api
+
+    lib = api.lib()
+    rng = np.random.default_rng(3)
+
+    def device_words(box, allowed):
+        b = (C.c_int32 * 4)(*box)
+        a = (C.c_int32 * 4)(*allowed)
+        n = C.c_int64(0)
+        dummy = (C.c_int32 * 1)()
+        assert lib.pb_ring_words(b, a, C.c_int64(0), dummy, dummy, C.byref(n)) == 0
+        rows = (C.c_int32 * max(n.value, 1))()
+        words = (C.c_int32 * max(n.value, 1))()
+        assert lib.pb_ring_words(b, a, C.c_int64(n.value), rows, words, C.byref(n)) == 0
+        return list(zip(rows[:n.value], words[:n.value]))
+
+    def expected_words(box, allowed):
+        tlx, tly, brx, bry = box
+        ax0, ay0, ax1, ay1 = allowed
+        out = []
+        if ax1 < ax0 or ay1 < ay0:
+            return out
+        for row in range(ay0, ay1 + 1):
+            for wi in range(ax0 >> 2, (ax1 >> 2) + 1):
+                inside = tly < row < bry and all(tlx < col < brx for col in range(4 * wi, 4 * wi + 4))
+                if not inside:
+                    out.append((row, wi))
+        return out
+
+    cases = []
+    for _ in range(300):
+        wr = int(rng.integers(0, 40))
+        rad = int(rng.integers(0, 40))
+        cx, cy = int(rng.integers(-60, 260)), int(rng.integers(-60, 200))
+        rows, cols = 180, 240
+        box = (cx - wr, cy - wr, cx + wr, cy + wr)
+        allowed = (max(cx - wr - rad, 0), max(cy - wr - rad, 0), min(cx + wr + rad, cols - 1), min(cy + wr + rad, rows - 1))
+        cases.append((box, allowed))
+    cases += [((5, 5, 5, 5), (0, 0, 20, 20)), ((5, 5, 6, 6), (3, 3, 9, 9)), ((0, 0, 100, 100), (10, 10, 50, 50)),
+              ((10, 10, 50, 50), (10, 10, 50, 50)), ((-30, -30, 10, 10), (0, 0, 40, 40)), ((10, 10, 20, 20), (30, 30, 20, 20))]
+    total = skipped = 0
+    for box, allowed in cases:
+        got, want = device_words(box, allowed), expected_words(box, allowed)
+        assert len(got) == len(set(got)), (box, allowed)  # every word once
+        assert set(got) == set(want), (box, allowed)
+        total += len(got)
+        if allowed[2] >= allowed[0] and allowed[3] >= allowed[1]:
+            skipped += ((allowed[2] >> 2) - (allowed[0] >> 2) + 1) * (allowed[3] - allowed[1] + 1) - len(got)
+    assert total > 10000 and skipped > 10000  # the interior really is left out
