@@ -360,3 +360,110 @@ def test_ring_word_enumeration_matches_the_reference_ring(built_lib):
         if allowed[2] >= allowed[0] and allowed[3] >= allowed[1]:
             skipped += ((allowed[2] >> 2) - (allowed[0] >> 2) + 1) * (allowed[3] - allowed[1] + 1) - len(got)
     assert total > 10000 and skipped > 10000  # the interior really is left out
+
+
+def _emulate_queues(n, seg_first, seg_off, ps, pn, order, pool, run, slots, rng):
+    """Discrete-event emulation of the device protocol: per pool and launch, `slots` clusters pop strokes strictly in
+    claim order and block on (stroke, segments needed) waits; segment durations are random. Returns the number of
+    strokes that finished (== n unless the protocol deadlocks)."""
+    import heapq
+
+    nseg = np.diff(seg_first)
+    queues = {}
+    for s in order:
+        queues.setdefault((int(pool[s]), int(run[s])), []).append(int(s))
+    progress = np.zeros(n, dtype=np.int64)
+    cur_run = {p: 0 for p in range(len(slots))}
+    head = {k: 0 for k in queues}
+    left = {k: len(v) for k, v in queues.items()}
+    state = {p: [None] * max(slots[p][0], 1) if slots[p] else [] for p in range(len(slots))}
+    events, now, done = [], 0.0, 0
+
+    def ready(s, k):
+        g = seg_first[s] + k
+        return all(progress[ps[i]] >= pn[i] for i in range(seg_off[g], seg_off[g + 1]))
+
+    def advance(p):
+        nonlocal now
+        while cur_run[p] < len(slots[p]) and left.get((p, cur_run[p]), 0) == 0:
+            cur_run[p] += 1
+            if cur_run[p] < len(slots[p]):
+                state[p] = [None] * max(slots[p][cur_run[p]], 1)
+        if cur_run[p] >= len(slots[p]):
+            return
+        key = (p, cur_run[p])
+        for i in range(len(state[p])):
+            st = state[p][i]
+            if st is None and head[key] < len(queues[key]):
+                st = state[p][i] = [queues[key][head[key]], 0, False]
+                head[key] += 1
+            if st is not None and not st[2] and ready(st[0], st[1]):
+                st[2] = True
+                heapq.heappush(events, (now + float(rng.uniform(0.2, 3.0)), p, i))
+
+    for p in range(len(slots)):
+        advance(p)
+    while events:
+        now, p, i = heapq.heappop(events)
+        s, k, _ = state[p][i]
+        k += 1
+        if k >= nseg[s]:
+            progress[s] = 1 << 40
+            state[p][i] = None
+            left[(p, cur_run[p])] -= 1
+            done += 1
+        else:
+            progress[s] = k
+            state[p][i] = [s, k, False]
+        for q in range(len(slots)):
+            advance(q)
+    return done
+
+
+def test_claim_order_protocol_never_deadlocks_on_eight_gpus(built_lib):
+    """The band-sharded bench workload shape on 8 pools (GPUs): executor = band of the first imprint, strokes whose
+    region leaves their band are single-segment (as the multi-GPU path plans them), launches split by footprint class.
+    The planned claim order must let the in-order queues drain under arbitrary timing. Pure host code."""
+    from painty_b200 import api, assets
+
+    rng = np.random.default_rng(23)
+    world, rpb, cols = 8, 300, 700
+    rows = world * rpb
+    n = 1200
+    first, count, side, radius, cx, cy = [], [], [], [], [], []
+    for i in range(n):
+        m = int(rng.integers(1, 260))
+        r = float(rng.choice([6.0, 14.0, 30.0, 45.0])) if i % 3 else float(rng.uniform(5, 45))
+        x, y, a = rng.uniform(0, cols), rng.uniform(0, rows), rng.uniform(0, 2 * np.pi)
+        first.append(len(cx)); count.append(m); radius.append(r); side.append(assets.footprint_geometry(r)[3])
+        for _ in range(m):
+            cx.append(x); cy.append(y)
+            a += rng.normal(0, 0.06); x += np.cos(a); y += np.sin(a)
+    cxa, cya = np.asarray(cx), np.asarray(cy)
+    pool = np.zeros(n, np.int32)
+    single = np.zeros(n, np.uint8)
+    for s in range(n):
+        a, m = first[s], count[s]
+        pool[s] = min(min(max(int(cya[a]), 0), rows - 1) // rpb, world - 1)
+        mm = (side[s] - 1) // 2 + radius[s] + 2.0
+        lo = max(0, int(np.floor(cya[a:a + m].min() - mm)))
+        hi = min(rows - 1, int(np.ceil(cya[a:a + m].max() + mm)))
+        single[s] = lo < pool[s] * rpb or hi > min((pool[s] + 1) * rpb, rows) - 1
+    assert 0.05 < single.mean() < 0.9
+    run, slots, last = np.zeros(n, np.int32), [[] for _ in range(world)], [None] * world
+    for s in range(n):
+        cls = 0 if radius[s] < 10 else (1 if radius[s] < 35 else 2)
+        if last[pool[s]] != cls:
+            slots[pool[s]].append(9 if cls else 20)
+            last[pool[s]] = cls
+        run[s] = len(slots[pool[s]]) - 1
+    cost = 5.2 + 0.002 * np.asarray(side, dtype=np.float64) ** 2
+    order, makespan = api.plan_claim_order(rows, cols, first, count, side, radius, cx, cy, pool, run, cost, slots, 32, True,
+                                           single=single, return_makespan=True)
+    assert sorted(order) == list(range(n)) and makespan > 0
+    seg_first, seg_len, seg_off, ps, pn = api.plan_segments(rows, cols, first, count, side, radius, cx, cy, 32, True, single=single)
+    assert all(seg_first[s + 1] - seg_first[s] == 1 for s in range(n) if single[s])
+    for trial in range(3):
+        assert _emulate_queues(n, seg_first, seg_off, ps, pn, order, pool, run, slots, np.random.default_rng(trial)) == n
+    # the check has teeth: reversing the queues makes later strokes wait for strokes stuck behind them
+    assert _emulate_queues(n, seg_first, seg_off, ps, pn, order[::-1], pool, run[::-1] * 0, [[2]] * world, np.random.default_rng(0)) < n
