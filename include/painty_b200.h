@@ -108,9 +108,6 @@ int pb_plan_claim_order(int rows, int cols, int64_t n, const int64_t* first, con
  * Writes up to `capacity` (row, word index) pairs and the total count. */
 int pb_ring_words(const int32_t box[4], const int32_t allowed[4], int64_t capacity, int32_t* rows, int32_t* words, int64_t* n_words);
 
-/* Test hook (host only): the device's exact test "(int)round(x) == m" for a pickup-cell index m >= 0. */
-int pb_rounds_to(double x, int m);
-
 /* ---- PaintLayer ------------------------------------------------------------------------------ */
 int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out);
 int pb_layer_destroy(pb_layer* l);

@@ -766,8 +766,6 @@ int pb_ring_words(const int32_t box[4], const int32_t allowed[4], int64_t capaci
   PB_API_END
 }
 
-int pb_rounds_to(double x, int m) { return rounds_to(x, m) ? 1 : 0; }
-
 // ---- PaintLayer --------------------------------------------------------------------------------------
 int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out) {
   PB_API_BEGIN

@@ -16,14 +16,6 @@
 
 namespace pb {
 
-// (int)round(x) == m for an index m >= 0, without evaluating round(): C's round() is round-half-away-from-zero, so
-// round(x) == m  <=>  m - 0.5 <= x < m + 0.5 for m >= 1, and -0.5 < x < 0.5 for m == 0. m +- 0.5 is exact in f64,
-// hence both comparisons are exact and the decision is bit-identical to FootprintBrush.hxx:97-100.
-PB_HD bool rounds_to(double x, int m) {
-  const double md = static_cast<double>(m);
-  return m > 0 ? (x >= md - 0.5 && x < md + 0.5) : (x > -0.5 && x < 0.5);
-}
-
 struct RingGeom {
   int tlx, tly, brx, bry;  // footprint box corners (exclusive interior bounds)
   int ax0, ay0, ax1, ay1;  // allowed box, clipped to canvas and stored rows
