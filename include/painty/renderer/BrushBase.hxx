@@ -1,4 +1,8 @@
-/** Drop-in for painty/renderer/BrushBase.hxx (reference lines 15-47): the abstract brush interface, unchanged. */
+/** Abstract brush contract of the B200 façade.
+ *
+ * Keeps the member names, argument types and defaults of the reference's interface
+ * (painty/renderer/BrushBase.hxx:15-47), so code written against BrushBase<vec3> compiles unchanged; the two concrete
+ * brushes of this façade (FootprintBrush, TextureBrush) forward to the C ABI in painty_b200.h. */
 #pragma once
 
 #include <array>
@@ -7,22 +11,33 @@
 #include "painty/renderer/Canvas.hxx"
 
 namespace painty {
+
 template <class vector_type>
 class BrushBase {
- public:
-  using T                 = typename DataType<vector_type>::channel_type;
-  static constexpr auto N = DataType<vector_type>::dim;
+  using Traits = DataType<vector_type>;
 
+ public:
+  using T                 = typename Traits::channel_type;
+  static constexpr auto N = Traits::dim;
+  using Paint             = std::array<vector_type, 2UL>;  ///< {absorption K, scattering S}
+  using Path              = std::vector<vec2>;              ///< canvas coordinates, x = column
+
+  BrushBase()          = default;
   virtual ~BrushBase() = default;
 
+  /// Brush radius in canvas pixels.
   virtual void setRadius(double radius) = 0;
-  virtual void dip(const std::array<vector_type, 2UL>& paint) = 0;
-  virtual void paintStroke(const std::vector<vec2>& path, Canvas<vector_type>& canvas) = 0;
+  /// Load the brush with a paint.
+  virtual void dip(const Paint& paint) = 0;
+  /// Paint one stroke along `path`.
+  virtual void paintStroke(const Path& path, Canvas<vector_type>& canvas) = 0;
 
-  void setThicknessScale(const T scale) { _thicknessScale = scale; }
-  auto getThicknessScale() const -> T { return _thicknessScale; }
+  /// Factor applied to the thickness of the deposited layer; 1 unless set.
+  auto getThicknessScale() const -> T { return thickness_scale_; }
+  void setThicknessScale(const T scale) { thickness_scale_ = scale; }
 
  private:
-  T _thicknessScale = 1.0;
+  T thickness_scale_ = static_cast<T>(1);
 };
+
 }  // namespace painty
