@@ -383,6 +383,10 @@ def main():
                        "imprints_per_s": world * len(cx) / max(world, 1) / (imp_ms * 1e-3),
                        "active_stroke_pixels_per_s": active / (imp_ms * 1e-3),
                        "model_bytes_per_active_px": 88, "model_GBps": 88 * active / (imp_ms * 1e-3) / 1e9}
+    try:  # host-side share of a batch: dataflow planning, per-imprint constants, the planner's model of the step
+        line["host"] = br.batch_stats()
+    except Exception as exc:  # diagnostics only
+        line["host"] = {"unavailable": str(exc)}
     if rank == 0 and not args.no_cpu and world == 1:
         info = cpu_sample(rec, cx, cy, th, ROWS, COLS)
         t = info["t_imprint"] + info["t_compose_full"] * info["n_sample"] / len(rec)

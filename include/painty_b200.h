@@ -214,6 +214,13 @@ typedef struct pb_stroke {
 int pb_fbrush_register_footprint(pb_fbrush* b, double radius, int side, const double* footprint);
 int pb_fbrush_stroke_batch(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_stroke* strokes, int64_t n_imprints,
                            const double* cx, const double* cy, const double* theta);
+/* Host-side figures of the brush's last stroke or imprint batch (no device access):
+ * [0] dataflow planning ms (segments + claim order), [1] per-imprint constants ms, [2] strokes planned (all ranks),
+ * [3] dataflow segments, [4] wait entries, [5] the planner's model of the batch duration in ms (0 if the queue order
+ * was not planned), [6] strokes executed by this rank, [7] kernel launches of this rank. */
+#define PB_BATCH_STATS 8
+int pb_fbrush_batch_stats(const pb_fbrush* b, double out[PB_BATCH_STATS]);
+
 /* Stroke-pixel counters since creation: visited = the reference's `counter` (:119), cells passing both bounds
  * checks; active = those with footprint height > 0. `visited` is only maintained while counting is enabled
  * (it costs a pass over all footprint cells). */

@@ -468,6 +468,14 @@ class FootprintBrush:
         _chk(lib().pb_fbrush_counters(self.h, C.byref(v), C.byref(a)))
         return v.value, a.value
 
+    def batch_stats(self):
+        """Host-side figures of the last stroke / imprint batch (pb_fbrush_batch_stats)."""
+        out = (C.c_double * 8)()
+        _chk(lib().pb_fbrush_batch_stats(self.h, out))
+        keys = ("plan_ms", "imprint_constants_ms", "strokes_planned", "segments", "wait_entries", "model_ms",
+                "strokes_this_rank", "launches_this_rank")
+        return {k: float(v) for k, v in zip(keys, out)}
+
 
 class TextureBrush:
     """painty::TextureBrush<vec3> with smudge disabled (renderer/TextureBrush.hxx)."""

@@ -3,6 +3,7 @@
 // that computes pixels needs a CUDA device and fails loudly otherwise.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -123,6 +124,8 @@ struct pb_fbrush {
   double paintK[3] = {0, 0, 0}, paintS[3] = {0, 0, 0};                // zero-initialised
   unsigned long long* d_counters = nullptr;                          // [0] active [1] visited
   bool count_visited             = false;
+  // host-side figures of the last stroke / imprint batch (pb_fbrush_batch_stats)
+  double stats[PB_BATCH_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 struct pb_tbrush {
@@ -302,6 +305,8 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     }
     return StrokeSpan{h.first, h.n, (h.g->side - 1) / 2, h.radius, single};
   };
+  const auto t_plan0 = std::chrono::steady_clock::now();
+  double model_makespan = 0.0;
   const SegmentPlan plan = plan_segments(c->rows, c->cols, n, span_of, cx, cy, kSegmentLength, b->use_snapshot,
                                          [&](size_t s, const Region&, const Region& r) {
     const HostStroke& h = hs[s];
@@ -368,7 +373,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
       }
     }
     for (size_t s = 0; s < n; ++s) counts64[s] = hs[s].n;
-    const std::vector<int32_t> seq = plan_claim_order(plan, counts64, spec, slots);
+    const std::vector<int32_t> seq = plan_claim_order(plan, counts64, spec, slots, 64, &model_makespan);
     claim_pos.assign(n, -1);
     for (size_t q = 0; q < seq.size(); ++q) claim_pos[seq[q]] = static_cast<int32_t>(q);
     // the device relies on the order being topological; fall back to submission order otherwise
@@ -381,6 +386,8 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     if (!ok) claim_pos.clear();
   }
   PB_REQUIRE(static_cast<int64_t>(mine.size()) <= kDistFlagCapacity, "too many strokes in one batch");
+
+  const auto t_plan1 = std::chrono::steady_clock::now();
 
   // per-imprint constants of the strokes this rank executes, compacted in execution order
   std::vector<DevImprint> im;
@@ -400,6 +407,18 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
         im[o].s  = std::sin(-theta[i]);
       }
     }
+  }
+  const auto t_prep1 = std::chrono::steady_clock::now();
+  {
+    auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
+    b->stats[0] = ms(t_plan0, t_plan1);                                   // dataflow planning (segments + claim order)
+    b->stats[1] = ms(t_plan1, t_prep1);                                   // per-imprint constants (cos / sin)
+    b->stats[2] = static_cast<double>(n);                                 // strokes planned (all ranks)
+    b->stats[3] = static_cast<double>(plan.seg_first[n]);                 // dataflow segments
+    b->stats[4] = static_cast<double>(plan.pred_stroke.size());           // wait entries
+    b->stats[5] = model_makespan * 1e-3;                                  // the planner's model of the batch, ms
+    b->stats[6] = static_cast<double>(mine.size());                       // strokes this rank executes
+    b->stats[7] = static_cast<double>(my_runs.size());                    // kernel launches of this rank
   }
   DevBuf<DevImprint> d_im(ctx, im.size());
   d_im.upload(im.data(), im.size());
@@ -1394,6 +1413,12 @@ int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* 
 int pb_fbrush_enable_visited_count(pb_fbrush* b, int enable) {
   PB_CHECK_HANDLE(b, "pb_fbrush_enable_visited_count");
   b->count_visited = enable != 0;
+  return 0;
+}
+int pb_fbrush_batch_stats(const pb_fbrush* b, double out[PB_BATCH_STATS]) {
+  PB_CHECK_HANDLE(b, "pb_fbrush_batch_stats");
+  PB_CHECK_HANDLE(out, "pb_fbrush_batch_stats");
+  for (int i = 0; i < PB_BATCH_STATS; ++i) out[i] = b->stats[i];
   return 0;
 }
 int pb_fbrush_counters(pb_fbrush* b, uint64_t* visited, uint64_t* active) {
