@@ -147,7 +147,8 @@ def test_dataflow_planner_orders_every_conflicting_pair(built_lib):
     assert conflicts > 1000 and independent > 1000  # the plan really leaves parallelism
 
 
-def test_segment_plan_orders_every_conflicting_segment_pair(built_lib):
+@pytest.mark.parametrize("use_snapshot", [True, False])
+def test_segment_plan_orders_every_conflicting_segment_pair(built_lib, use_snapshot):
     """The footprint brush tracks dependencies per SEGMENT of a stroke (progress counters instead of one completion
     flag). For a random overlapping stroke list: every pair of segments of two different strokes whose regions
     conflict (box of one meets the allowed region of the other) must be ordered, earlier stroke first, through the
@@ -167,7 +168,7 @@ def test_segment_plan_orders_every_conflicting_segment_pair(built_lib):
             a += rng.normal(0, 0.05); x += np.cos(a); y += np.sin(a)
     first.append(len(cx)); count.append(0); radius.append(10.0); side.append(assets.footprint_geometry(10.0)[3])  # empty stroke
     n += 1
-    seg_first, seg_len, seg_off, ps, pn = api.plan_segments(rows, cols, first, count, side, radius, cx, cy, seg, True)
+    seg_first, seg_len, seg_off, ps, pn = api.plan_segments(rows, cols, first, count, side, radius, cx, cy, seg, use_snapshot)
     n_seg = int(seg_first[-1])
     assert len(seg_off) == n_seg + 1 and seg_off[0] == 0 and seg_off[-1] == len(ps)
     owner = np.repeat(np.arange(n), np.diff(seg_first))
@@ -213,7 +214,8 @@ def test_segment_plan_orders_every_conflicting_segment_pair(built_lib):
     conflicts = free = 0
     for g in range(n_seg):
         for q in range(int(seg_first[owner[g]])):  # segments of earlier strokes
-            if meets(box[g], alw[q]) or meets(alw[g], box[q]):
+            # snapshot buffer on: box of one meets the allowed region of the other; off: the boxes meet
+            if (meets(box[g], alw[q]) or meets(alw[g], box[q])) if use_snapshot else meets(box[g], box[q]):
                 conflicts += 1
                 assert (reach[g] >> q) & 1, (q, g)
             elif not (reach[g] >> q) & 1:
