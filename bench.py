@@ -43,24 +43,64 @@ METRIC = "stroke-pixels/sec (imprint+KM compose) at 4K canvas; % of HBM roofline
 COMPOSE_BYTES_PER_PX = 52  # 7 layer planes + 3 R0 read, 3 R written, FP32
 
 
-def build_workload(n_strokes, rows=ROWS, cols=COLS, seed=1234):
-    from painty_b200 import api, assets
+def build_strokes(n_strokes, rows=ROWS, cols=COLS, seed=1234):
+    """The synthetic stroke list (numpy only — the reference arm must not load the product library): list of
+    dict(radius, K, S, path[n,2]); paint = palette mix thinned like the sbr painter's mixed(p, 1, thinner, 0)
+    (PaintMixer.cxx:539-545: ((1*K1) + (0*K2)) * (1 / (1 + 0)))."""
+    from painty_b200 import assets
     from tests.workloads import sbr_strokes
 
     pk, ps = assets.palette("lindemeier_measured")
     tk, ts = assets.palette("thinning_medium")
     strokes = sbr_strokes(rows, cols, n_strokes, seed=seed, safe_radius=assets.snap_to_safe_radius, palette=(pk, ps))
+    inv = 1.0 / (1.0 + 0.0)
+    for s in strokes:
+        s["K"] = ((1.0 * s["K"]) + (0.0 * tk[0])) * inv
+        s["S"] = ((1.0 * s["S"]) + (0.0 * ts[0])) * inv
+    return strokes
+
+
+def imprint_counts(strokes):
+    """Imprints per stroke of FootprintBrush::paintStroke (:251-267): sum over segments of int(|p1 - p0|)."""
+    out = np.zeros(len(strokes), dtype=np.int64)
+    for i, s in enumerate(strokes):
+        d = np.diff(s["path"], axis=0)
+        out[i] = int(np.sum(np.floor(np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]))))
+    return out
+
+
+def build_workload(n_strokes, rows=ROWS, cols=COLS, seed=1234):
+    """Stroke records + imprint arrays for the product arm (expansion = pb_expand_stroke, host f64)."""
+    from painty_b200 import api
+
+    strokes = build_strokes(n_strokes, rows, cols, seed)
     rec = np.zeros(len(strokes), dtype=api.STROKE_DTYPE)
     xs, ys, ts_ = [], [], []
     first = 0
     for i, s in enumerate(strokes):
-        K, S = api.mixed(s["K"], s["S"], 1.0, tk[0], ts[0], 0.0)  # mixed(p,1,thinner,0) like the sbr painter
         cx, cy, th = api.expand_stroke(s["path"], mode=0)
-        rec[i] = (s["radius"], K, S, first, len(cx))
+        rec[i] = (s["radius"], s["K"], s["S"], first, len(cx))
         first += len(cx)
         xs.append(cx), ys.append(cy), ts_.append(th)
     radii = sorted(set(float(s["radius"]) for s in strokes))
-    return rec, np.concatenate(xs), np.concatenate(ys), np.concatenate(ts_), radii
+    return strokes, rec, np.concatenate(xs), np.concatenate(ys), np.concatenate(ts_), radii
+
+
+def expand_with_oracle(cpu, path):
+    """FootprintBrush::paintStroke's expansion (:251-267) evaluated with the CPU checker's Catmull-Rom — the reference
+    arm's own stroke -> imprint step (no product code)."""
+    path = np.asarray(path, dtype=np.float64)
+    cx, cy, th = [], [], []
+    n = len(path)
+    for i in range(n - 1):
+        p_pre, p0, p1, p_next = path[max(i - 1, 0)], path[i], path[i + 1], path[min(i + 2, n - 1)]
+        dist = math.sqrt((p1[0] - p0[0]) * (p1[0] - p0[0]) + (p1[1] - p0[1]) * (p1[1] - p0[1]))
+        for pd in range(1, int(dist) + 1):
+            t = pd / dist
+            d = cpu.catmull_rom(p_pre, p0, p1, p_next, t, True)
+            q = cpu.catmull_rom(p_pre, p0, p1, p_next, t)
+            cx.append(q[0]), cy.append(q[1]), th.append(math.atan2(d[1], d[0]))
+    return np.array(cx), np.array(cy), np.array(th)
 
 
 class ClockSampler:
@@ -98,10 +138,11 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_sample(rec, cx, cy, th, rows, cols, budget_cells=1.5e8, threads=None):
+def cpu_sample(strokes, rows, cols, budget_cells=1.5e8, threads=None, want_image=False):
     """Time the CPU reference path (oracle/_ref when present, else the oracle port) on a bounded sample of the
-    same workload: strokes taken round-robin over the brush-size passes until ~budget visited cells, rendered
-    in submission order on a fresh canvas, plus one threaded ComputeReflectance pass over a canvas slice."""
+    same workload: strokes taken round-robin over the brush-size passes until ~budget visited cells, expanded with the
+    checker's own Catmull-Rom and rendered in submission order on a fresh canvas, plus one threaded ComputeReflectance
+    pass over a canvas slice. No product code runs here."""
     from oracle import cpu as ocpu
     from painty_b200 import assets
 
@@ -109,7 +150,8 @@ def cpu_sample(rec, cx, cy, th, rows, cols, budget_cells=1.5e8, threads=None):
     kind = "reference" if ocpu.have_ref() else "port"
     c = ocpu.Cpu("ref" if kind == "reference" else "port")
     threads = threads or os.cpu_count() or 1
-    n = len(rec)
+    n = len(strokes)
+    counts = imprint_counts(strokes)
     order = []
     per_pass = max(1, n // 4)
     k = 0
@@ -117,32 +159,32 @@ def cpu_sample(rec, cx, cy, th, rows, cols, budget_cells=1.5e8, threads=None):
     while est < budget_cells and k < per_pass:
         for p in range(4):
             i = min(p * per_pass + k, n - 1)
-            side = assets.footprint_geometry(float(rec["radius"][i]))[3]
-            est += float(rec["n_imprints"][i]) * side * side * 0.8
+            side = assets.footprint_geometry(float(strokes[i]["radius"]))[3]
+            est += float(counts[i]) * side * side * 0.8
             order.append(i)
             if est >= budget_cells:
                 break
         k += 1
     order = sorted(set(order))
+    expanded = {i: expand_with_oracle(c, strokes[i]["path"]) for i in order}
     cv = c.canvas(rows, cols)
-    br = c.footprint_brush(float(rec["radius"][order[0]]))
-    counter = ocpu.Cpu("port")  # visited-cell count comes from the port's counters (the reference discards its own)
+    br = c.footprint_brush(float(strokes[order[0]]["radius"]))
     t_imp = 0.0
     for i in order:
-        a, m = int(rec["first_imprint"][i]), int(rec["n_imprints"][i])
-        br.dip(rec["K"][i], rec["S"][i])
-        br.set_radius(float(rec["radius"][i]))
-        t_imp += br.imprint_batch(cv, cx[a:a + m], cy[a:a + m], th[a:a + m])
-    # visited cells of the sample, exact, from the device-independent port on a tiny canvas is not
-    # possible (bounds depend on the canvas) -> count analytically with the port on the same canvas
-    cvp = counter.canvas(rows, cols) if kind == "reference" else None
+        s = strokes[i]
+        br.dip(s["K"], s["S"])
+        br.set_radius(float(s["radius"]))
+        t_imp += br.imprint_batch(cv, *expanded[i])
+    # visited cells of the sample (the reference discards its own `counter`): replay on the port, which counts them
     if kind == "reference":
-        brp = counter.footprint_brush(float(rec["radius"][order[0]]))
+        counter = ocpu.Cpu("port")
+        cvp = counter.canvas(rows, cols)
+        brp = counter.footprint_brush(float(strokes[order[0]]["radius"]))
         for i in order:
-            a, m = int(rec["first_imprint"][i]), int(rec["n_imprints"][i])
-            brp.dip(rec["K"][i], rec["S"][i])
-            brp.set_radius(float(rec["radius"][i]))
-            brp.imprint_batch(cvp, cx[a:a + m], cy[a:a + m], th[a:a + m])
+            s = strokes[i]
+            brp.dip(s["K"], s["S"])
+            brp.set_radius(float(s["radius"]))
+            brp.imprint_batch(cvp, *expanded[i])
         visited = brp.counters()[0]
     else:
         visited = br.counters()[0]
@@ -151,23 +193,27 @@ def cpu_sample(rec, cx, cy, th, rows, cols, budget_cells=1.5e8, threads=None):
     sl = slice(0, max(1, rows // 8))
     t_cmp_slice, _ = c.compose_timed(st["K"][sl], st["S"][sl], st["V"][sl], st["R0"][sl], threads=threads)
     t_cmp_full = t_cmp_slice * rows / (sl.stop - sl.start)
-    return dict(kind=kind, visited=int(visited), t_imprint=t_imp, t_compose_full=t_cmp_full, n_sample=len(order),
-                threads=threads)
+    out = dict(kind=kind, visited=int(visited), t_imprint=t_imp, t_compose_full=t_cmp_full, n_sample=len(order), threads=threads,
+               order=order, expanded=expanded)
+    if want_image:  # for the parity field: the reference's reflectance image and wet-pixel set of the sample
+        out["R"] = cv.compose()
+        out["wet"] = st["V"] > 0
+    return out
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    rec, cx, cy, th, _ = build_workload(args.strokes)
+    strokes = build_strokes(args.strokes)
     vals = []
     info = None
     budget = 1.2e8
     for it in range(args.warmup + args.steps):
         t0 = time.time()
-        info = cpu_sample(rec, cx, cy, th, ROWS, COLS, budget_cells=budget)
+        info = cpu_sample(strokes, ROWS, COLS, budget_cells=budget)
         # compose prorated to the sample's share of the canvas work is negligible next to imprint; we charge
         # the full-canvas compose scaled by sample/total strokes
-        t = info["t_imprint"] + info["t_compose_full"] * info["n_sample"] / len(rec)
+        t = info["t_imprint"] + info["t_compose_full"] * info["n_sample"] / len(strokes)
         if it >= args.warmup:
             vals.append(info["visited"] / t)
         if time.time() - t0 > 40:
@@ -178,9 +224,9 @@ def run_reference(args, rank, world):
             "impl": "reference",
             "config": {"workload": "sbr-style 3840x2160, %d footprint strokes + KM compose (bounded CPU sample)" % args.strokes},
             "cpu_baseline": {"value": v, "unit": "stroke-pixels/s", "cores": 1, "kind": info["kind"],
-                             "sample": "%d of %d strokes (round-robin over the 4 brush-size passes, %d visited cells), imprint single-threaded "
-                                       "as in the reference; compose prorated from a %d-thread row-split" % (
-                                           info["n_sample"], len(rec), info["visited"], info["threads"])},
+                             "sample": "%d of %d strokes (round-robin over the 4 brush-size passes, %d visited cells), stroke expansion and "
+                                       "imprint single-threaded as in the reference; compose prorated from a %d-thread row-split" % (
+                                           info["n_sample"], len(strokes), info["visited"], info["threads"])},
             "e2e": {"value": v, "unit": "stroke-pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -215,7 +261,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     rows_total = ROWS * world
-    rec, cx, cy, th, radii = build_workload(args.strokes * world, rows=rows_total)  # same list on every rank
+    strokes, rec, cx, cy, th, radii = build_workload(args.strokes * world, rows=rows_total)  # same list on every rank
     ctx = api.Context(local, api.F32)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
     dc = None
@@ -237,11 +283,11 @@ def main():
     h_R_np = h_R.numpy()
     gathered = torch.empty((world, 3, n_px), dtype=torch.float32, device="cuda") if world > 1 else None
 
-    def strokes_all():
+    def strokes_all(r=rec, x=cx, y=cy, t=th):
         if dc is not None:
-            dc.stroke_batch(br, rec, cx, cy, th)
+            dc.stroke_batch(br, r, x, y, t)
         else:
-            br.stroke_batch(cv, rec, cx, cy, th)
+            br.stroke_batch(cv, r, x, y, t)
 
     # untimed: exact stroke-pixel count of the workload (reference's `counter`)
     br.enable_visited_count(True)
@@ -316,8 +362,8 @@ def main():
         strokes_all()
         cv.compose(h_R_np)
 
-    # one warm-up pass (first use of the host-buffer path allocates staging memory), one timed pass
-    e2e_steps = 1
+    # one warm-up pass (first use of the host-buffer path allocates staging memory), then timed passes
+    e2e_steps = max(3, args.steps)
     step_e2e()
     barrier()
     t0 = time.perf_counter()
@@ -329,24 +375,25 @@ def main():
         tt = torch.tensor([e2e_ms], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item())
-    h2d = rec.nbytes + cx.nbytes * 4  # stroke records + (cx, cy, cos, sin) per imprint
+    h2d = rec.nbytes + cx.nbytes * 3  # stroke records + (cx, cy, theta) per imprint (the library derives the rest)
     d2h = n_px * 3 * 8
 
-    # roofline of the KM compose kernel, measured live with events around each launch
-    cmp_ms = t_cmp / args.steps
-    roofline_how = "events around the compose launch of every timed step"
-    if world > 1:
-        # at N > 1 the in-step launch follows a host-side process-group barrier (idle GPU + launch latency inside the
-        # event pair); the kernel itself is timed with back-to-back launches right after the timed steps
-        ce0, ce1 = ev(), ev()
+    # Roofline of the KM compose kernel, measured live. "in_step": events around the compose launch of every timed step
+    # (behind the imprint kernel, cold L2; at N > 1 the launch also follows a host-side process-group barrier, so the
+    # event pair includes an idle gap). "back_to_back": 5 launches in a row right after the timed steps. The line's
+    # roofline uses the in-step time at N = 1 and the back-to-back time at N > 1 and says which.
+    cmp_in_step_ms = t_cmp / args.steps
+    ce0, ce1 = ev(), ev()
+    cv.compose_device(d_R.data_ptr(), n_px)
+    ce0.record(stream)
+    for _ in range(5):
         cv.compose_device(d_R.data_ptr(), n_px)
-        ce0.record(stream)
-        for _ in range(5):
-            cv.compose_device(d_R.data_ptr(), n_px)
-        ce1.record(stream)
-        ctx.synchronize()
-        cmp_ms = ce0.elapsed_time(ce1) / 5
-        roofline_how = "5 back-to-back launches after the timed steps (the in-step launch follows a host barrier)"
+    ce1.record(stream)
+    ctx.synchronize()
+    cmp_b2b_ms = ce0.elapsed_time(ce1) / 5
+    cmp_ms = cmp_in_step_ms if world == 1 else cmp_b2b_ms
+    roofline_how = "events around the compose launch of every timed step" if world == 1 else \
+        "5 back-to-back launches after the timed steps (the in-step launch follows a host barrier)"
     achieved = COMPOSE_BYTES_PER_PX * n_px / (cmp_ms * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback"
     try:
@@ -363,38 +410,103 @@ def main():
                    "reflectance" % (rows_total, COLS, world),
                    "stroke_pixels_per_step": int(visited_all), "stroke_pixels_per_step_this_rank": int(visited),
                    "active_stroke_pixels_per_step_this_rank": int(active),
-                   "l2": "canvas working set 8.3 Mpx x 14 planes x 4 B = 464 MB > 126 MB L2; canvas cleared every step",
+                   "l2": "canvas working set 8.3 Mpx x (2 x 32 B records + 1 B) = 539 MB > 126 MB L2; canvas cleared every step",
                    "imprint_ms": t_imp / args.steps, "compose_ms": cmp_ms},
         "clocks": clocks,
         "e2e": {"value": visited_all / (e2e_ms * 1e-3), "unit": "stroke-pixels/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "passes": e2e_steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "km_compose_kernel<float>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "measured": roofline_how,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one 4K launch, ncu --set full (profiles/r01_compose_f32_raw.csv)
-                     "traffic": 401643264 if world == 1 else None, "algorithmic_bytes_per_launch": COMPOSE_BYTES_PER_PX * n_px,
-                     "frac_of_8TBs_nominal": achieved / 8000.0},
+                     "compose_ms_in_step": cmp_in_step_ms, "compose_ms_back_to_back": cmp_b2b_ms,
+                     # NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one 4K launch from the committed
+                     # ncu --set full capture (profiles/r01_compose_f32_raw.csv); null where the launch has another size
+                     "traffic": 401643264 if world == 1 else None, "traffic_source": "ncu constant (profiles/r01_compose_f32_raw.csv)",
+                     "algorithmic_bytes_per_launch": COMPOSE_BYTES_PER_PX * n_px, "frac_of_8TBs_nominal": achieved / 8000.0},
     }
-    # the step's dominant kernel is the imprint chain: latency bound (dependent imprints, L2-resident working set), so no
-    # roofline claim — reported with the upper-bound byte model of SURVEY.md §8d (88 B per active stroke-pixel)
+    # the step's dominant kernel is the imprint chain: a dependency chain of imprints whose working set lives in L2, bound by
+    # the SM's L1 wavefront rate and by barrier latency, not by HBM — reported with its own figures, no roofline claim
     imp_ms = t_imp / args.steps
-    line["imprint"] = {"kernel": "imprint_kernel<float>", "bound": "latency (dependency chain of imprints, see DESIGN.md §5)",
+    line["imprint"] = {"kernel": "imprint_kernel<float>", "bound": "latency (dependency chain of imprints, see DESIGN.md)",
                        "ms_per_step": imp_ms, "ms_each_step": [round(t[0].elapsed_time(t[1]), 1) for t in timers],
-                       "imprints_per_s": world * len(cx) / max(world, 1) / (imp_ms * 1e-3),
+                       "imprints_per_s_this_rank": len(cx) / max(world, 1) / (imp_ms * 1e-3),
                        "active_stroke_pixels_per_s": active / (imp_ms * 1e-3),
-                       "model_bytes_per_active_px": 88, "model_GBps": 88 * active / (imp_ms * 1e-3) / 1e9}
+                       "record_bytes_per_active_px": 101, "record_GBps": 101 * active / (imp_ms * 1e-3) / 1e9}
     try:  # host-side share of a batch: dataflow planning, per-imprint constants, the planner's model of the step
         line["host"] = br.batch_stats()
     except Exception as exc:  # diagnostics only
         line["host"] = {"unavailable": str(exc)}
+
+    if world > 1:
+        # Proof that the band-sharded render is the single-GPU render: a bounded sub-list (every k-th stroke, ~3000 strokes
+        # over all bands) is rendered once across the N GPUs and once on rank 0 alone; K/S/V must agree bit for bit.
+        k = max(1, len(rec) // 3000)
+        sub = np.arange(0, len(rec), k)
+        srec = rec[sub].copy()
+        sx, sy, st_, first = [], [], [], 0
+        for j, i in enumerate(sub):
+            a, m = int(rec["first_imprint"][i]), int(rec["n_imprints"][i])
+            sx.append(cx[a:a + m]), sy.append(cy[a:a + m]), st_.append(th[a:a + m])
+            srec["first_imprint"][j] = first
+            first += m
+        sx, sy, st_ = np.concatenate(sx), np.concatenate(sy), np.concatenate(st_)
+        cv.clear()
+        br.updateSnapshot(cv)
+        strokes_all(srec, sx, sy, st_)
+        ctx.synchronize()
+        band = cv.download("KSV")
+        mine = np.concatenate([band["K"].reshape(-1), band["S"].reshape(-1), band["V"].reshape(-1)])
+        everyone = [None] * world if rank == 0 else None
+        dist.gather_object(mine, everyone, dst=0)
+        if rank == 0:
+            import hashlib
+
+            full = api.Canvas(ctx, rows_total, COLS)
+            br1 = api.FootprintBrush(ctx, radii[0])
+            for r in radii:
+                br1.register_radius(r)
+            br1.stroke_batch(full, srec, sx, sy, st_)
+            ref = full.download("KSV")
+            exact = True
+            h = hashlib.sha256()
+            for r_ in range(world):
+                r0, r1 = r_ * ROWS, (r_ + 1) * ROWS
+                want = np.concatenate([ref["K"][r0:r1].reshape(-1), ref["S"][r0:r1].reshape(-1), ref["V"][r0:r1].reshape(-1)])
+                exact = exact and np.array_equal(want, everyone[r_])
+                h.update(everyone[r_].tobytes())
+            line["parity_vs_1gpu"] = {"bit_exact": bool(exact), "strokes": int(len(srec)), "imprints": int(len(sx)),
+                                      "checksum_sha256_KSV": h.hexdigest()[:16],
+                                      "what": "every %d-th stroke of the workload rendered on %d GPUs vs on one GPU (rank 0)" % (k, world)}
+            del br1, full
+        dist.barrier()
+
     if rank == 0 and not args.no_cpu and world == 1:
-        info = cpu_sample(rec, cx, cy, th, ROWS, COLS)
+        info = cpu_sample(strokes, ROWS, COLS, want_image=True)
         t = info["t_imprint"] + info["t_compose_full"] * info["n_sample"] / len(rec)
         line["cpu_baseline"] = {"value": info["visited"] / t, "unit": "stroke-pixels/s", "cores": 1, "kind": info["kind"],
                                 "sample": "%d of %d strokes (round-robin over the 4 brush-size passes, %d visited cells, %.1f s imprint "
                                           "single-threaded as in the reference); full-canvas compose %.2f s on %d threads, prorated" % (
                                               info["n_sample"], len(rec), info["visited"], info["t_imprint"], info["t_compose_full"],
                                               info["threads"])}
+        # parity of the product path on the very strokes the CPU just rendered: same sample, fresh canvas, FP32 mode
+        order = info["order"]
+        prec = np.zeros(len(order), dtype=api.STROKE_DTYPE)
+        px_, py_, pt_, first = [], [], [], 0
+        for j, i in enumerate(order):
+            a, m = int(rec["first_imprint"][i]), int(rec["n_imprints"][i])
+            px_.append(cx[a:a + m]), py_.append(cy[a:a + m]), pt_.append(th[a:a + m])
+            prec[j] = (rec["radius"][i], rec["K"][i], rec["S"][i], first, m)
+            first += m
+            ex = info["expanded"][i]  # the oracle's own expansion must equal the library's, bit for bit
+            assert np.array_equal(ex[0], px_[-1]) and np.array_equal(ex[1], py_[-1]) and np.array_equal(ex[2], pt_[-1])
+        cv.clear()
+        br.stroke_batch(cv, prec, np.concatenate(px_), np.concatenate(py_), np.concatenate(pt_))
+        got = cv.compose()
+        wet = cv.download("V")["V"] > 0
+        line["parity"] = {"max_abs_err": float(np.abs(got - info["R"]).max()), "tolerance": 1e-4, "strokes": len(order),
+                          "wet_px": int(wet.sum()), "wet_px_equal": bool(np.array_equal(wet, info["wet"])),
+                          "against": "oracle/_ref (the reference's headers)" if info["kind"] == "reference" else "oracle port",
+                          "what": "reflectance of the CPU sample's strokes rendered by the product in FP32 mode on a fresh 4K canvas"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

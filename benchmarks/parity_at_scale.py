@@ -35,7 +35,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--strokes", type=int, default=10000)
     args = ap.parse_args()
-    rec, cx, cy, th, radii = bench.build_workload(args.strokes)
+    _, rec, cx, cy, th, radii = bench.build_workload(args.strokes)
     R32, V32 = render(api.F32, rec, cx, cy, th, radii)
     R64, V64 = render(api.F64, rec, cx, cy, th, radii)
     err = np.abs(R32 - R64)

@@ -105,8 +105,19 @@ int pb_plan_claim_order(int rows, int cols, int64_t n, const int64_t* first, con
 /* Test hook (host only): the dirty-map words (4 pixels each) the imprint kernel reads for one snapshot ring pass
  * (FootprintBrush.hxx:278-319), enumerated by the same code the device runs. box = (tlx, tly, brx, bry), the
  * footprint box whose open interior is excluded; allowed = (ax0, ay0, ax1, ay1), the clipped allowed box, inclusive.
- * Writes up to `capacity` (row, word index) pairs and the total count. */
-int pb_ring_words(const int32_t box[4], const int32_t allowed[4], int64_t capacity, int32_t* rows, int32_t* words, int64_t* n_words);
+ * prev_box / prev_allowed (both NULL or both set) = geometry of the previous imprint: the pass then only enumerates what
+ * entered the ring since. The dirty map is flat (byte index = row * pitch + column): writes up to `capacity`
+ * (row, flat word index) pairs and the total count. */
+int pb_ring_rects(const int32_t box[4], const int32_t allowed[4], const int32_t* prev_box, const int32_t* prev_allowed, int pitch,
+                  int64_t capacity, int32_t* rows, int32_t* words, int64_t* n_words);
+
+/* Test hook (host only): the canvas pixels whose rotated + rounded position (FootprintBrush.hxx:88-114) is pickup-map
+ * cell (mx[i], my[i]) for an imprint at (cx, cy, theta) of a footprint with half side `half_side`, evaluated by the
+ * code the device runs. mode 0: the exact f64 test; mode 1: the single-precision test with undecided band `eps`
+ * (n_hits[i] = -1 where it defers to the exact test). phase = -1, or the border phase 0..3. px/py hold 2 entries
+ * per cell in the reference's row-major order. */
+int pb_imprint_hits(double cx, double cy, double theta, int half_side, int rows, int cols, int64_t n_cells, const int32_t* mx,
+                    const int32_t* my, int mode, double eps, int phase, int32_t* n_hits, int32_t* px, int32_t* py);
 
 /* ---- PaintLayer ------------------------------------------------------------------------------ */
 int pb_layer_create(pb_context* ctx, int rows, int cols, pb_layer** out);
@@ -238,10 +249,12 @@ int pb_fbrush_counters(pb_fbrush* b, uint64_t* visited, uint64_t* active);
 #define PB_MAX_BANDS 8
 typedef struct pb_dist_desc {
   int32_t world, rank, rows_per_band, reserved;
-  void* canvas_base[PB_MAX_BANDS]; /* [rank] = own allocation, others = pb_ipc_import'ed */
-  int64_t canvas_stride[PB_MAX_BANDS];   /* bytes between planes */
+  /* Per rank, the four buffers pb_fbrush_dist_storage returns on that rank: [rank] = own allocation, others =
+   * pb_ipc_import'ed. canvas_base / snapshot_base are pixel-RECORD arrays (8 elements per pixel) of the rank's band. */
+  void* canvas_base[PB_MAX_BANDS];
+  int64_t canvas_stride[PB_MAX_BANDS];   /* unused, 0 */
   void* snapshot_base[PB_MAX_BANDS];
-  int64_t snapshot_stride[PB_MAX_BANDS];
+  int64_t snapshot_stride[PB_MAX_BANDS]; /* unused, 0 */
   void* dirty_base[PB_MAX_BANDS];
   void* flags_base[PB_MAX_BANDS];
 } pb_dist_desc;
@@ -249,13 +262,18 @@ int pb_ipc_export(pb_context* ctx, void* dev_ptr, unsigned char handle[PB_IPC_HA
 int pb_ipc_import(pb_context* ctx, const unsigned char handle[PB_IPC_HANDLE_BYTES], void** dev_ptr);
 int pb_ipc_close(pb_context* ctx, void* dev_ptr);
 int pb_canvas_storage(pb_canvas* c, void** base, int64_t* plane_stride_bytes);
-/* Makes sure the brush's snapshot buffer (full copy of the band, FootprintBrush.hxx:281-284), dirty map and flag
- * buffer exist for this canvas and returns their base pointers for export. */
-int pb_fbrush_dist_storage(pb_fbrush* b, pb_canvas* c, void** snapshot_base, int64_t* snapshot_stride_bytes, void** dirty_base,
+/* Makes sure the brush's working record copy of the band's wet layer, its snapshot buffer (full copy of the band,
+ * FootprintBrush.hxx:281-284), dirty map and flag buffer exist for this canvas and returns their base pointers for
+ * export. */
+int pb_fbrush_dist_storage(pb_fbrush* b, pb_canvas* c, void** canvas_records, void** snapshot_records, void** dirty_base,
                            void** flags_base);
-/* Same contract as pb_fbrush_stroke_batch; every rank passes the SAME global stroke list. The caller must place a
- * process-group barrier before (all ranks have finished preparing their bands) and after (all ranks' kernels have
- * completed) this call. */
+/* A distributed batch runs on the ranks' record copies of their bands, which peers read and write through NVLink:
+ *   pb_fbrush_dist_begin (planes -> records, synchronises the stream)  ->  process-group barrier  ->
+ *   pb_fbrush_stroke_batch_dist, any number of times                  ->  context sync + process-group barrier  ->
+ *   pb_fbrush_dist_end (records -> planes).
+ * pb_fbrush_stroke_batch_dist has the contract of pb_fbrush_stroke_batch; every rank passes the SAME global stroke list. */
+int pb_fbrush_dist_begin(pb_fbrush* b, pb_canvas* c);
+int pb_fbrush_dist_end(pb_fbrush* b, pb_canvas* c);
 int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* dist, int64_t n_strokes, const pb_stroke* strokes,
                                 int64_t n_imprints, const double* cx, const double* cy, const double* theta);
 

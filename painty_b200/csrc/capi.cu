@@ -15,7 +15,6 @@
 #include "common.cuh"
 #include "host_math.hpp"
 #include "imprint.cuh"
-#include "ring_words.hpp"
 #include "schedule.hpp"
 #include "texture.cuh"
 #include "texture_host.hpp"
@@ -110,10 +109,14 @@ struct pb_fbrush {
   std::map<int, std::pair<int, uint64_t>> by_width;         // width -> key of the footprint registered for it
   const FootprintGeom* cur = nullptr;
   pb_planes pick;      // dense pickup map, 7 planes of size_map^2
-  pb_planes snapshot;  // 7 planes, canvas sized, allocated at the first imprint (:281-284)
+  // The engine's pixel records (8 elements per pixel, imprint.cuh), both canvas sized: the snapshot buffer, allocated
+  // at the first imprint (:281-284), and the working copy of the canvas' wet layer the kernels run on (converted from
+  // the SoA planes when a batch starts and back when it ends).
+  void* snap_rec = nullptr;
+  void* work_rec = nullptr;
+  int snap_rows = 0, snap_cols = 0, work_rows = 0, work_cols = 0;
   // 1 byte per canvas pixel: snapshot may differ from canvas there (touched by an imprint since its last ring copy)
-  unsigned char* dirty = nullptr;
-  int dirty_pitch      = 0;
+  unsigned char* dirty = nullptr;  // flat: byte index == pixel index of the stored planes (+ kDirtyPad bytes)
   uint64_t snap_canvas_id = 0, snap_canvas_version = 0;  // canvas state the dirty map is valid for
   // multi-GPU: 64-bit progress words other GPUs poll (kDistFlagCapacity words + 1024 queue counters), batch epoch
   long long* dist_flags = nullptr;
@@ -173,6 +176,17 @@ const FootprintGeom* register_footprint(pb_fbrush* b, double radius, int side, c
         }
       }
     g.n_active = static_cast<int>(xy.size());
+    {  // how far from the imprint centre a touched pixel can lie (imprint.cuh: FootprintGeom::reach)
+      const int wr = (side - 1) / 2;
+      double reach = 0.0;
+      for (uint32_t c : xy) {
+        const double u = std::fabs(static_cast<double>(static_cast<int>(c & 0xffffu) - wr)) + 0.5;
+        const double v = std::fabs(static_cast<double>(static_cast<int>(c >> 16) - wr)) + 0.5;
+        reach          = std::max(reach, std::sqrt(u * u + v * v));
+      }
+      g.reach   = reach;
+      g.compact = reach <= static_cast<double>(wr - 2) && std::getenv("PB_IMPRINT_TWO_PHASE") == nullptr;
+    }
     if (std::getenv("PB_CELL_ORDER") == nullptr || std::atoi(std::getenv("PB_CELL_ORDER")) != 0) {
       // Order the compacted cells by 8x4 tiles of the pickup map: a warp (32 consecutive cells) then covers a compact
       // 2-D patch whose rotated image touches far fewer 32 B sectors of the SoA canvas planes than a 32-cell row
@@ -221,25 +235,45 @@ void brush_set_geometry(pb_fbrush* b, double radius, const FootprintGeom* g) {
   for (int p = 0; p < kLayerPlanes; ++p) fill_plane(b->ctx, b->pick.plane(p), b->pick.n(), 0.0);
 }
 
+// the ring pass reads the dirty map in aligned 32-bit words that may extend a few bytes past the last pixel
+constexpr size_t kDirtyPad = 64;
+size_t dirty_bytes(const pb_canvas* c) { return static_cast<size_t>(c->pl.n()) + kDirtyPad; }
+
+size_t record_bytes(const pb_canvas* c) { return std::max<size_t>(static_cast<size_t>(c->pl.n()) * kRecord * c->pl.ctx->esize(), 256); }
+
+void ensure_work(pb_fbrush* b, pb_canvas* c) {
+  if (b->work_rec != nullptr && b->work_rows == c->pl.rows && b->work_cols == c->pl.cols) return;
+  PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  if (b->work_rec) cudaFree(b->work_rec);
+  b->work_rec = nullptr;
+  PB_CUDA(cudaMalloc(&b->work_rec, record_bytes(c)));
+  b->work_rows = c->pl.rows;
+  b->work_cols = c->pl.cols;
+}
+
+bool snapshot_matches(const pb_fbrush* b, const pb_canvas* c) {
+  return b->snap_rec != nullptr && b->snap_rows == c->pl.rows && b->snap_cols == c->pl.cols;
+}
+
 void ensure_snapshot(pb_fbrush* b, pb_canvas* c) {  // FootprintBrush.hxx:281-284
   pb_context* ctx = b->ctx;
-  if (b->snapshot.base == nullptr || b->snapshot.rows != c->pl.rows || b->snapshot.cols != c->pl.cols) {
+  if (!snapshot_matches(b, c)) {
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
-    planes_free(b->snapshot);
+    if (b->snap_rec) cudaFree(b->snap_rec);
     if (b->dirty) cudaFree(b->dirty);
-    b->dirty = nullptr;
-    planes_alloc(ctx, b->snapshot, c->pl.rows, c->pl.cols, kLayerPlanes);
-    for (int p = 0; p < kLayerPlanes; ++p)
-      PB_CUDA(cudaMemcpyAsync(b->snapshot.plane(p), c->pl.plane(p), static_cast<size_t>(c->pl.n()) * ctx->esize(),
-                              cudaMemcpyDeviceToDevice, ctx->stream));
-    b->dirty_pitch = (c->pl.cols + 15) / 16 * 16;
-    const size_t bytes = static_cast<size_t>(b->dirty_pitch) * std::max(c->pl.rows, 1);
+    b->snap_rec = nullptr;
+    b->dirty    = nullptr;
+    PB_CUDA(cudaMalloc(&b->snap_rec, record_bytes(c)));
+    b->snap_rows = c->pl.rows;
+    b->snap_cols = c->pl.cols;
+    planes_to_records(ctx, c->pl, b->snap_rec, 0, 0, c->pl.cols - 1, c->pl.rows - 1);  // canvas.copyTo(snapshot)
+    const size_t bytes = dirty_bytes(c);
     PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->dirty), bytes));
     PB_CUDA(cudaMemsetAsync(b->dirty, 0, bytes, ctx->stream));
   } else if (b->snap_canvas_id != c->id || b->snap_canvas_version != c->version) {
     // the canvas changed behind this brush's back (clear / dry / upload / another brush / another canvas of
     // the same size): every pixel may now differ from the snapshot
-    PB_CUDA(cudaMemsetAsync(b->dirty, 1, static_cast<size_t>(b->dirty_pitch) * std::max(c->pl.rows, 1), ctx->stream));
+    PB_CUDA(cudaMemsetAsync(b->dirty, 1, dirty_bytes(c), ctx->stream));
   }
   b->snap_canvas_id      = c->id;
   b->snap_canvas_version = c->version;
@@ -275,14 +309,12 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
   PB_REQUIRE(c->pl.ctx == ctx, "canvas and brush belong to different contexts");
   if (hs.empty()) return;
   const bool multi = dist != nullptr && dist->world > 1;
-  if (b->use_snapshot || b->snapshot.base != nullptr) {
-    if (b->use_snapshot || (b->snapshot.rows == c->pl.rows && b->snapshot.cols == c->pl.cols)) ensure_snapshot(b, c);
-  }
-  const bool have_dirty = b->dirty != nullptr && b->snapshot.rows == c->pl.rows && b->snapshot.cols == c->pl.cols;
+  if (b->use_snapshot || snapshot_matches(b, c)) ensure_snapshot(b, c);
+  ensure_work(b, c);
+  const bool have_dirty = b->dirty != nullptr && snapshot_matches(b, c);
   PB_REQUIRE(!multi || (have_dirty && b->use_snapshot), "distributed strokes need the snapshot buffer enabled");
 
   // Global plan: executor rank, local numbering, and the dataflow graph at segment granularity (schedule.hpp).
-  // Strokes that stage neighbour rows in windows read them once at the start, so they keep a single segment.
   const size_t n = hs.size();
   static const int kSegmentLength = [] {
     const char* e = std::getenv("PB_IMPRINT_SEGMENT");  // imprints per dataflow segment; 0 = whole strokes
@@ -294,22 +326,18 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
   std::vector<Region> allowed(multi ? n : 0);
   auto span_of = [&](size_t s) {
     const HostStroke& h = hs[s];
-    bool single         = false;
-    if (multi && h.n > 0) {  // decided from the whole-stroke region, i.e. before the planner asks for segments
-      Region box, r;
-      imprint_regions(h.first, h.n, (h.g->side - 1) / 2, h.radius, cx, cy, c->rows, c->cols, box, r);
-      const int y0 = std::min(std::max(static_cast<int>(cy[h.first]), 0), c->rows - 1);
-      const int ex = std::min(y0 / dist->rows_per_band, dist->world - 1);
-      const int b0 = ex * dist->rows_per_band, b1 = std::min(b0 + dist->rows_per_band, c->rows) - 1;
-      single       = (r.y1 >= r.y0) && (r.y0 < b0 || r.y1 > b1);
-    }
-    return StrokeSpan{h.first, h.n, (h.g->side - 1) / 2, h.radius, single};
+    return StrokeSpan{h.first, h.n, (h.g->side - 1) / 2, h.radius, false};
   };
   const auto t_plan0 = std::chrono::steady_clock::now();
   double model_makespan = 0.0;
+  Region batch{c->cols, c->rows, -1, -1};
   const SegmentPlan plan = plan_segments(c->rows, c->cols, n, span_of, cx, cy, kSegmentLength, b->use_snapshot,
                                          [&](size_t s, const Region&, const Region& r) {
     const HostStroke& h = hs[s];
+    if (r.x1 >= r.x0 && r.y1 >= r.y0) {  // everything the batch reads or writes
+      batch.x0 = std::min(batch.x0, r.x0), batch.y0 = std::min(batch.y0, r.y0);
+      batch.x1 = std::max(batch.x1, r.x1), batch.y1 = std::max(batch.y1, r.y1);
+    }
     if (multi && h.n > 0) {
       const int y0 = std::min(std::max(static_cast<int>(cy[h.first]), 0), c->rows - 1);
       executor[s]  = std::min(y0 / dist->rows_per_band, dist->world - 1);
@@ -352,6 +380,15 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     const char* e = std::getenv("PB_IMPRINT_REORDER");
     return e == nullptr || std::atoi(e) != 0;
   }();
+  // us per imprint = kCostBase + kCostPerCell * active cells (scratch/imprint_micro.py on a 16-CTA cluster)
+  static const double kCostBase = [] {
+    const char* e = std::getenv("PB_IMPRINT_COST_BASE");
+    return e ? std::atof(e) : 3.0;
+  }();
+  static const double kCostPerCell = [] {
+    const char* e = std::getenv("PB_IMPRINT_COST_CELL");
+    return e ? std::atof(e) : 0.35e-3;
+  }();
   std::vector<int32_t> claim_pos;  // global stroke -> position in the claim sequence (empty = submission order)
   if (kReorder && n > 1) {
     std::vector<ClaimSpec> spec(n);
@@ -365,10 +402,10 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
         size_t smem = 0;
         imprint_plan(ctx, run_max_active(locals[r], runs[j]), L, smem);
         const int64_t n_run = static_cast<int64_t>(runs[j].second - runs[j].first);
-        slots[r].push_back(static_cast<int>(std::min<int64_t>(L.grid / (L.cluster * L.group), n_run)));
+        slots[r].push_back(static_cast<int>(std::min<int64_t>(imprint_slots(L), n_run)));
         for (size_t k = runs[j].first; k < runs[j].second; ++k) {
           const size_t s = locals[r][k];
-          spec[s]        = ClaimSpec{r, static_cast<int32_t>(j), 5.2 + 0.81e-3 * hs[s].g->n_active};
+          spec[s]        = ClaimSpec{r, static_cast<int32_t>(j), kCostBase + kCostPerCell * hs[s].g->n_active};
         }
       }
     }
@@ -400,12 +437,8 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     for (size_t k = 0; k < mine.size(); ++k) {
       const HostStroke& h = hs[mine[k]];
       local_first[k]      = static_cast<int64_t>(o);
-      for (int64_t i = h.first; i < h.first + h.n; ++i, ++o) {
-        im[o].cx = cx[i];
-        im[o].cy = cy[i];
-        im[o].c  = std::cos(-theta[i]);  // FootprintBrush.hxx:95-96, per-imprint constants
-        im[o].s  = std::sin(-theta[i]);
-      }
+      const int wr        = (h.g->side - 1) / 2;
+      for (int64_t i = h.first; i < h.first + h.n; ++i, ++o) im[o] = make_imprint(cx[i], cy[i], theta[i], wr);  // :95-96
     }
   }
   const auto t_prep1 = std::chrono::steady_clock::now();
@@ -432,6 +465,18 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     d_flags.zero(mine.size() + 1);
   }
 
+  // Single GPU: the kernels run on the record copy of the wet layer — convert the batch's region (stored rows, columns
+  // rounded to 4) on the way in and back on the way out. Multi GPU: the whole band is converted by pb_fbrush_dist_begin /
+  // _end around the batch (peers read each other's records, so every rank must be converted before any kernel starts).
+  Region conv{0, 0, -1, -1};
+  if (!multi && batch.x1 >= batch.x0 && batch.y1 >= batch.y0) {
+    conv.x0 = batch.x0 & ~3;
+    conv.x1 = std::min(c->cols - 1, batch.x1 | 3);
+    conv.y0 = std::max(batch.y0, c->store_first) - c->store_first;
+    conv.y1 = std::min(batch.y1, c->store_first + c->pl.rows - 1) - c->store_first;
+    planes_to_records(ctx, c->pl, b->work_rec, conv.x0, conv.y0, conv.x1, conv.y1);
+  }
+
   for (const auto& my_run : my_runs) {
     const size_t run_begin = my_run.first, run_end = my_run.second;
     const size_t n_run = run_end - run_begin;
@@ -439,6 +484,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     std::vector<DevStroke> ds(n_run);
     std::vector<int2> run_preds;
     std::vector<int32_t> run_seg_off(1, 0);
+    std::vector<DevWindow> run_windows;  // one entry per segment of the run, parallel to run_seg_off
     int max_active = 1;
     size_t max_window = 0;
     for (size_t k = 0; k < n_run; ++k) {
@@ -458,40 +504,52 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
         d.paintS[q] = h.S[q];
       }
       d.flags    = h.flags;
-      d.pad      = 0;
-      d.win_band[0] = d.win_band[1] = -1;
-      d.win_row0[0] = d.win_row0[1] = d.win_rows[0] = d.win_rows[1] = 0;
+      if (!h.g->compact) d.flags |= kStrokeTwoPhase;
+      // half width of the undecided band of the single-precision hit test: 3x the error bound of imprint_geom.hpp
+      d.eps      = static_cast<float>(1e-6 * ((h.g->side - 1) / 2) + 2e-5);
       d.win_ox = d.win_cols = 0;
+      const int nseg = plan.seg_first[s + 1] - plan.seg_first[s];
+      const size_t win_first = run_windows.size();
+      run_windows.resize(win_first + static_cast<size_t>(nseg), DevWindow{{-1, -1}, {0, 0}, {0, 0}});
       if (multi && remote[s]) {
-        // the part of the region in a neighbour's band is staged in a local window (<= 2 neighbours, bounded size);
-        // anything larger falls back to direct peer accesses with system-scope fences
+        // Per dataflow segment, the part of the segment's region in a neighbour's band is staged in a local window
+        // (<= 2 neighbours, bounded size); anything larger falls back to direct peer accesses with system-scope fences.
         const Region& r = allowed[s];
-        const int rpb = dist->rows_per_band, ba = r.y0 / rpb, bb = r.y1 / rpb;
+        const int rpb = dist->rows_per_band;
         const int ox = r.x0 & ~3, wc = ((r.x1 - ox + 1) + 3) & ~3;
-        int nw = 0;
+        const int half = (h.g->side - 1) / 2;
         size_t bytes = 0;
-        bool ok = (bb - ba) <= 2 && std::getenv("PB_DIST_DIRECT") == nullptr;  // env: force the direct path (tests)
-        for (int bnd = ba; bnd <= bb && ok; ++bnd) {
-          if (bnd == dist->rank) continue;
-          if (nw == 2) {
-            ok = false;
-            break;
+        bool ok = std::getenv("PB_DIST_DIRECT") == nullptr;  // env: force the direct path (tests)
+        for (int k2 = 0; k2 < nseg && ok; ++k2) {
+          Region sbox, sall;
+          const int64_t len = plan.seg_len[s];
+          imprint_regions(h.first + k2 * len, std::min<int64_t>(len, h.n - k2 * len), half, h.radius, cx, cy, c->rows, c->cols, sbox,
+                          sall);
+          if (sall.y1 < sall.y0) continue;
+          DevWindow& w = run_windows[win_first + static_cast<size_t>(k2)];
+          int nw = 0;
+          for (int bnd = sall.y0 / rpb; bnd <= sall.y1 / rpb && ok; ++bnd) {
+            if (bnd == dist->rank) continue;
+            if (nw == 2) {
+              ok = false;
+              break;
+            }
+            const int g0 = std::max(sall.y0, bnd * rpb), g1 = std::min(sall.y1, std::min((bnd + 1) * rpb, c->rows) - 1);
+            w.band[nw] = bnd;
+            w.row0[nw] = g0 - bnd * rpb;
+            w.rows[nw] = g1 - g0 + 1;
+            bytes = std::max(bytes, static_cast<size_t>(w.rows[nw]) * wc * (2 * kRecord * ctx->esize() + 2) + 64);
+            ++nw;
           }
-          const int g0 = std::max(r.y0, bnd * rpb), g1 = std::min(r.y1, std::min((bnd + 1) * rpb, c->rows) - 1);
-          d.win_band[nw] = bnd;
-          d.win_row0[nw] = g0 - bnd * rpb;
-          d.win_rows[nw] = g1 - g0 + 1;
-          bytes = std::max(bytes, static_cast<size_t>(d.win_rows[nw]) * wc * (2 * kLayerPlanes * ctx->esize() + 2));
-          ++nw;
         }
         if (ok && bytes <= (size_t(192) << 20)) {
           d.win_ox   = ox;
           d.win_cols = wc;
-          d.flags |= 8;
+          d.flags |= kStrokeWindows;
           max_window = std::max(max_window, (bytes + 255) / 256 * 256);
         } else {
-          d.win_band[0] = d.win_band[1] = -1;
-          d.flags |= 4;
+          for (int k2 = 0; k2 < nseg; ++k2) run_windows[win_first + static_cast<size_t>(k2)] = DevWindow{{-1, -1}, {0, 0}, {0, 0}};
+          d.flags |= kStrokeDirect;
         }
       }
       max_active = std::max(max_active, d.n_active);
@@ -510,25 +568,21 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     L.n_bands = multi ? dist->world : 1;
     size_t smem = 0;
     imprint_plan(ctx, max_active, L, smem);
-    L.grid = static_cast<int>(std::min<int64_t>(L.grid, static_cast<int64_t>(n_run) * L.cluster * L.group));
+    L.grid = static_cast<int>(std::min<int64_t>(L.grid, static_cast<int64_t>(n_run) * L.cluster));
     if (multi) {
       for (int r = 0; r < dist->world; ++r) {
-        for (int p = 0; p < kLayerPlanes; ++p) {
-          L.canvas[r][p]   = static_cast<char*>(dist->canvas_base[r]) + static_cast<size_t>(p) * dist->canvas_stride[r];
-          L.snapshot[r][p] = static_cast<char*>(dist->snapshot_base[r]) + static_cast<size_t>(p) * dist->snapshot_stride[r];
-        }
-        L.dirty[r] = dist->dirty_base[r];
-        L.done[r]  = dist->flags_base[r];
+        L.canvas[r]   = dist->canvas_base[r];
+        L.snapshot[r] = dist->snapshot_base[r];
+        L.dirty[r]    = dist->dirty_base[r];
+        L.done[r]     = dist->flags_base[r];
       }
       L.rows_per_band = dist->rows_per_band;
       L.my_band       = dist->rank;
       L.queue         = reinterpret_cast<int*>(b->dist_flags + kDistFlagCapacity + (b->dist_queue_slot++ % 1024));
       PB_CUDA(cudaMemsetAsync(L.queue, 0, sizeof(int), ctx->stream));
     } else {
-      for (int p = 0; p < kLayerPlanes; ++p) {
-        L.canvas[0][p]   = c->pl.plane(p);
-        L.snapshot[0][p] = b->use_snapshot ? b->snapshot.plane(p) : c->pl.plane(p);
-      }
+      L.canvas[0]     = b->work_rec;
+      L.snapshot[0]   = b->use_snapshot ? b->snap_rec : b->work_rec;
       L.dirty[0]      = have_dirty ? b->dirty : nullptr;
       L.done[0]       = d_flags.p;
       L.rows_per_band = std::max(c->pl.rows, 1);
@@ -536,15 +590,12 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
       L.queue         = reinterpret_cast<int*>(d_flags.p + mine.size());
       if (run_begin > 0) PB_CUDA(cudaMemsetAsync(L.queue, 0, sizeof(int), ctx->stream));
     }
-    for (int p = 0; p < kLayerPlanes; ++p) {
-      L.own_canvas[p]   = L.canvas[L.my_band][p];
-      L.own_snapshot[p] = L.snapshot[L.my_band][p];
-      L.pick_dense[p]   = b->pick.base ? b->pick.plane(p) : nullptr;
-    }
+    L.own_canvas   = L.canvas[L.my_band];
+    L.own_snapshot = L.snapshot[L.my_band];
+    for (int p = 0; p < kLayerPlanes; ++p) L.pick_dense[p] = b->pick.base ? b->pick.plane(p) : nullptr;
     L.own_dirty = L.dirty[L.my_band];
     L.epoch           = epoch;
     L.flag_offset     = static_cast<int>(run_begin);
-    L.dirty_pitch     = b->dirty_pitch;
     L.use_snapshot    = b->use_snapshot ? 1 : 0;
     L.rows            = c->rows;
     L.cols            = c->cols;
@@ -571,15 +622,14 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     d_strokes.upload(ds.data(), ds.size());
     d_preds.upload(run_preds.data(), run_preds.size());
     d_seg_off.upload(run_seg_off.data(), run_seg_off.size());
-    DevBuf<char> d_scratch(ctx, static_cast<size_t>(L.scratch_stride) * L.grid * ctx->esize());
-    const size_t n_groups = static_cast<size_t>(L.grid / (L.cluster * L.group));
-    DevBuf<unsigned char> d_windows(ctx, 2 * max_window * n_groups);
+    DevBuf<char> d_scratch(ctx, static_cast<size_t>(L.scratch_stride) * L.grid);
+    const size_t n_slots = static_cast<size_t>(imprint_slots(L));
+    DevBuf<unsigned char> d_windows(ctx, 2 * max_window * n_slots);
+    DevBuf<DevWindow> d_win_desc(ctx, multi ? run_windows.size() : 0);
+    if (multi) d_win_desc.upload(run_windows.data(), run_windows.size());
+    L.windows     = multi ? d_win_desc.p : nullptr;
     L.win_scratch = d_windows.p;
     L.win_stride  = static_cast<int64_t>(2 * max_window);
-    DevBuf<long long> d_group(ctx, L.group > 1 ? 2 * n_groups : 0);  // [0,n): stroke slots, [n,2n): barrier counters
-    if (L.group > 1) d_group.zero(2 * n_groups);
-    L.group_stroke = d_group.p;
-    L.group_bar    = reinterpret_cast<unsigned*>(d_group.p + n_groups);
     L.scratch  = d_scratch.p;
     L.strokes  = d_strokes.p;
     L.imprints = d_im.p;
@@ -589,6 +639,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     imprint_launch(ctx, L, smem);
     if (b->count_visited) imprint_count_visited(ctx, d_strokes.p, L.n_strokes, d_im.p, c->rows, c->cols, b->d_counters + 1);
   }
+  if (!multi) records_to_planes(ctx, b->work_rec, c->pl, conv.x0, conv.y0, conv.x1, conv.y1);
   c->version++;
   if (have_dirty) {
     b->snap_canvas_id      = c->id;
@@ -770,18 +821,53 @@ int pb_plan_claim_order(int rows, int cols, int64_t n, const int64_t* first, con
   PB_API_END
 }
 
-int pb_ring_words(const int32_t box[4], const int32_t allowed[4], int64_t capacity, int32_t* rows, int32_t* words, int64_t* n_words) {
+int pb_ring_rects(const int32_t box[4], const int32_t allowed[4], const int32_t* prev_box, const int32_t* prev_allowed, int pitch,
+                  int64_t capacity, int32_t* rows, int32_t* words, int64_t* n_words) {
   PB_API_BEGIN
-  PB_REQUIRE(box != nullptr && allowed != nullptr && n_words != nullptr, "pb_ring_words: null argument");
+  PB_REQUIRE(box != nullptr && allowed != nullptr && n_words != nullptr && pitch > 0, "pb_ring_rects: bad argument");
+  PB_REQUIRE((prev_box == nullptr) == (prev_allowed == nullptr), "pb_ring_rects: previous box and allowed go together");
   const RingGeom g{box[0], box[1], box[2], box[3], allowed[0], allowed[1], allowed[2], allowed[3]};
-  const RingWords rw(g);
-  for (int64_t i = 0; i < std::min<int64_t>(capacity, rw.total); ++i) {
-    int row = 0, wi = 0;
-    rw.at(static_cast<int>(i), row, wi);
-    rows[i]  = row;
-    words[i] = wi;
+  RingGeom prev{};
+  if (prev_box) prev = RingGeom{prev_box[0], prev_box[1], prev_box[2], prev_box[3], prev_allowed[0], prev_allowed[1], prev_allowed[2], prev_allowed[3]};
+  int64_t n = 0;
+  // the device's enumeration (imprint.cu: ring_scan), item by item
+  ring_rects(g, prev_box ? &prev : nullptr, [&](const Rect& r) {
+    const int nw = rect_words(r), cnt = (r.y1 - r.y0 + 1) * nw;
+    const float inv = 1.0f / static_cast<float>(nw);
+    for (int t = 0; t < cnt; ++t, ++n) {
+      int row = 0, j = 0;
+      rect_item(r, nw, inv, t, row, j);
+      if (n < capacity) {
+        rows[n]  = row;
+        words[n] = ((row * pitch + r.x0) >> 2) + j;
+      }
+    }
+  });
+  *n_words = n;
+  PB_API_END
+}
+
+int pb_imprint_hits(double cx, double cy, double theta, int half_side, int rows, int cols, int64_t n_cells, const int32_t* mx,
+                    const int32_t* my, int mode, double eps, int phase, int32_t* n_hits, int32_t* px, int32_t* py) {
+  PB_API_BEGIN
+  PB_REQUIRE(n_cells >= 0 && (n_cells == 0 || (mx && my && n_hits && px && py)), "pb_imprint_hits: null argument");
+  PB_REQUIRE(mode == 0 || mode == 1, "pb_imprint_hits: mode must be 0 (exact) or 1 (single precision)");
+  const DevImprint im = make_imprint(cx, cy, theta, half_side);
+  const float lo = 0.5f - static_cast<float>(eps), hi = 0.5f + static_cast<float>(eps);
+  for (int64_t i = 0; i < n_cells; ++i) {
+    PixelHits h;
+    if (mode == 0) {
+      hits_exact(im, half_side, mx[i], my[i], rows, cols, phase, h);
+    } else {
+      hits_fast(im.fc, im.fs, im.ix, im.iy, im.flags, static_cast<float>(mx[i] - half_side), static_cast<float>(my[i] - half_side), lo, hi,
+                rows, cols, phase, h);
+    }
+    n_hits[i] = h.n;
+    for (int j = 0; j < 2; ++j) {
+      px[2 * i + j] = h.px[j];
+      py[2 * i + j] = h.py[j];
+    }
   }
-  *n_words = rw.total;
   PB_API_END
 }
 
@@ -1145,7 +1231,8 @@ int pb_fbrush_destroy(pb_fbrush* b) {
       if (kv.second.d_fh) cudaFree(kv.second.d_fh);
     }
     planes_free(b->pick);
-    planes_free(b->snapshot);
+    if (b->snap_rec) cudaFree(b->snap_rec);
+    if (b->work_rec) cudaFree(b->work_rec);
     if (b->dirty) cudaFree(b->dirty);
     if (b->dist_flags) cudaFree(b->dist_flags);
     cudaFree(b->d_counters);
@@ -1232,13 +1319,11 @@ int pb_fbrush_update_snapshot(pb_fbrush* b, pb_canvas* c) {
   PB_REQUIRE(b != nullptr, "pb_fbrush_update_snapshot: null handle");
   PB_REQUIRE(c != nullptr, "pb_fbrush_update_snapshot: null handle");
   DeviceGuard g(b->ctx);
-  if (b->snapshot.base == nullptr || b->snapshot.rows != c->pl.rows || b->snapshot.cols != c->pl.cols) {
+  if (!snapshot_matches(b, c)) {
     ensure_snapshot(b, c);
   } else {
-    for (int p = 0; p < kLayerPlanes; ++p)
-      PB_CUDA(cudaMemcpyAsync(b->snapshot.plane(p), c->pl.plane(p), static_cast<size_t>(c->pl.n()) * b->ctx->esize(),
-                              cudaMemcpyDeviceToDevice, b->ctx->stream));
-    PB_CUDA(cudaMemsetAsync(b->dirty, 0, static_cast<size_t>(b->dirty_pitch) * std::max(c->pl.rows, 1), b->ctx->stream));
+    planes_to_records(b->ctx, c->pl, b->snap_rec, 0, 0, c->pl.cols - 1, c->pl.rows - 1);
+    PB_CUDA(cudaMemsetAsync(b->dirty, 0, dirty_bytes(c), b->ctx->stream));
     b->snap_canvas_id      = c->id;
     b->snap_canvas_version = c->version;
   }
@@ -1248,10 +1333,19 @@ int pb_fbrush_snapshot_download(pb_fbrush* b, double* K, double* S, double* V) {
   PB_API_BEGIN
   PB_REQUIRE(b != nullptr, "pb_fbrush_snapshot_download: null handle");
   DeviceGuard g(b->ctx);
-  PB_REQUIRE(b->snapshot.base != nullptr, "brush has no snapshot buffer yet");
-  if (K) download_aos(b->ctx, b->snapshot, PK, 3, K);
-  if (S) download_aos(b->ctx, b->snapshot, PS, 3, S);
-  if (V) download_aos(b->ctx, b->snapshot, PV, 1, V);
+  PB_REQUIRE(b->snap_rec != nullptr, "brush has no snapshot buffer yet");
+  pb_planes tmp;
+  planes_alloc_temp(b->ctx, tmp, b->snap_rows, b->snap_cols, kLayerPlanes);
+  try {
+    records_to_planes(b->ctx, b->snap_rec, tmp, 0, 0, b->snap_cols - 1, b->snap_rows - 1);
+    if (K) download_aos(b->ctx, tmp, PK, 3, K);
+    if (S) download_aos(b->ctx, tmp, PS, 3, S);
+    if (V) download_aos(b->ctx, tmp, PV, 1, V);
+  } catch (...) {
+    planes_free_temp(tmp);
+    throw;
+  }
+  planes_free_temp(tmp);
   PB_API_END
 }
 int pb_fbrush_imprint_batch(pb_fbrush* b, pb_canvas* c, int64_t n, const double* cx, const double* cy,
@@ -1366,22 +1460,46 @@ int pb_canvas_storage(pb_canvas* c, void** base, int64_t* plane_stride_bytes) {
   if (plane_stride_bytes) *plane_stride_bytes = static_cast<int64_t>(c->pl.stride);
   return 0;
 }
-int pb_fbrush_dist_storage(pb_fbrush* b, pb_canvas* c, void** snapshot_base, int64_t* snapshot_stride_bytes, void** dirty_base,
+int pb_fbrush_dist_storage(pb_fbrush* b, pb_canvas* c, void** canvas_records, void** snapshot_records, void** dirty_base,
                            void** flags_base) {
   PB_API_BEGIN
   PB_REQUIRE(b != nullptr, "pb_fbrush_dist_storage: null handle");
   PB_REQUIRE(c != nullptr, "pb_fbrush_dist_storage: null handle");
   DeviceGuard g(b->ctx);
   ensure_snapshot(b, c);
+  ensure_work(b, c);
   if (b->dist_flags == nullptr) {
     PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->dist_flags), sizeof(long long) * (kDistFlagCapacity + 1024)));
     PB_CUDA(cudaMemsetAsync(b->dist_flags, 0, sizeof(long long) * (kDistFlagCapacity + 1024), b->ctx->stream));
   }
   PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
-  if (snapshot_base) *snapshot_base = b->snapshot.base;
-  if (snapshot_stride_bytes) *snapshot_stride_bytes = static_cast<int64_t>(b->snapshot.stride);
+  if (canvas_records) *canvas_records = b->work_rec;
+  if (snapshot_records) *snapshot_records = b->snap_rec;
   if (dirty_base) *dirty_base = b->dirty;
   if (flags_base) *flags_base = b->dist_flags;
+  PB_API_END
+}
+int pb_fbrush_dist_begin(pb_fbrush* b, pb_canvas* c) {
+  PB_API_BEGIN
+  PB_REQUIRE(b != nullptr && c != nullptr, "pb_fbrush_dist_begin: null handle");
+  DeviceGuard g(b->ctx);
+  PB_REQUIRE(b->work_rec != nullptr && b->work_rows == c->pl.rows && b->work_cols == c->pl.cols && snapshot_matches(b, c),
+             "call pb_fbrush_dist_storage first");
+  ensure_snapshot(b, c);  // marks everything dirty when the canvas changed behind the brush's back
+  planes_to_records(b->ctx, c->pl, b->work_rec, 0, 0, c->pl.cols - 1, c->pl.rows - 1);
+  PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  PB_API_END
+}
+int pb_fbrush_dist_end(pb_fbrush* b, pb_canvas* c) {
+  PB_API_BEGIN
+  PB_REQUIRE(b != nullptr && c != nullptr, "pb_fbrush_dist_end: null handle");
+  DeviceGuard g(b->ctx);
+  PB_REQUIRE(b->work_rec != nullptr && b->work_rows == c->pl.rows && b->work_cols == c->pl.cols, "call pb_fbrush_dist_storage first");
+  records_to_planes(b->ctx, b->work_rec, c->pl, 0, 0, c->pl.cols - 1, c->pl.rows - 1);
+  // the brush's own writes: its dirty map stays valid for the new canvas state
+  c->version++;
+  b->snap_canvas_id      = c->id;
+  b->snap_canvas_version = c->version;
   PB_API_END
 }
 int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* d, int64_t n_strokes, const pb_stroke* strokes,

@@ -92,6 +92,11 @@ void fill_plane(pb_context* ctx, void* plane, int64_t n, double value);
 void upload_aos(pb_context* ctx, const pb_planes& pl, int p0, int ch, const double* host);
 void download_aos(pb_context* ctx, const pb_planes& pl, int p0, int ch, double* host);
 void copy_planes(pb_context* ctx, const pb_planes& src, pb_planes& dst, int nplanes);
+// The imprint engine's pixel records (8 elements per pixel: Kr Kg Kb Sr Sg Sb V 0; record index = stored row * cols +
+// column): convert the rectangle [y0, y1] x [x0, x1] (stored rows) of the 7 layer planes to / from a record array.
+constexpr int kRecord = 8;
+void planes_to_records(pb_context* ctx, const pb_planes& pl, void* records, int x0, int y0, int x1, int y1);
+void records_to_planes(pb_context* ctx, const void* records, const pb_planes& pl, int x0, int y0, int x1, int y1);
 
 // ---- km_compose.cu ------------------------------------------------------------------------------
 struct ComposeArgs {

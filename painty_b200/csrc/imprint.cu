@@ -5,30 +5,29 @@
 //
 // Parallel decomposition (nothing like the reference's serial double loop):
 //   * a STROKE (dip -> setRadius -> chain of imprints) is owned by one persistent thread-block CLUSTER
-//     (1..16 CTAs, ~2 active footprint cells per thread); strokes are popped from a queue in submission
-//     order. Dependencies are tracked per SEGMENT of a stroke (64 imprints): a segment waits until the earlier
-//     strokes whose footprint+snapshot region overlaps its own have published enough progress (host-built
-//     lists of (stroke, segments needed), schedule.hpp) — a dataflow schedule that keeps the reference's
-//     stroke order wherever it is observable while letting overlapping strokes follow each other closely.
-//     Consecutive imprints of a stroke are a true dependency chain; the cluster-wide hardware barrier between
-//     them is the latency floor;
-//   * inside an imprint a thread owns ACTIVE pickup-map cells (footprint height > 0, ~14.5 % of the
-//     padded square, compacted once per radius). Its pickup-map state (7 values per cell) lives in the
-//     CTA's shared memory for the whole stroke. For each imprint the thread inverts the rotation to find
-//     the <= 2 canvas pixels whose rotated+rounded position is its cell, checks each candidate with the
-//     reference's exact f64 forward expression, and applies pickup+deposit to them in row-major order —
-//     exactly the order in which the reference's (row, col) loop hits a shared pickup cell. No two
-//     threads ever touch the same cell;
-//   * canvas pixels are hit at most once per imprint except at the left/top border, where C++
-//     truncation folds column/row (-1,0) onto 0. Those imprints run in <= 4 barrier-separated
-//     phases ordered by (row-negative?, col-negative?) which reproduces the row-major order;
+//     (1..16 CTAs); strokes are popped from a queue in a host-planned order. Dependencies are tracked per SEGMENT
+//     of a stroke (64 imprints): a segment waits until the earlier strokes whose footprint+snapshot region overlaps
+//     its own have published enough progress (host-built lists of (stroke, segments needed), schedule.hpp).
+//     Consecutive imprints of a stroke are a true dependency chain: ONE cluster-wide barrier per imprint;
+//   * inside an imprint a thread owns ACTIVE pickup-map cells (footprint height > 0, ~14.5 % of the padded square,
+//     compacted once per radius). Cell state (7 pickup values, height, coordinates) lives in the CTA's shared memory
+//     for the whole stroke. Per imprint a thread first turns its cells into a list of INTERACTIONS (cell, canvas
+//     pixel): the inverse rotation gives the 2x2 pixel neighbourhood of the cell's pre-image; a single-precision test
+//     decides which of them round onto the cell and falls back to the reference's f64 expression whenever a candidate
+//     is within the float error bound of a rounding boundary (imprint_geom.hpp) — bit-identical decisions, no FP64 on
+//     the common path. A cell has 0, 1 or 2 interactions (1 on average), listed in the row-major order of the
+//     reference's loop; the list of the NEXT imprint is built before the barrier (it depends on no pixel data);
+//   * the interactions are then processed two at a time: all 28 loads in flight, pickup + deposit, stores. Canvas
+//     pixels are unique per imprint except at the left/top border, where C++ truncation folds column/row (-1,0) onto
+//     0: those imprints run in <= 4 barrier-separated phases which reproduce the row-major order;
 //   * updateSnapshot copies a canvas ring of ~2x the footprint area on EVERY imprint in the reference. Here a
-//     byte-per-pixel dirty map records where snapshot and canvas can differ (only pixels touched by an
-//     imprint since their last copy); the ring pass scans the map with 32-bit loads and copies just the dirty
-//     pixels — bit-identical result, ~50x less traffic;
-//   * per-imprint constants (centre, cos/sin(-theta)) are computed on the host in f64 with the same libm
-//     as the reference; all index maths on the device is IEEE f64 without FMA contraction, so every
-//     round()/trunc() decision is bit-identical to the CPU's;
+//     byte-per-pixel dirty map records where snapshot and canvas can differ; the first imprint after a wait scans
+//     the whole ring, every later one only the pixels that ENTERED the ring since the previous imprint (a few
+//     one-pixel strips, handled by the last two warps of each CTA) — bit-identical result. For compact footprints
+//     (every touched pixel lies in the open interior of the footprint box) ring pixels and touched pixels of one imprint
+//     are disjoint, so the ring pass needs no barrier of its own;
+//   * per-imprint constants (centre, cos/sin(-theta), float copies, floor of the centre) come from the host in f64
+//     with the same libm as the reference;
 //   * canvas, snapshot and dirty planes are accessed with L2-only loads/stores (ld/st.global.cg): they are
 //     shared between SMs, and the 126 MB L2 keeps the working set of the running strokes resident.
 #include <cooperative_groups.h>
@@ -41,18 +40,12 @@
 #include <type_traits>
 
 #include "imprint.cuh"
-#include "ring_words.hpp"
 
 namespace cg = cooperative_groups;
 
 namespace pb {
 namespace {
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 // progress words: (batch epoch << 32) | segments completed
 __device__ __forceinline__ long long ld_acquire64(const long long* p) {
   long long v;
@@ -109,40 +102,62 @@ struct OpCtx {
   T paintK[3], paintS[3];
 };
 
-// View of one row band: plane pointers, dirty map and row pitches, indexed with (band-local row) * pitch + column.
-// Single GPU: built from the launch parameters (band is a compile-time 0, everything folds into constant-bank
-// loads). Multi GPU: one view per band in shared memory, rebuilt per stroke — the executor's own band, peer
-// mappings, or local staging windows (virtual base pointers so that the same index arithmetic works).
+// A pixel record: 8 elements (Kr Kg Kb Sr Sg Sb V 0). FP32: 32 bytes = one 256-bit L2-only access (sm_100a
+// LDG/STG.E.256) and exactly one sector; FP64: two of them.
+template <typename T>
+struct Rec {
+  T v[kRecord];
+};
+__device__ __forceinline__ Rec<float> ld_rec(const float* p) {
+  Rec<float> r;
+  asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_rec(float* p, const Rec<float>& r) {
+  asm volatile("st.global.cg.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]),
+               "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+               : "memory");
+}
+__device__ __forceinline__ Rec<double> ld_rec(const double* p) {
+  Rec<double> r;
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p) : "memory");
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[4]), "=d"(r.v[5]), "=d"(r.v[6]), "=d"(r.v[7]) : "l"(p + 4) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_rec(double* p, const Rec<double>& r) {
+  asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.v[0]), "d"(r.v[1]), "d"(r.v[2]), "d"(r.v[3]) : "memory");
+  asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + 4), "d"(r.v[4]), "d"(r.v[5]), "d"(r.v[6]), "d"(r.v[7]) : "memory");
+}
+
+// View of one row band: canvas records, snapshot records and dirty map, all indexed with (band-local row) * pitch +
+// column. Single GPU: built from the launch parameters (everything folds into constant-bank loads). Multi GPU: one view
+// per band in shared memory, rebuilt per dataflow segment — the executor's own band, peer mappings, or local staging
+// windows (virtual base pointers so that the same index arithmetic works).
 template <typename T>
 struct Band {
-  T* can[kLayerPlanes];
-  T* src[kLayerPlanes];
+  T* can;
+  T* src;
   unsigned char* dirty;
   unsigned char* touched;  // staging windows only: pixels to push back to their owner
-  int pitch, dpitch;
+  int pitch;
   __device__ __forceinline__ Band() {}
   __device__ __forceinline__ Band(const ImprintLaunch& L, int band) {
-#pragma unroll
-    for (int k = 0; k < kLayerPlanes; ++k) {
-      can[k] = static_cast<T*>(L.canvas[band][k]);
-      src[k] = static_cast<T*>(L.snapshot[band][k]);
-    }
+    can     = static_cast<T*>(L.canvas[band]);
+    src     = static_cast<T*>(L.snapshot[band]);
     dirty   = L.dirty[band];
     touched = nullptr;
     pitch   = L.cols;
-    dpitch  = L.dirty_pitch;
   }
   // the executor's own band, from dedicated launch fields (compile-time offsets into the constant bank)
   __device__ __forceinline__ explicit Band(const ImprintLaunch& L) {
-#pragma unroll
-    for (int k = 0; k < kLayerPlanes; ++k) {
-      can[k] = static_cast<T*>(L.own_canvas[k]);
-      src[k] = static_cast<T*>(L.own_snapshot[k]);
-    }
+    can     = static_cast<T*>(L.own_canvas);
+    src     = static_cast<T*>(L.own_snapshot);
     dirty   = L.own_dirty;
     touched = nullptr;
     pitch   = L.cols;
-    dpitch  = L.dirty_pitch;
   }
 };
 // VIEWS = the stroke may touch rows of other bands (multi GPU, straddling strokes): pixels are addressed through the
@@ -162,32 +177,22 @@ __device__ __forceinline__ int band_of(const ImprintLaunch& L, int row) {
 // Split in two so that a thread can put the loads of all its interactions in flight before it computes any.
 template <typename T>
 struct OpData {
-  T cK[3], cS[3], sK[3], sS[3], vSrc, vCan;
+  Rec<T> can, src;
 };
 
 template <typename T>
 __device__ __forceinline__ void op_load(const Band<T>& C, int ci, OpData<T>& d) {
-  const bool own_src = C.src[PV] == C.can[PV];  // snapshot buffer disabled: pickup source is the canvas itself
-  d.vSrc = __ldcg(C.src[PV] + ci);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    d.cK[k] = __ldcg(C.can[PK + k] + ci);
-    d.cS[k] = __ldcg(C.can[PS + k] + ci);
-  }
-  d.vCan = own_src ? d.vSrc : __ldcg(C.can[PV] + ci);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    d.sK[k] = own_src ? d.cK[k] : __ldcg(C.src[PK + k] + ci);
-    d.sS[k] = own_src ? d.cS[k] : __ldcg(C.src[PS + k] + ci);
-  }
+  const bool own_src = C.src == C.can;  // snapshot buffer disabled: pickup source is the canvas itself
+  d.can = ld_rec(C.can + static_cast<int64_t>(ci) * kRecord);
+  d.src = own_src ? d.can : ld_rec(C.src + static_cast<int64_t>(ci) * kRecord);
 }
 
 template <typename T>
 __device__ __forceinline__ void op_finish(const OpCtx<T>& P, const Band<T>& C, int ci, T fh, const OpData<T>& d, T* pick, int ps,
                                           int slot) {
   using Blend = typename BlendSel<T>::type;
-  const bool own_src = C.src[PV] == C.can[PV];
-  T vCan = d.vCan;
+  const bool own_src = C.src == C.can;
+  T vCan = d.can.v[PV];
   T vP   = pick[PV * ps + slot];
   T pK[3], pS[3];
 #pragma unroll
@@ -196,16 +201,20 @@ __device__ __forceinline__ void op_finish(const OpCtx<T>& P, const Band<T>& C, i
     pS[k] = pick[(PS + k) * ps + slot];
   }
   // pickup
-  const T leave = P.pickup_rate * d.vSrc * fh;
+  const T vSrc  = d.src.v[PV];
+  const T leave = P.pickup_rate * vSrc * fh;
   if (leave > static_cast<T>(kMinVolume)) {
-    const T remain = d.vSrc - leave;
-    __stcg(C.src[PV] + ci, remain);
-    if (own_src) vCan = remain;
+    const T remain = vSrc - leave;
+    if (own_src) {
+      vCan = remain;
+    } else {
+      __stcg(C.src + static_cast<int64_t>(ci) * kRecord + PV, remain);
+    }
     const Blend bl(vP, leave);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      pK[k] = bl(pK[k], d.sK[k]);
-      pS[k] = bl(pS[k], d.sS[k]);
+      pK[k] = bl(pK[k], d.src.v[PK + k]);
+      pS[k] = bl(pS[k], d.src.v[PS + k]);
     }
     vP = vP + leave;
 #pragma unroll
@@ -221,327 +230,243 @@ __device__ __forceinline__ void op_finish(const OpCtx<T>& P, const Band<T>& C, i
   pick[PV * ps + slot] = vP - vLeave;
   const T vB           = P.cap * fh;
   const Blend b_can(vB, vCan);
+  Rec<T> out;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    __stcg(C.can[PK + k] + ci, b_can(b_src(pK[k], P.paintK[k]), d.cK[k]));
-    __stcg(C.can[PS + k] + ci, b_can(b_src(pS[k], P.paintS[k]), d.cS[k]));
+    out.v[PK + k] = b_can(b_src(pK[k], P.paintK[k]), d.can.v[PK + k]);
+    out.v[PS + k] = b_can(b_src(pS[k], P.paintS[k]), d.can.v[PS + k]);
   }
-  __stcg(C.can[PV] + ci, vB + vCan);
+  out.v[PV] = vB + vCan;
+  out.v[7]  = static_cast<T>(0);
+  st_rec(C.can + static_cast<int64_t>(ci) * kRecord, out);
 }
 
-// The <= 2 canvas pixels whose rotated + rounded position is pickup cell (mx,my), in row-major (row, col) order.
-// Inverse rotation gives the centre (colf,rowf) of the cell's pre-image, a unit square rotated by theta: a lattice
-// point can only map to this cell if its rotated offset from the cell centre is within 0.5 in both axes. A float
-// pre-filter with a 0.01 margin leaves 1-2 of the 2x2 neighbourhood; those are decided by the reference's exact
-// f64 forward expression (:95-100), same operation order, no FMA. Returns the number of hits of phase `ph`.
-struct Hits {
-  int ci[2];   // pixel index in the stored planes (< 2^31, like the reference's int32 K(i))
-  int dof[2];  // byte offset in the dirty map
-  int band[2];
-  int n;
-};
-template <typename T, bool MULTI>
-__device__ __forceinline__ Hits find_hits(const ImprintLaunch& L, const Band<T>* views, const DevImprint& im, float fc, float fs,
-                                          int wr, int mx, int my, bool border, int ph, int row_lo, int row_hi) {
-  Hits h;
-  h.n = 0;
-  h.ci[0] = h.ci[1] = h.dof[0] = h.dof[1] = h.band[0] = h.band[1] = 0;
-  const float u = static_cast<float>(mx - wr), v = static_cast<float>(my - wr);
-  const float colf = fmaf(u, fc, v * fs), rowf = fmaf(v, fc, -u * fs);
-  const int c0 = static_cast<int>(floorf(colf)), r0 = static_cast<int>(floorf(rowf));
-#pragma unroll
-  for (int dr = 0; dr < 2; ++dr) {
-#pragma unroll
-    for (int dc = 0; dc < 2; ++dc) {
-      const int row = r0 + dr, col = c0 + dc;
-      const float ec = static_cast<float>(col) - colf, er = static_cast<float>(row) - rowf;
-      const float du = fmaf(ec, fc, -er * fs), dv = fmaf(ec, fs, er * fc);
-      if (fabsf(du) > 0.51f || fabsf(dv) > 0.51f) continue;
-      if (col < -wr || col > wr || row < -wr || row > wr) continue;
-      const double rc = col * im.c - row * im.s;
-      const double rr = col * im.s + row * im.c;
-      if (static_cast<int>(round(rc + wr)) != mx || static_cast<int>(round(rr + wr)) != my) continue;
-      const double fx = col + im.cx, fy = row + im.cy;
-      const int px = static_cast<int>(fx), py = static_cast<int>(fy);  // trunc toward zero (:92-93)
-      if (py < 0 || px < 0 || px >= L.cols || py >= L.rows) continue;
-      if (border && ((fy >= 0.0 ? 2 : 0) + (fx >= 0.0 ? 1 : 0)) != ph) continue;
-      int band = 0, lrow = py - row_lo, pitch = L.cols, dpitch = L.dirty_pitch;
-      if (MULTI) {
-        band   = band_of(L, py);  // the row's owner GPU
-        lrow   = py - band * L.rows_per_band;
-        pitch  = views[band].pitch;
-        dpitch = views[band].dpitch;
-      } else if (py < row_lo || py > row_hi) {
-        continue;  // band canvas without peers: rows outside the stored window are not ours
-      }
-      const int ci = lrow * pitch + px, dof = lrow * dpitch + px;
-      if (h.n == 0) h.ci[0] = ci, h.dof[0] = dof, h.band[0] = band;
-      if (h.n == 1) h.ci[1] = ci, h.dof[1] = dof, h.band[1] = band;
-      ++h.n;  // a unit cell cannot hold more than 2 lattice points (min distance 1 < diagonal sqrt 2)
-    }
-  }
-  h.n = min(h.n, 2);
-  return h;
+// The rare path of the hit test (a candidate within the float error of a rounding boundary): the reference's f64
+// expression. Kept out of line: it is 4x larger than the common path and runs for well under 1 % of the cells.
+__device__ __noinline__ int3 hits_exact_cold(const DevImprint* imprints, int64_t index, int wr, int mx, int my, int rows, int cols,
+                                             int ph) {
+  const DevImprint full = imprints[index];
+  PixelHits h;
+  hits_exact(full, wr, mx, my, rows, cols, ph, h);
+  return make_int3(h.n, (h.py[0] << 16) | h.px[0], (h.py[1] << 16) | h.px[1]);  // canvas sides are < 65536
 }
 
 // updateSnapshot(canvas, centre) (:278-319): copy canvas -> snapshot on the ring "allowed box minus open
 // interior". Only pixels flagged in the dirty map can differ, so the pass scans the map (one 32-bit word = 4
-// pixels) and copies just those. The imprint chain is latency bound, hence every thread first issues ALL of its
-// word loads (kScanBatch independent L2 requests in flight), then all pixel loads of a dirty word, then stores.
-constexpr int kScanBatch = 8;
-
-template <typename T, bool MULTI>
-__device__ __forceinline__ void ring_word(const ImprintLaunch& L, const Band<T>* views, const RingGeom& g, int row, int wi,
+// pixels) and copies just those. The rectangles to scan come from ring_rects (imprint_geom.hpp): the whole ring, or
+// only what entered it since the previous imprint. Items (words) are numbered across the rectangles; a thread takes
+// items t0, t0 + stride, ...
+template <typename T, bool VIEWS>
+__device__ __forceinline__ void ring_word(const ImprintLaunch& L, const Band<T>* views, const RingGeom& g, int row, int w,
                                           unsigned word) {
-  const bool mid = row > g.tly && row < g.bry;
-  const int band = MULTI ? band_of(L, row) : 0;
-  const int lrow = MULTI ? row - band * L.rows_per_band : row - L.store_first;
-  const Band<T> C = band_view<T, MULTI>(L, views, band);
-  unsigned char* drow = C.dirty + static_cast<int64_t>(lrow) * C.dpitch;
-  const int64_t rbase = static_cast<int64_t>(lrow) * C.pitch;
-  bool need[4];
-  T v[4][kLayerPlanes];
-#pragma unroll
+  const int band = VIEWS ? band_of(L, row) : 0;
+  const int lrow = VIEWS ? row - band * L.rows_per_band : row - L.store_first;
+  const Band<T> C = band_view<T, VIEWS>(L, views, band);
+  const int rbase = lrow * C.pitch;
+#pragma unroll 1
   for (int b = 0; b < 4; ++b) {
-    const int col = wi * 4 + b;
-    need[b] = ((word >> (8 * b)) & 0xffu) != 0u && col >= g.ax0 && col <= g.ax1 && !(mid && col > g.tlx && col < g.brx);
-    if (need[b]) {
-#pragma unroll
-      for (int k = 0; k < kLayerPlanes; ++k) v[b][k] = __ldcg(C.can[k] + rbase + col);
-    }
-  }
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    if (need[b]) {
-      const int col = wi * 4 + b;
-#pragma unroll
-      for (int k = 0; k < kLayerPlanes; ++k) __stcg(C.src[k] + rbase + col, v[b][k]);
-      __stcg(drow + col, static_cast<unsigned char>(0));
-      if (MULTI && C.touched) __stcg(C.touched + static_cast<int64_t>(lrow) * C.dpitch + col, static_cast<unsigned char>(1));
-    }
+    const int f = 4 * w + b;  // flat pixel index == dirty byte index
+    if (((word >> (8 * b)) & 0xffu) == 0u || !in_ring(g, row, f - rbase)) continue;
+    st_rec(C.src + static_cast<int64_t>(f) * kRecord, ld_rec(C.can + static_cast<int64_t>(f) * kRecord));
+    __stcg(C.dirty + f, static_cast<unsigned char>(0));
+    if (VIEWS && C.touched) __stcg(C.touched + f, static_cast<unsigned char>(1));
   }
 }
 
-template <typename T, bool MULTI>
-__device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const Band<T>* views, const RingGeom& g, int gt, int gstride) {
-  const RingWords rw(g);  // exactly the words outside the open interior (ring_words.hpp)
-  const int total = rw.total;
-  for (int base = gt; base < total; base += gstride * kScanBatch) {
-    unsigned word[kScanBatch];
-    int rows[kScanBatch], wis[kScanBatch];
-#pragma unroll
-    for (int u = 0; u < kScanBatch; ++u) {
-      const int i = base + u * gstride;
-      word[u]     = 0u;
-      if (i < total) {
-        int row, wi;
-        rw.at(i, row, wi);
-        rows[u] = row;
-        wis[u]  = wi;
-        const int band = MULTI ? band_of(L, row) : 0;
-        const int lrow = MULTI ? row - band * L.rows_per_band : row - L.store_first;
-        const unsigned char* dbase = MULTI ? views[band].dirty : L.own_dirty;
-        const int dpitch           = MULTI ? views[band].dpitch : L.dirty_pitch;
-        word[u] = __ldcg(reinterpret_cast<const unsigned*>(dbase + static_cast<int64_t>(lrow) * dpitch) + wi);
+template <typename T, bool VIEWS>
+__device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const Band<T>* views, const RingGeom& g, const RingGeom* prev,
+                                          int t0, int stride) {
+  // the rectangle list is small and indexed dynamically below: it lives in local memory (L1), which keeps the scan
+  // loop — instantiated once — out of the emit sites of ring_rects
+  Rect rl[8];
+  int n_rects = 0;
+  ring_rects(g, prev, [&](const Rect& r) {
+    if (n_rects < 8) rl[n_rects++] = r;
+  });
+  int t = t0;  // next item of this thread, relative to the current rectangle
+#pragma unroll 1
+  for (int ri = 0; ri < n_rects; ++ri) {
+    const Rect r = rl[ri];
+    const int nw = rect_words(r), cnt = (r.y1 - r.y0 + 1) * nw;
+    if (t < cnt) {
+      const float inv = __frcp_rn(static_cast<float>(nw));
+#pragma unroll 1
+      for (; t < cnt; t += stride) {
+        int row, j;
+        rect_item(r, nw, inv, t, row, j);
+        const int band = VIEWS ? band_of(L, row) : 0;
+        const int lrow = VIEWS ? row - band * L.rows_per_band : row - L.store_first;
+        const unsigned char* dbase = VIEWS ? views[band].dirty : L.own_dirty;
+        const int pitch            = VIEWS ? views[band].pitch : L.cols;
+        const int w                = ((lrow * pitch + r.x0) >> 2) + j;
+        const unsigned word        = __ldcg(reinterpret_cast<const unsigned*>(dbase) + w);
+        if (word != 0u) ring_word<T, VIEWS>(L, views, g, row, w, word);
       }
     }
-#pragma unroll
-    for (int u = 0; u < kScanBatch; ++u)
-      if (word[u] != 0u) ring_word<T, MULTI>(L, views, g, rows[u], wis[u], word[u]);
+    t -= cnt;
   }
 }
 
 // ---- multi-GPU staging windows ------------------------------------------------------------------------------------
-// Layout of one window in the stroke slot's scratch: 7 canvas planes | 7 snapshot planes (npx elements each) | dirty
+// Layout of one window in the stroke slot's scratch: canvas records | snapshot records (npx records each) | dirty
 // bytes | touched bytes, npx = rows * cols (cols a multiple of 4).
 template <typename T>
 struct Window {
-  T* can[kLayerPlanes];
-  T* src[kLayerPlanes];
+  T* can;
+  T* src;
   unsigned char *dirty, *touched;
   int band, row0, rows, ox, cols;
-  __device__ __forceinline__ Window(const ImprintLaunch& L, const DevStroke& st, int group, int w) {
-    band = st.win_band[w], row0 = st.win_row0[w], rows = st.win_rows[w], ox = st.win_ox, cols = st.win_cols;
-    unsigned char* base = L.win_scratch + static_cast<int64_t>(group) * L.win_stride + static_cast<int64_t>(w) * (L.win_stride / 2);
+  __device__ __forceinline__ Window(const ImprintLaunch& L, const DevStroke& st, const DevWindow& dw, int slot, int w) {
+    band = dw.band[w], row0 = dw.row0[w], rows = dw.rows[w], ox = st.win_ox, cols = st.win_cols;
+    unsigned char* base = L.win_scratch + static_cast<int64_t>(slot) * L.win_stride + static_cast<int64_t>(w) * (L.win_stride / 2);
     const int64_t npx   = static_cast<int64_t>(rows) * cols;
-    T* planes           = reinterpret_cast<T*>(base);
-#pragma unroll
-    for (int k = 0; k < kLayerPlanes; ++k) {
-      can[k] = planes + k * npx;
-      src[k] = planes + (kLayerPlanes + k) * npx;
-    }
-    dirty   = base + 2 * kLayerPlanes * npx * static_cast<int64_t>(sizeof(T));
+    can     = reinterpret_cast<T*>(base);
+    src     = can + npx * kRecord;
+    dirty   = base + 2 * kRecord * npx * static_cast<int64_t>(sizeof(T));
     touched = dirty + npx;
   }
 };
 
-// Build the per-band views of a stroke and pull its windows from the neighbours' HBM (coalesced rows over NVLink).
+// Build the per-band views of a segment and pull its windows from the neighbours' HBM (whole records over NVLink).
 template <typename T>
-__device__ __forceinline__ void stage_in(const ImprintLaunch& L, const DevStroke& st, Band<T>* views, int group, int sgt, int gstride,
-                                         int tid) {
+__device__ __forceinline__ void stage_in(const ImprintLaunch& L, const DevStroke& st, const DevWindow& dw, Band<T>* views, int slot,
+                                         int sgt, int gstride, int tid) {
+  const bool windows = (st.flags & kStrokeWindows) != 0;
   if (tid < L.n_bands) {
     Band<T> v(L, tid);
-    if (st.flags & 8) {
+    if (windows) {
       for (int w = 0; w < 2; ++w) {
-        if (st.win_band[w] != tid) continue;
-        const Window<T> W(L, st, group, w);
+        if (dw.band[w] != tid) continue;
+        const Window<T> W(L, st, dw, slot, w);
         const int64_t off = static_cast<int64_t>(W.row0) * W.cols + W.ox;  // virtual base: index = lrow * cols + px
-#pragma unroll
-        for (int k = 0; k < kLayerPlanes; ++k) {
-          v.can[k] = W.can[k] - off;
-          v.src[k] = W.src[k] - off;
-        }
+        v.can     = W.can - off * kRecord;
+        v.src     = W.src - off * kRecord;
         v.dirty   = W.dirty - off;
         v.touched = W.touched - off;
         v.pitch   = W.cols;
-        v.dpitch  = W.cols;
       }
     }
     views[tid] = v;
   }
-  if (!(st.flags & 8)) return;
-  constexpr int CH = 16 / static_cast<int>(sizeof(T));  // pixels per 16-byte chunk
-  const bool vec   = (L.cols & 3) == 0;                 // row starts of the peer planes are 16 B aligned
+  if (!windows) return;
   for (int w = 0; w < 2; ++w) {
-    if (st.win_band[w] < 0) continue;
-    const Window<T> W(L, st, group, w);
+    if (dw.band[w] < 0) continue;
+    const Window<T> W(L, st, dw, slot, w);
     const int npx = W.rows * W.cols;
-    if (vec) {
-      const int cpr = W.cols / 4;  // 4-pixel groups per window row
-      for (int i = sgt; i < W.rows * cpr; i += gstride) {
-        const int lr = i / cpr, c = (i - lr * cpr) * 4, wi = lr * W.cols + c;
-        const int64_t gi = static_cast<int64_t>(W.row0 + lr) * L.cols + W.ox + c;
-        uint4 a[kLayerPlanes][4 / CH], b[kLayerPlanes][4 / CH];
-#pragma unroll
-        for (int k = 0; k < kLayerPlanes; ++k) {
-#pragma unroll
-          for (int j = 0; j < 4 / CH; ++j) {
-            a[k][j] = __ldcg(reinterpret_cast<const uint4*>(static_cast<const T*>(L.canvas[W.band][k]) + gi) + j);
-            b[k][j] = __ldcg(reinterpret_cast<const uint4*>(static_cast<const T*>(L.snapshot[W.band][k]) + gi) + j);
-          }
-        }
-        const unsigned dflags =
-          __ldcg(reinterpret_cast<const unsigned*>(L.dirty[W.band] + static_cast<int64_t>(W.row0 + lr) * L.dirty_pitch + W.ox + c));
-#pragma unroll
-        for (int k = 0; k < kLayerPlanes; ++k) {
-#pragma unroll
-          for (int j = 0; j < 4 / CH; ++j) {
-            __stcg(reinterpret_cast<uint4*>(W.can[k] + wi) + j, a[k][j]);
-            __stcg(reinterpret_cast<uint4*>(W.src[k] + wi) + j, b[k][j]);
-          }
-        }
-        __stcg(reinterpret_cast<unsigned*>(W.dirty + wi), dflags);
-        __stcg(reinterpret_cast<unsigned*>(W.touched + wi), 0u);
-      }
-      continue;
-    }
+#pragma unroll 1
     for (int i = sgt; i < npx; i += gstride) {
       const int lr = i / W.cols, c = i - lr * W.cols, px = W.ox + c;
       __stcg(W.touched + i, static_cast<unsigned char>(0));
-      if (px >= L.cols) continue;
+      if (px >= L.cols) {
+        __stcg(W.dirty + i, static_cast<unsigned char>(0));
+        continue;
+      }
       const int64_t gi = static_cast<int64_t>(W.row0 + lr) * L.cols + px;
-      T a[kLayerPlanes], b[kLayerPlanes];
-#pragma unroll
-      for (int k = 0; k < kLayerPlanes; ++k) {
-        a[k] = __ldcg(static_cast<const T*>(L.canvas[W.band][k]) + gi);
-        b[k] = __ldcg(static_cast<const T*>(L.snapshot[W.band][k]) + gi);
-      }
-      const unsigned char dflag = __ldcg(L.dirty[W.band] + static_cast<int64_t>(W.row0 + lr) * L.dirty_pitch + px);
-#pragma unroll
-      for (int k = 0; k < kLayerPlanes; ++k) {
-        __stcg(W.can[k] + i, a[k]);
-        __stcg(W.src[k] + i, b[k]);
-      }
+      const Rec<T> a = ld_rec(static_cast<const T*>(L.canvas[W.band]) + gi * kRecord);
+      const Rec<T> b = ld_rec(static_cast<const T*>(L.snapshot[W.band]) + gi * kRecord);
+      const unsigned char dflag = __ldcg(L.dirty[W.band] + gi);
+      st_rec(W.can + static_cast<int64_t>(i) * kRecord, a);
+      st_rec(W.src + static_cast<int64_t>(i) * kRecord, b);
       __stcg(W.dirty + i, dflag);
     }
   }
 }
 
-// Push back only what this stroke changed: untouched pixels may meanwhile have been refreshed by a commuting stroke's
+// Push back only what this segment changed: untouched pixels may meanwhile have been refreshed by a commuting stroke's
 // snapshot ring on their owner (an idempotent copy this window must not undo).
 template <typename T>
-__device__ __forceinline__ void stage_out(const ImprintLaunch& L, const DevStroke& st, int group, int sgt, int gstride) {
+__device__ __forceinline__ void stage_out(const ImprintLaunch& L, const DevStroke& st, const DevWindow& dw, int slot, int sgt,
+                                          int gstride) {
   for (int w = 0; w < 2; ++w) {
-    if (st.win_band[w] < 0) continue;
-    const Window<T> W(L, st, group, w);
+    if (dw.band[w] < 0) continue;
+    const Window<T> W(L, st, dw, slot, w);
     const int nwords = W.rows * W.cols / 4;  // the touched map is scanned 4 pixels at a time
     const int cpr    = W.cols / 4;
+#pragma unroll 1
     for (int i = sgt; i < nwords; i += gstride) {
       const unsigned t = __ldcg(reinterpret_cast<const unsigned*>(W.touched) + i);
       if (t == 0u) continue;
       const int lr = i / cpr, c = (i - lr * cpr) * 4;
-#pragma unroll
+#pragma unroll 1
       for (int b = 0; b < 4; ++b) {
         if (((t >> (8 * b)) & 0xffu) == 0u) continue;
         const int wi = lr * W.cols + c + b, px = W.ox + c + b;
         const int64_t gi = static_cast<int64_t>(W.row0 + lr) * L.cols + px;
-        T va[kLayerPlanes], vb[kLayerPlanes];
-#pragma unroll
-        for (int k = 0; k < kLayerPlanes; ++k) {
-          va[k] = __ldcg(W.can[k] + wi);
-          vb[k] = __ldcg(W.src[k] + wi);
-        }
-#pragma unroll
-        for (int k = 0; k < kLayerPlanes; ++k) {
-          __stcg(static_cast<T*>(L.canvas[W.band][k]) + gi, va[k]);
-          __stcg(static_cast<T*>(L.snapshot[W.band][k]) + gi, vb[k]);
-        }
-        __stcg(L.dirty[W.band] + static_cast<int64_t>(W.row0 + lr) * L.dirty_pitch + px, __ldcg(W.dirty + wi));
+        const Rec<T> va = ld_rec(W.can + static_cast<int64_t>(wi) * kRecord);
+        const Rec<T> vb = ld_rec(W.src + static_cast<int64_t>(wi) * kRecord);
+        st_rec(static_cast<T*>(L.canvas[W.band]) + gi * kRecord, va);
+        st_rec(static_cast<T*>(L.snapshot[W.band]) + gi * kRecord, vb);
+        __stcg(L.dirty[W.band] + gi, __ldcg(W.dirty + wi));
       }
     }
   }
 }
 
-constexpr int kRegCells = 2;  // cells per thread whose geometry is kept in registers across the stroke
+// 16-byte asynchronous copy global -> shared (no registers held while the data is in flight)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <typename T, bool CL, int MAXB, bool MULTI>
+// SCR: the per-cell state lives in a per-CTA global scratch area instead of shared memory (footprints beyond ~60 000
+// active cells in FP64 mode); everything else is identical.
+template <typename T, bool CL, int MAXB, bool MULTI, bool SCR>
 __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L) {
+  // interactions in flight per thread: 16 registers of records each in FP32 mode, 32 in FP64 mode; as many as fit
+  // without spilling (512-thread CTAs leave 128 registers per thread)
+  constexpr int kInFlight = sizeof(T) == 4 ? (MAXB > 256 ? 3 : 4) : (MAXB > 256 ? 1 : 2);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_stroke;
   __shared__ unsigned long long s_active;
   __shared__ Band<T> s_view[MULTI ? kMaxBands : 1];
+  // Register diet (one CTA of 512 threads leaves 128 registers per thread): everything that is constant over a stroke
+  // or an imprint lives in shared memory and is re-read where it is used — the stroke record, the paint constants, and a
+  // ring of four imprint records (previous, current, next, and the one being prefetched with cp.async).
+  __shared__ DevStroke s_st;
+  __shared__ OpCtx<T> s_ctx;
+  __shared__ DevImprint s_im[4];
   const Band<T>* views = MULTI ? s_view : nullptr;
 
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, bd = blockDim.x;
-  // A stroke is owned by `G` clusters of `csize0` CTAs. Within a cluster the hardware barrier synchronises; across
-  // the clusters of a group a monotonic counter in L2 does (arrive = fence + atomicAdd by one thread per cluster,
-  // wait = acquire-poll), bracketed by two cluster barriers — the classic grid-sync construction at group scope.
-  const int csize0 = CL ? static_cast<int>(cluster.num_blocks()) : 1;
-  const int G      = CL ? L.group : 1;
-  const int cid    = static_cast<int>(blockIdx.x) / csize0;  // cluster index in the grid
-  const int group  = cid / G, grank = cid % G;
-  const int crank  = (CL ? static_cast<int>(cluster.block_rank()) : 0) + grank * csize0;  // CTA rank within the group
-  const int csize  = csize0 * G;
-  const int gstride = csize * bd;
-  const int sgt     = crank * bd + tid;  // contiguous numbering for the coalesced dirty-map scan
-  bool remote   = false;  // current stroke touches rows of another GPU: barriers need system-scope fences
+  const int csize   = CL ? static_cast<int>(cluster.num_blocks()) : 1;
+  const int crank   = CL ? static_cast<int>(cluster.block_rank()) : 0;
+  bool remote   = false;  // current stroke touches rows of another GPU directly: barriers need system-scope fences
   auto sync_all = [&]() {
     if (MULTI && remote) __threadfence_system();
     if (CL) {
       cluster.sync();
-      if (G > 1) {
-        if (cluster.block_rank() == 0 && tid == 0) {
-          __threadfence();
-          const unsigned ticket = atomicAdd(L.group_bar + group, 1u);
-          const unsigned target = (ticket / static_cast<unsigned>(G) + 1u) * static_cast<unsigned>(G);
-          while (static_cast<unsigned>(ld_acquire(reinterpret_cast<const int*>(L.group_bar + group))) < target) {
-          }
-        }
-        cluster.sync();
-      }
     } else {
       __syncthreads();
     }
   };
+  // numbering of the threads of a stroke for coalesced scans: all of them, or only the ring threads (the last
+  // ring_threads threads of every CTA; they own the fewest cells)
+  auto scan_id     = [&]() { return crank * bd + tid; };
+  auto scan_stride = [&]() { return csize * bd; };
+  auto slot_id     = [&]() { return static_cast<int>(blockIdx.x) / csize; };  // stroke slot (cluster index in the grid)
 
-  OpCtx<T> C;
-  C.pickup_rate     = static_cast<T>(L.pickup_rate);
-  C.deposition_rate = static_cast<T>(L.deposition_rate);
-  C.cap             = static_cast<T>(L.capacity);
+  // Per-cell state of this CTA: 7 pickup planes, heights, cell coordinates relative to the map centre; then the
+  // interaction lists (always in shared memory).
+  const int cc = L.cta_cells;
+  unsigned char* cell_base;
+  unsigned char* list_base;
+  if constexpr (SCR) {
+    cell_base = static_cast<unsigned char*>(L.scratch) + static_cast<int64_t>(blockIdx.x) * L.scratch_stride;
+    list_base = smem_raw;
+  } else {
+    cell_base = smem_raw;
+    list_base = smem_raw + static_cast<size_t>(cc) * (8 * sizeof(T) + sizeof(float2));
+  }
+  T* const pick     = reinterpret_cast<T*>(cell_base);
+  T* const fhp      = pick + static_cast<int64_t>(kLayerPlanes) * cc;
+  float2* const uvp = reinterpret_cast<float2*>(fhp + cc);
+  const int ps      = cc;
+  int* const lci          = reinterpret_cast<int*>(list_base);
+  unsigned char* const lk = list_base + static_cast<size_t>(2 * L.chunk_cells) * bd * sizeof(int);
 
   if (tid == 0) s_active = 0ull;
-  unsigned long long my_active = 0;
   const int row_lo = L.store_first, row_hi = L.store_first + L.store_rows - 1;
 
   for (;;) {
@@ -549,20 +474,22 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
     if (crank == 0 && tid == 0) {
       const long long ticket = atomicAdd(L.queue, 1);
       s_stroke = (ticket < L.n_strokes && L.order != nullptr) ? static_cast<long long>(L.order[ticket]) : ticket;
-      if (G > 1) __stcg(L.group_stroke + group, s_stroke);
     }
     sync_all();
-    const int64_t si = G > 1 ? __ldcg(L.group_stroke + group) : (CL ? *cluster.map_shared_rank(&s_stroke, 0) : s_stroke);
+    const int64_t si = CL ? *cluster.map_shared_rank(&s_stroke, 0) : s_stroke;
     if (si >= L.n_strokes) break;
-    const DevStroke st = L.strokes[si];
+    static_assert(sizeof(DevStroke) == 128, "DevStroke is copied in eight 16-byte pieces");
+    if (tid < 8) cp_async16(reinterpret_cast<char*>(&s_st) + 16 * tid, reinterpret_cast<const char*>(L.strokes + si) + 16 * tid);
+    if (tid < 8) cp_async_wait_all();
+    __syncthreads();
+    const DevStroke& st = s_st;
 
     // Dataflow wait. A stroke is cut into SEGMENTS of seg_len imprints; segment k may start once every earlier
     // stroke has finished the segments whose region meets segment k's (host-built lists of (stroke, segments
-    // needed)); strokes publish their progress at segment boundaries. The wait of segment 0 comes first because
-    // the staging windows below snapshot the neighbours' rows (windowed strokes have a single segment).
-    auto seg_wait = [&](int k) {
+    // needed)); strokes publish their progress at segment boundaries. Returns whether there was anything to wait for.
+    auto seg_wait = [&](int k) -> bool {
       const int pb0 = L.seg_off[st.seg_begin + k], pb1 = L.seg_off[st.seg_begin + k + 1];
-      if (pb1 == pb0) return;
+      if (pb1 == pb0) return false;
       if (crank == 0) {
         for (int p = pb0 + tid; p < pb1; p += bd) {
           const int2 pr        = L.preds[p];
@@ -577,6 +504,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
         }
       }
       sync_all();
+      return true;
     };
     auto seg_publish = [&](int done_segments) {  // call after a sync_all: every CTA's stores precede it
       if (crank == 0 && tid == 0) {
@@ -592,143 +520,226 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
     };
     seg_wait(0);
 
+    // imprint records 0 and 1 -> ring slots 0 and 1; paint constants
+    if (tid < 8 && (tid >> 2) < st.n_imprints)
+      cp_async16(reinterpret_cast<char*>(&s_im[tid >> 2]) + 16 * (tid & 3),
+                 reinterpret_cast<const char*>(L.imprints + st.first_imprint + (tid >> 2)) + 16 * (tid & 3));
+    if (tid == 0) {
+      s_ctx.pickup_rate     = static_cast<T>(L.pickup_rate);
+      s_ctx.deposition_rate = static_cast<T>(L.deposition_rate);
+      s_ctx.cap             = static_cast<T>(L.capacity);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      C.paintK[k] = static_cast<T>(st.paintK[k]);
-      C.paintS[k] = static_cast<T>(st.paintS[k]);
+      for (int k = 0; k < 3; ++k) {
+        s_ctx.paintK[k] = static_cast<T>(st.paintK[k]);
+        s_ctx.paintS[k] = static_cast<T>(st.paintS[k]);
+      }
     }
-    remote       = MULTI && (st.flags & 4) != 0;
-    if (MULTI && (st.flags & 12)) stage_in<T>(L, st, s_view, group, sgt, gstride, tid), sync_all();
-    const int nA = st.n_active;
+    remote = MULTI && (st.flags & kStrokeDirect) != 0;
+    const bool two_phase = (st.flags & kStrokeTwoPhase) != 0;
     const int wr = (st.side - 1) / 2;  // == hr (square footprint), FootprintBrush.hxx:75-78
-    const T* fhs = static_cast<const T*>(st.fh);
     // The compacted cell list is cut into csize contiguous chunks (neighbouring cells -> neighbouring lanes ->
-    // neighbouring canvas pixels); cell = cell0 + k*bd of this thread lives in shared-memory slot tid + k*bd.
-    const int per_cta   = (nA + csize - 1) / csize;
-    const int cell_end  = min(nA, (crank + 1) * per_cta);
-    const int cell0     = crank * per_cta + tid;
-    const int my_cells  = cell_end > cell0 ? (cell_end - cell0 + bd - 1) / bd : 0;
-    const int cta_cells = ((per_cta + bd - 1) / bd) * bd;
-    const bool in_smem  = cta_cells <= L.smem_cells;
-    T* pick      = in_smem ? reinterpret_cast<T*>(smem_raw) : static_cast<T*>(L.scratch) + blockIdx.x * L.scratch_stride;
-    const int ps = in_smem ? L.smem_cells : static_cast<int>(L.scratch_stride / kLayerPlanes);
-
-    // per-thread cell geometry in registers; dip() = clean pickup map (:150-166) or continue with the brush's map
-    int cmx[kRegCells], cmy[kRegCells];
-    T cfh[kRegCells];
+    // neighbouring canvas pixels); cell = cell0 + k*bd of this thread lives in slot tid + k*bd.
+    int my_cells;
+    {
+      const int nA       = st.n_active;
+      const int per_cta  = (nA + csize - 1) / csize;
+      const int cell_end = min(nA, (crank + 1) * per_cta);
+      const int cell0    = crank * per_cta + tid;
+      my_cells           = cell_end > cell0 ? (cell_end - cell0 + bd - 1) / bd : 0;
+      const T* fhs       = static_cast<const T*>(st.fh);
+      // dip() = clean pickup map (:150-166), or continue with the brush's map
+      for (int k = 0; k < my_cells; ++k) {
+        const int cell = cell0 + k * bd, slot = tid + k * bd;
+        const uint32_t xy = st.xy[cell];
+        const int mx = static_cast<int>(xy & 0xffffu), my = static_cast<int>(xy >> 16);
+        uvp[slot] = make_float2(static_cast<float>(mx - wr), static_cast<float>(my - wr));
+        fhp[slot] = fhs[cell];
+        if (st.flags & kStrokeLoadPick) {
+          const int64_t mi = static_cast<int64_t>(my) * st.size_map + mx;
 #pragma unroll
-    for (int k = 0; k < kRegCells; ++k) {
-      cmx[k] = cmy[k] = 0;
-      cfh[k]          = static_cast<T>(0);
-    }
-    for (int k = 0; k < my_cells; ++k) {
-      const int cell = cell0 + k * bd, slot = tid + k * bd;
-      const uint32_t xy = st.xy[cell];
-      if (k < kRegCells) {
+          for (int q = 0; q < kLayerPlanes; ++q) pick[q * ps + slot] = static_cast<const T*>(L.pick_dense[q])[mi];
+        } else {
 #pragma unroll
-        for (int q = 0; q < kRegCells; ++q)
-          if (q == k) {
-            cmx[q] = static_cast<int>(xy & 0xffffu);
-            cmy[q] = static_cast<int>(xy >> 16);
-            cfh[q] = fhs[cell];
-          }
-      }
-      if (st.flags & 1) {
-        const int64_t mi = static_cast<int64_t>(xy >> 16) * st.size_map + (xy & 0xffffu);
-#pragma unroll
-        for (int q = 0; q < kLayerPlanes; ++q) pick[q * ps + slot] = static_cast<const T*>(L.pick_dense[q])[mi];
-      } else {
-#pragma unroll
-        for (int q = 0; q < kLayerPlanes; ++q) pick[q * ps + slot] = static_cast<T>(0);
+          for (int q = 0; q < kLayerPlanes; ++q) pick[q * ps + slot] = static_cast<T>(0);
+        }
       }
     }
+    if (tid < 8) cp_async_wait_all();
+    __syncthreads();
+    int my_active = 0;
 
     // The imprint chain, instantiated twice in the multi-GPU kernel: strokes that stay inside the executor's band
     // (the large majority) address it directly like the single-GPU kernel; only straddling strokes pay for the
     // per-band views.
     auto imprint_chain = [&](auto views_tag) {
       constexpr bool VIEWS = decltype(views_tag)::value;
-      DevImprint nxt = st.n_imprints > 0 ? L.imprints[st.first_imprint] : DevImprint{0, 0, 1, 0};
-      int seg_k = 0, seg_next = st.seg_len;  // next segment boundary (imprint index)
-      for (int ii = 0; ii < st.n_imprints; ++ii) {
-        if (ii == seg_next) {
-          ++seg_k;
-          seg_next += st.seg_len;
-          seg_publish(seg_k);
-          seg_wait(seg_k);
-        }
-        const DevImprint im = nxt;
-        if (ii + 1 < st.n_imprints) nxt = L.imprints[st.first_imprint + ii + 1];  // prefetch (hidden behind this imprint)
+      if (st.n_imprints <= 0) return;
+      const DevWindow* wins = (VIEWS && (st.flags & kStrokeWindows)) ? L.windows + st.seg_begin : nullptr;
+      const DevWindow no_window{{-1, -1}, {0, 0}, {0, 0}};
 
-        if (L.use_snapshot) {
-          // updateSnapshot(canvas, centre) (:278-319): refresh the ring allowed-box \ open interior
-          RingGeom g;
-          g.tlx = static_cast<int>(im.cx - wr), g.tly = static_cast<int>(im.cy - wr);
-          g.brx = static_cast<int>(im.cx + wr), g.bry = static_cast<int>(im.cy + wr);
-          g.ax0 = max(static_cast<int>(im.cx - wr - st.radius), 0);
-          g.ay0 = max(max(static_cast<int>(im.cy - wr - st.radius), 0), VIEWS ? 0 : row_lo);
-          g.ax1 = min(static_cast<int>(im.cx + wr + st.radius), L.cols - 1);
-          g.ay1 = min(min(static_cast<int>(im.cy + wr + st.radius), L.rows - 1), VIEWS ? L.rows - 1 : row_hi);
-          ring_scan<T, VIEWS>(L, views, g, sgt, gstride);
-        }
-        // left/top overhang: canvas pixels of column/row 0 can be hit twice (B#11) -> ordered phases
-        const bool border = (im.cx - wr < 0.0) || (im.cy - wr < 0.0);
-        const float fc = static_cast<float>(im.c), fs = static_cast<float>(im.s);
-        sync_all();
-
-        const int n_phase = border ? 4 : 1;
-        for (int ph = 0; ph < n_phase; ++ph) {
-          // CPP cells per pass: all loads of up to 2*CPP interactions are in flight before any is computed
-          constexpr int CPP = MAXB <= 256 ? 2 : 1;
-          for (int k = 0; k < my_cells; k += CPP) {
-            int mx[CPP], my[CPP], slot[CPP];
-            T fh[CPP];
-            bool have[CPP];
-  #pragma unroll
-            for (int q = 0; q < CPP; ++q) {
-              have[q] = k + q < my_cells;
-              slot[q] = tid + (k + q) * bd;
-              if (k + q < kRegCells) {
-                mx[q] = cmx[(k + q) & 1], my[q] = cmy[(k + q) & 1], fh[q] = cfh[(k + q) & 1];
-              } else if (have[q]) {
-                const int cell    = cell0 + (k + q) * bd;
-                const uint32_t xy = st.xy[cell];
-                mx[q] = static_cast<int>(xy & 0xffffu), my[q] = static_cast<int>(xy >> 16), fh[q] = fhs[cell];
-              } else {
-                mx[q] = my[q] = 0, fh[q] = static_cast<T>(0);
+      // Interactions (cell, pixel) of `chunk` of this thread's cells for imprint ii, border phase ph (-1 = all).
+      auto build_list = [&](int ii, int chunk, int ph) -> int {
+        const DevImprint& im = s_im[ii & 3];
+        const float fc = im.fc, fs = im.fs, lo = 0.5f - st.eps, hi = 0.5f + st.eps;
+        const int ix = im.ix, iy = im.iy, flags = im.flags;
+        int n        = 0;
+        const int k0 = chunk * L.chunk_cells, k1 = min(my_cells, k0 + L.chunk_cells);
+        for (int k = k0; k < k1; ++k) {
+          const float2 uv = uvp[tid + k * bd];
+          PixelHits h;
+          if (two_phase) {
+            h.n = -1;
+          } else {
+            hits_fast(fc, fs, ix, iy, flags, uv.x, uv.y, lo, hi, L.rows, L.cols, ph, h);
+          }
+          if (h.n < 0) {  // a candidate within the float error of a rounding boundary: the reference's f64 expression
+            const int3 e = hits_exact_cold(L.imprints, st.first_imprint + ii, wr, static_cast<int>(uv.x) + wr,
+                                           static_cast<int>(uv.y) + wr, L.rows, L.cols, ph);
+            h.n = e.x;
+            h.px[0] = e.y & 0xffff, h.py[0] = e.y >> 16;
+            h.px[1] = e.z & 0xffff, h.py[1] = e.z >> 16;
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (j < h.n) {
+              const int py = h.py[j], px = h.px[j];
+              int band = 0, lrow = py - row_lo, pitch = L.cols;
+              bool ok = true;
+              if (VIEWS) {
+                band  = band_of(L, py);  // the row's owner GPU
+                lrow  = py - band * L.rows_per_band;
+                pitch = views[band].pitch;
+              } else if (py < row_lo || py > row_hi) {
+                ok = false;  // band canvas without peers: rows outside the stored window are not ours
               }
-            }
-            Hits h[CPP];
-            OpData<T> d[CPP][2];
-  #pragma unroll
-            for (int q = 0; q < CPP; ++q) {
-              h[q].n = 0;
-              if (have[q]) h[q] = find_hits<T, VIEWS>(L, views, im, fc, fs, wr, mx[q], my[q], border, ph, row_lo, row_hi);
-  #pragma unroll
-              for (int j = 0; j < 2; ++j)
-                if (j < h[q].n) op_load(band_view<T, VIEWS>(L, views, h[q].band[j]), h[q].ci[j], d[q][j]);
-            }
-  #pragma unroll
-            for (int q = 0; q < CPP; ++q) {
-  #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                if (j < h[q].n) {
-                  const Band<T> B = band_view<T, VIEWS>(L, views, h[q].band[j]);
-                  op_finish(C, B, h[q].ci[j], fh[q], d[q][j], pick, ps, slot[q]);
-                  if (B.dirty) __stcg(B.dirty + h[q].dof[j], static_cast<unsigned char>(1));
-                  if (VIEWS && B.touched) __stcg(B.touched + h[q].dof[j], static_cast<unsigned char>(1));
-                  ++my_active;
-                }
+              if (ok) {
+                lci[n * bd + tid] = lrow * pitch + px;
+                lk[n * bd + tid]  = static_cast<unsigned char>((k - k0) | (band << 4));
+                ++n;
               }
             }
           }
+        }
+        return n;
+      };
+      // pickup + deposit of the listed interactions, kInFlight at a time (all record loads of the group in flight
+      // before any compute). Interactions of one cell are adjacent in the list and finish in list order.
+      auto process = [&](int n, int chunk) {
+        const int k0 = chunk * L.chunk_cells;
+#pragma unroll 1
+        for (int j = 0; j < n; j += kInFlight) {
+          int ci[kInFlight];
+          unsigned e[kInFlight];
+          OpData<T> d[kInFlight];
+#pragma unroll
+          for (int q = 0; q < kInFlight; ++q) {
+            ci[q] = 0, e[q] = 0u;
+            if (j + q < n) {
+              ci[q] = lci[(j + q) * bd + tid];
+              e[q]  = lk[(j + q) * bd + tid];
+              op_load(band_view<T, VIEWS>(L, views, static_cast<int>(e[q] >> 4)), ci[q], d[q]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < kInFlight; ++q) {
+            if (j + q < n) {
+              const Band<T> B = band_view<T, VIEWS>(L, views, static_cast<int>(e[q] >> 4));
+              const int slot  = tid + (k0 + static_cast<int>(e[q] & 15u)) * bd;
+              op_finish(s_ctx, B, ci[q], fhp[slot], d[q], pick, ps, slot);
+              if (B.dirty) __stcg(B.dirty + ci[q], static_cast<unsigned char>(1));
+              if (VIEWS && B.touched) __stcg(B.touched + ci[q], static_cast<unsigned char>(1));
+              ++my_active;
+            }
+          }
+        }
+      };
+      auto first_phase = [&](int ii) { return (s_im[ii & 3].flags & kImBorder) ? 0 : -1; };
+      auto geom_of     = [&](int ii) {
+        const DevImprint& im = s_im[ii & 3];
+        return ring_geom(im.cx, im.cy, wr, st.radius, L.cols, VIEWS ? 0 : row_lo, VIEWS ? L.rows - 1 : row_hi);
+      };
+
+      if (VIEWS) {
+        stage_in<T>(L, st, wins ? wins[0] : no_window, s_view, slot_id(), scan_id(), scan_stride(), tid);
+        sync_all();
+      }
+      // The chain is a flat loop over UNITS (imprint ii, border phase ph, cell chunk): process the unit's list, build
+      // the list of the next unit (geometry only, so the one that starts the next imprint is built before the barrier),
+      // and synchronise whenever the next unit starts a new phase or imprint. One build site, one process site.
+      const int chunks = max((my_cells + L.chunk_cells - 1) / L.chunk_cells, 1);
+      int ii = 0, ph = first_phase(0), chunk = 0;
+      int n_list = build_list(0, 0, ph);
+      bool need_full = true, imprint_start = true;
+      int seg_k = 0, seg_next = st.seg_len;  // next segment boundary (imprint index)
+      for (;;) {
+        if (imprint_start) {
+          if (ii == seg_next) {
+            ++seg_k;
+            seg_next += st.seg_len;
+            if (wins) {  // push the pixels the finished segment touched back into their owners' HBM
+              stage_out<T>(L, st, wins[seg_k - 1], slot_id(), scan_id(), scan_stride());
+              __threadfence_system();
+              sync_all();
+            }
+            seg_publish(seg_k);
+            if (seg_wait(seg_k)) need_full = true;
+            if (wins) {
+              stage_in<T>(L, st, wins[seg_k], s_view, slot_id(), scan_id(), scan_stride(), tid);
+              sync_all();
+              n_list    = build_list(ii, 0, ph);  // the views (window pitch) may have changed
+              need_full = true;
+            }
+          }
+          // imprint record ii + 2 -> ring slot (ii + 2) & 3 (nobody reads that slot during this imprint); completed
+          // before this imprint's barrier
+          if (tid < 4 && ii + 2 < st.n_imprints)
+            cp_async16(reinterpret_cast<char*>(&s_im[(ii + 2) & 3]) + 16 * tid,
+                       reinterpret_cast<const char*>(L.imprints + st.first_imprint + ii + 2) + 16 * tid);
+          if (L.use_snapshot) {
+            const int rt_local = tid - (bd - L.ring_threads);
+            if (two_phase || need_full) {
+              ring_scan<T, VIEWS>(L, views, geom_of(ii), nullptr, scan_id(), scan_stride());
+            } else if (rt_local >= 0) {
+              const RingGeom prev = geom_of(ii - 1);
+              ring_scan<T, VIEWS>(L, views, geom_of(ii), &prev, crank * L.ring_threads + rt_local, csize * L.ring_threads);
+            }
+            need_full = false;
+            if (two_phase) sync_all();
+          }
+          imprint_start = false;
+        }
+        process(n_list, chunk);
+        // next unit; left/top overhang: canvas pixels of column/row 0 can be hit twice (B#11) -> 4 ordered phases
+        bool barrier = false, done = false;
+        if (chunk + 1 < chunks) {
+          ++chunk;
+        } else {
+          chunk   = 0;
+          barrier = true;
+          if (ph >= 0 && ph < 3) {
+            ++ph;
+          } else if (ii + 1 < st.n_imprints) {
+            ++ii;
+            ph            = first_phase(ii);
+            imprint_start = true;
+          } else {
+            done = true;
+          }
+        }
+        if (!done) n_list = build_list(ii, chunk, ph);
+        if (barrier) {
+          if (tid < 4) cp_async_wait_all();
           sync_all();
         }
+        if (done) break;
       }
-
+      if (wins) {
+        stage_out<T>(L, st, wins[seg_k], slot_id(), scan_id(), scan_stride());
+        __threadfence_system();
+      }
     };
     if constexpr (MULTI) {
-      if (st.flags & 12) {
+      if (st.flags & (kStrokeDirect | kStrokeWindows)) {
         imprint_chain(std::true_type{});
       } else {
         imprint_chain(std::false_type{});
@@ -737,25 +748,23 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
       imprint_chain(std::false_type{});
     }
 
-    if (st.flags & 2) {
+    if (st.flags & kStrokeStorePick) {
       for (int k = 0; k < my_cells; ++k) {
-        const int cell = cell0 + k * bd, slot = tid + k * bd;
-        const uint32_t xy = st.xy[cell];
-        const int64_t mi  = static_cast<int64_t>(xy >> 16) * st.size_map + (xy & 0xffffu);
+        const int slot   = tid + k * bd;
+        const float2 uv  = uvp[slot];
+        const int64_t mi = static_cast<int64_t>(static_cast<int>(uv.y) + wr) * st.size_map + (static_cast<int>(uv.x) + wr);
 #pragma unroll
         for (int q = 0; q < kLayerPlanes; ++q) static_cast<T*>(L.pick_dense[q])[mi] = pick[q * ps + slot];
       }
     }
-    sync_all();
-    if (MULTI && (st.flags & 8)) {  // push the touched window pixels back into their owners' HBM
-      stage_out<T>(L, st, group, sgt, gstride);
-      __threadfence_system();
-      sync_all();
+    {  // active stroke-pixels of this stroke: one shared-memory atomic per warp
+      const int warp_sum = __reduce_add_sync(0xffffffffu, my_active);
+      if ((tid & 31) == 0 && warp_sum) atomicAdd(&s_active, static_cast<unsigned long long>(warp_sum));
     }
+    sync_all();
     seg_publish(kStrokeDone);
   }
 
-  if (my_active) atomicAdd(&s_active, my_active);
   __syncthreads();
   if (tid == 0 && s_active) atomicAdd(L.counters, s_active);
   if (CL) cluster.sync();  // rank 0's shared memory must outlive the last remote read of s_stroke
@@ -790,83 +799,91 @@ __global__ void __launch_bounds__(256) count_visited_kernel(const DevStroke* str
   if (threadIdx.x == 0 && s_sum) atomicAdd(counter, s_sum);
 }
 
-// variants by maximum block size: smaller CTAs get a larger register budget (no spills on the critical path).
-// A 1024-thread variant (64 registers, ~1.5 KB of spill traffic per thread) was measured and is slower: 24.3 vs
-// 21.1 us per imprint at r = 129, 8.71 vs 8.14 s on the 10k-stroke workload. So is a 384-thread variant with two
-// cells in flight per thread (168 registers): 23.1 us at r = 129, 18.5 vs 16.6 us at r = 112 — for the large
-// footprints more resident warps beat more independent work per thread.
+// variants by maximum block size: smaller CTAs get a larger register budget. The scratch variant only exists for the
+// shape very large footprints use (clusters of 512-thread CTAs).
 template <typename T, bool CL, bool MULTI>
-const void* kernel_ptr_b(int block) {
-  if (block <= 256) return reinterpret_cast<const void*>(imprint_kernel<T, CL, 256, MULTI>);
-  return reinterpret_cast<const void*>(imprint_kernel<T, CL, 512, MULTI>);
+const void* kernel_ptr_b(int block, bool scr) {
+  if constexpr (CL) {
+    if (scr) return reinterpret_cast<const void*>(imprint_kernel<T, true, 512, MULTI, true>);
+  }
+  if (block <= 256) return reinterpret_cast<const void*>(imprint_kernel<T, CL, 256, MULTI, false>);
+  return reinterpret_cast<const void*>(imprint_kernel<T, CL, 512, MULTI, false>);
 }
 template <typename T>
-const void* kernel_ptr_t(bool cl, int block, bool multi) {
-  if (multi) return cl ? kernel_ptr_b<T, true, true>(block) : kernel_ptr_b<T, false, true>(block);
-  return cl ? kernel_ptr_b<T, true, false>(block) : kernel_ptr_b<T, false, false>(block);
+const void* kernel_ptr_t(bool cl, int block, bool multi, bool scr) {
+  if (multi) return cl ? kernel_ptr_b<T, true, true>(block, scr) : kernel_ptr_b<T, false, true>(block, scr);
+  return cl ? kernel_ptr_b<T, true, false>(block, scr) : kernel_ptr_b<T, false, false>(block, scr);
 }
-const void* kernel_ptr(int precision, bool cl, int block, bool multi) {
-  return precision == PB_F64 ? kernel_ptr_t<double>(cl, block, multi) : kernel_ptr_t<float>(cl, block, multi);
+const void* kernel_ptr(int precision, bool cl, int block, bool multi, bool scr) {
+  return precision == PB_F64 ? kernel_ptr_t<double>(cl, block, multi, scr) : kernel_ptr_t<float>(cl, block, multi, scr);
+}
+
+int env_int(const char* name, int fallback) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : fallback;
 }
 
 }  // namespace
 
-// A stroke is latency bound (a chain of dependent imprints), so it is spread thin: CTAs of 128..1024 threads on
-// up to 16 SMs (non-portable cluster size), about one active cell per thread.
+// A stroke is latency bound (a chain of dependent imprints), so it is spread thin: CTAs of 128..512 threads on
+// up to 16 SMs (non-portable cluster size).
 // Launch classes (a run of consecutive strokes of one class shares a launch):
 //   1  : tiny footprints (<= 256 active cells), one CTA per stroke
-//   16 : cluster of 16 CTAs x 128 threads (<= 4096 cells, <= 2 per thread)
-//   17 : cluster of 16 CTAs x 256 or 512 threads for the large footprints
+//   16 : cluster x 128 threads (<= 4096 cells)
+//   17 : cluster x 256 or 512 threads for the large footprints
 int imprint_cluster_class(int n_active) { return n_active <= 256 ? 1 : (n_active <= 4096 ? 16 : 17); }
 
+int imprint_slots(const ImprintLaunch& L) { return std::max(1, L.grid / std::max(1, L.cluster)); }
+
 void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& smem_bytes) {
-  const int cls     = imprint_cluster_class(max_active);
-  const int cluster = cls == 1 ? 1 : 16;
-  // Large footprints are bound by the per-SM L2 sector rate of their scattered SoA accesses. PB_IMPRINT_GROUP=G lets
-  // G clusters (G x 16 SMs) cooperate on one stroke (1.8x faster per stroke at G = 4), but on the sbr workload the
-  // cluster slots are worth more as concurrent strokes (measured: 2.31 s vs 2.50 s per 2000 strokes), so G = 1.
-  const char* genv = std::getenv("PB_IMPRINT_GROUP");
-  int group        = (cls == 17 && genv) ? std::min(8, std::max(1, std::atoi(genv))) : 1;
-  // <= 256 threads per CTA: that kernel variant keeps two cells' interactions (56 loads) in flight without
-  // spills; without groups the largest footprints (> 2 cells per thread at 256) trade that for twice the warps.
+  const int cls = imprint_cluster_class(max_active);
+  // experiment knobs (sweeps in scratch/): cluster size and block size per class
+  const int cluster = cls == 1 ? 1 : std::min(16, std::max(1, env_int(cls == 16 ? "PB_IMPRINT_CLUSTER16" : "PB_IMPRINT_CLUSTER17", 16)));
   int block = 128;
-  if (cluster == 1) {
+  if (cls == 1) {
     block = max_active <= 128 ? 128 : 256;
-  } else if (group > 1) {
-    block = max_active <= group * 16 * 128 * 2 ? 128 : 256;
+  } else if (cls == 16) {
+    block = env_int("PB_IMPRINT_BLOCK16", 128);
   } else {
-    block = max_active <= 4096 ? 128 : (max_active <= 8192 ? 256 : 512);
+    block = env_int("PB_IMPRINT_BLOCK17", max_active <= 8192 ? 256 : 512);
   }
+  block               = std::min(512, std::max(32, block / 32 * 32));
   const size_t es     = ctx->esize();
-  const int per_cta   = (std::max(max_active, 1) + cluster * group - 1) / (cluster * group);
-  const int cta_cells = (per_cta + block - 1) / block * block;
-  const size_t budget = 200 * 1024;  // dynamic shared memory for this CTA's slice of the pickup map
-  size_t need         = static_cast<size_t>(cta_cells) * kLayerPlanes * es;
-  if (need <= budget) {
-    L.smem_cells     = cta_cells;
+  const int per_cta   = (std::max(max_active, 1) + cluster - 1) / cluster;
+  const int cpt       = (per_cta + block - 1) / block;  // cells per thread
+  const int cta_cells = cpt * block;
+  const int chunk     = std::min(cpt, 8);
+  const size_t list_bytes = (static_cast<size_t>(2 * chunk) * block * 5 + 15) / 16 * 16;
+  const size_t cell_bytes = static_cast<size_t>(cta_cells) * (8 * es + sizeof(float2));
+  const size_t budget     = 220 * 1024;  // dynamic shared memory
+  if (cell_bytes + list_bytes <= budget) {
+    L.cells_in_smem  = 1;
     L.scratch_stride = 0;
-  } else {  // only reachable for footprints beyond ~59k active cells (radius > 200): global scratch
-    L.smem_cells     = 0;
-    need             = 0;
-    L.scratch_stride = static_cast<int64_t>(cta_cells) * kLayerPlanes;
+    smem_bytes       = cell_bytes + list_bytes;
+  } else {  // only reachable for very large footprints (radius > 200 in FP64 mode): cell state in global scratch
+    L.cells_in_smem  = 0;
+    L.scratch_stride = static_cast<int64_t>((cell_bytes + 255) / 256 * 256);
+    smem_bytes       = list_bytes;
   }
-  smem_bytes = need;
-  L.block    = block;
-  L.cluster  = cluster;
-  L.group    = group;
+  L.cta_cells    = cta_cells;
+  L.chunk_cells  = chunk;
+  L.ring_threads = std::min(block, 64);
+  L.block        = block;
+  L.cluster      = cluster;
   // occupancy queries and attribute changes cost milliseconds: do them once per launch shape
   static std::mutex cache_mutex;  // contexts of different devices may plan from different host threads
   std::lock_guard<std::mutex> lock(cache_mutex);
   static std::map<std::tuple<int, int, int, int, size_t>, int> cache;
   const bool multi = L.n_bands > 1;
-  const auto key   = std::make_tuple(ctx->device, ctx->precision * 2 + (multi ? 1 : 0), cluster * 100 + group, block, smem_bytes);
+  const auto key   = std::make_tuple(ctx->device, ctx->precision * 2 + (multi ? 1 : 0), cluster, block, smem_bytes);
   auto it        = cache.find(key);
   if (it != cache.end()) {
     L.grid = it->second;
     return;
   }
-  const void* fn = kernel_ptr(ctx->precision, cluster > 1, block, multi);
-  PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PB_REQUIRE(L.cells_in_smem || (cluster > 1 && block == 512), "footprint too large for this launch shape");
+  const void* fn = kernel_ptr(ctx->precision, cluster > 1, block, multi, !L.cells_in_smem);
+  PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget)));
   if (cluster > 8) PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   if (cluster == 1) {
     int per_sm = 0;
@@ -887,15 +904,15 @@ void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& sme
     cfg.numAttrs             = 1;
     int n_clusters           = 0;
     PB_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, fn, &cfg));
-    PB_REQUIRE(n_clusters >= group, "imprint kernel: the cooperating clusters of one stroke do not fit on the device");
-    L.grid = (n_clusters / group) * group * cluster;
+    PB_REQUIRE(n_clusters >= 1, "imprint kernel: no thread-block cluster of this shape fits on the device");
+    L.grid = n_clusters * cluster;
   }
   cache[key] = L.grid;
 }
 
 void imprint_launch(pb_context* ctx, const ImprintLaunch& L, size_t smem_bytes) {
   if (L.n_strokes <= 0) return;
-  const void* fn = kernel_ptr(ctx->precision, L.cluster > 1, L.block, L.n_bands > 1);
+  const void* fn = kernel_ptr(ctx->precision, L.cluster > 1, L.block, L.n_bands > 1, !L.cells_in_smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim            = dim3(static_cast<unsigned>(L.grid));
   cfg.blockDim           = dim3(static_cast<unsigned>(L.block));

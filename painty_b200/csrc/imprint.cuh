@@ -1,6 +1,7 @@
 // Device-side interface of the footprint-brush imprint engine (imprint.cu).
 #pragma once
 #include "common.cuh"
+#include "imprint_geom.hpp"
 
 namespace pb {
 
@@ -11,18 +12,27 @@ struct FootprintGeom {
   int size_map = 0;  // ceil(sqrt(2)*width)
   int side     = 0;  // width + 2*pad (footprint rows == cols)
   int n_active = 0;
+  // max over the active cells of |(|u| + 0.5, |v| + 0.5)|, (u, v) = cell - map centre: no pixel farther than this from
+  // the imprint centre can map to an active cell. compact = it is <= wr - 2, i.e. every pixel an imprint touches lies in
+  // the open interior of its footprint box, disjoint from the snapshot ring of the same imprint.
+  double reach = 0.0;
+  bool compact = false;
   uint32_t* d_xy = nullptr;  // device
   void* d_fh     = nullptr;  // device, context element type
-};
-
-struct DevImprint {  // per-imprint constants, computed on the host in f64 (FootprintBrush.hxx:95-96)
-  double cx, cy, c, s;  // c = cos(-theta), s = sin(-theta)
 };
 
 constexpr int kMaxBands = 8;  // GPUs of one NVSwitch node
 constexpr int kStrokeDone = 0x7fffffff;  // progress value of a finished stroke
 
-struct DevStroke {
+// DevStroke::flags
+constexpr int kStrokeLoadPick  = 1;   // load the pickup state from the brush's dense map (continue without dip)
+constexpr int kStrokeStorePick = 2;   // store it back after the stroke
+constexpr int kStrokeDirect    = 4;   // rows of another GPU are accessed directly through NVLink (system-scope fences)
+constexpr int kStrokeWindows   = 8;   // they are staged in local windows, one set per dataflow segment
+constexpr int kStrokeTwoPhase  = 16;  // footprint is not compact: ring pass and main pass are separated by a barrier,
+                                      // every ring pass scans the whole ring, hits are decided in f64 only
+
+struct alignas(16) DevStroke {
   int64_t first_imprint;
   int32_t n_imprints;
   int32_t n_active;
@@ -31,34 +41,38 @@ struct DevStroke {
   int32_t size_map, side;
   double radius;  // FootprintBrush::_radius as used by updateSnapshot (:298-305)
   double paintK[3], paintS[3];
-  int32_t seg_begin;             // first entry of this stroke in seg_off[] (one entry per segment, + 1)
-  int32_t seg_len;               // imprints per dataflow segment (>= 1)
-  int32_t flags;                 // bit0: load pick state from the dense map, bit1: store it back,
-                                 // bit2: rows of another GPU are accessed directly through NVLink (system-scope
-                                 //       fences at every barrier), bit3: they are staged in local windows instead
-  int32_t pad;
-  // Multi-GPU staging windows: the part of the stroke's region that lies in a neighbour's band is pulled into local
-  // scratch before the stroke and the touched pixels are pushed back afterwards (one bulk NVLink transfer each way
-  // instead of remote round trips on every imprint). Window w covers band-local rows [row0, row0+rows) and canvas
-  // columns [win_ox, win_ox + win_cols) of band win_band[w]; win_band[w] < 0 = unused.
-  int32_t win_band[2], win_row0[2], win_rows[2];
-  int32_t win_ox, win_cols;  // multiples of 4 (the dirty map is scanned in 32-bit words)
+  int32_t seg_begin;  // first entry of this stroke in seg_off[] / windows[] (one entry per segment)
+  int32_t seg_len;    // imprints per dataflow segment (>= 1)
+  int32_t flags;      // kStroke*
+  float eps;          // half width of the undecided band of the single-precision hit test (imprint_geom.hpp)
+  int32_t win_ox, win_cols;  // staging windows: canvas columns [win_ox, win_ox + win_cols), multiples of 4
+  int32_t pad[2];            // 128 bytes: the kernel copies the record into shared memory in 16-byte pieces
+};
+static_assert(sizeof(DevStroke) == 128, "DevStroke layout");
+
+// Multi-GPU staging windows of one dataflow segment: the part of the segment's region that lies in a neighbour's band is
+// pulled into local scratch when the segment starts and the touched pixels are pushed back when it ends (one bulk NVLink
+// transfer each way instead of remote round trips on every imprint). Window w covers band-local rows
+// [row0, row0 + rows) of band[w]; band[w] < 0 = unused.
+struct DevWindow {
+  int32_t band[2], row0[2], rows[2];
 };
 
 struct ImprintLaunch {
-  // Canvas / snapshot / dirty planes per row band. Single GPU: one band (n_bands = 1) holding the rows
+  // The engine works on pixel RECORDS (8 elements per pixel: Kr Kg Kb Sr Sg Sb V 0 — 32 bytes in FP32 mode, one
+  // 256-bit access and one L2 sector per pixel): a record copy of the canvas' wet layer (converted from / to the SoA
+  // planes around a batch) and the snapshot buffer, per row band. Single GPU: one band (n_bands = 1) holding the rows
   // [store_first, store_first + store_rows). Multi GPU (n_bands > 1): band b holds the rows
   // [b*rows_per_band, min((b+1)*rows_per_band, rows)) and lives in GPU b's HBM; the pointers of the other bands are
   // peer mappings (CUDA IPC) reached through NVLink.
-  void* canvas[kMaxBands][kLayerPlanes];
-  void* snapshot[kMaxBands][kLayerPlanes];  // == canvas planes when the snapshot buffer is disabled
-  unsigned char* dirty[kMaxBands];          // 1 byte per pixel: snapshot(p) may differ from canvas(p)
+  void* canvas[kMaxBands];          // canvas records
+  void* snapshot[kMaxBands];        // snapshot records; == canvas when the snapshot buffer is disabled
+  unsigned char* dirty[kMaxBands];  // 1 byte per pixel (flat, same index as the records): snapshot may differ from canvas
   // the executor's own band once more (== index my_band above): strokes that stay inside it use these fields
-  void* own_canvas[kLayerPlanes];
-  void* own_snapshot[kLayerPlanes];
+  void* own_canvas;
+  void* own_snapshot;
   unsigned char* own_dirty;
   int n_bands, rows_per_band, my_band;
-  int dirty_pitch;
   int use_snapshot;
   int rows, cols;               // logical canvas size (bounds checks)
   int store_first, store_rows;  // stored row window (single band only)
@@ -74,31 +88,34 @@ struct ImprintLaunch {
   // stroke = flag index (single GPU) or (rank << 27) | flag index on that rank (multi GPU).
   const int2* preds;
   const int32_t* seg_off;
+  const DevWindow* windows;      // per segment (multi GPU, strokes with kStrokeWindows); may be null otherwise
   long long* done[kMaxBands];    // per-rank progress words ([my_band] is local): (epoch << 32) | segments completed
   int epoch;
   int flag_offset;               // flag index of this launch's stroke 0 (strokes of earlier launches come first)
   int* queue;                    // single counter (zeroed): tickets
   const int32_t* order;          // ticket -> stroke of this launch (host-planned claim order); nullptr = identity
   unsigned long long* counters;  // [0] active stroke-pixels
-  unsigned char* win_scratch;  // staging windows, win_stride bytes per stroke slot (two halves, one per window)
+  unsigned char* win_scratch;    // staging windows, win_stride bytes per stroke slot (two halves, one per window)
   int64_t win_stride;
-  // per-CTA pick scratch in global memory for footprints that do not fit shared memory
+  // per-CTA cell state in global memory for footprints that do not fit shared memory
   void* scratch;
-  int64_t scratch_stride;  // elements per CTA
-  int smem_cells;          // cells per CTA that fit in dynamic shared memory
+  int64_t scratch_stride;  // bytes per CTA
+  int cta_cells;           // cell slots per CTA (a multiple of block)
+  int cells_in_smem;       // 1: pickup state, heights and cell coordinates live in dynamic shared memory
+  int chunk_cells;         // cells per thread whose interactions are listed at a time (list capacity 2 * chunk_cells)
+  int ring_threads;        // threads per CTA (the last ones) that run the incremental snapshot-ring pass
   int block;               // threads per CTA
   int cluster;             // CTAs per thread-block cluster
-  int group;               // clusters cooperating on one stroke (software barrier on top of the hardware one)
-  unsigned* group_bar;     // per group: monotonic arrival counter of the inter-cluster barrier (zeroed)
-  long long* group_stroke; // per group: stroke index popped by the group leader
   int grid;                // CTAs (multiple of cluster)
 };
 
 // Launch shape for a run of strokes whose largest footprint has max_active cells: a stroke is owned by a
-// thread-block cluster of `cluster` CTAs x `block` threads (~2 active cells per thread).
+// thread-block cluster of `cluster` CTAs x `block` threads.
 void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& smem_bytes);
 int imprint_cluster_class(int n_active);
 void imprint_launch(pb_context* ctx, const ImprintLaunch& L, size_t smem_bytes);
+// concurrent strokes of a launch shape (resident clusters), for the host's claim-order model
+int imprint_slots(const ImprintLaunch& L);
 
 // visited stroke-pixel count (the reference's `counter`, FootprintBrush.hxx:119): one pass over all
 // (2hr+1)(2wr+1) cells of every imprint, both bounds checks evaluated exactly in f64.

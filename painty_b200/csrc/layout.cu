@@ -2,11 +2,16 @@
 // The reference hands images over as cv::Mat_<Eigen::Vector3d> (24 B/px AoS f64) and cv::Mat_<double>
 // (painty/image/Mat.hxx:40-41); on the device they live as dense SoA planes of float or double.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
 namespace pb {
 namespace {
+
+struct PlanePtrs7 {
+  void* p[kLayerPlanes];
+};
 
 constexpr int64_t kChunkPx = int64_t(1) << 23;  // 8 Mpx per staging chunk (192 MB for a vec3 image)
 
@@ -35,6 +40,43 @@ __global__ void soa_to_aos_kernel(double* __restrict__ dst, const T* __restrict_
     dst[i * CH] = static_cast<double>(s0[i]);
     if (CH > 1) dst[i * CH + 1] = static_cast<double>(s1[i]);
     if (CH > 2) dst[i * CH + 2] = static_cast<double>(s2[i]);
+  }
+}
+
+// Pixel RECORDS of the imprint engine: 8 elements per pixel (Kr Kg Kb Sr Sg Sb V 0), 32 bytes in FP32 mode — one
+// 256-bit load / store and one L2 sector per pixel, where the SoA planes cost 7 scattered accesses (imprint.cu).
+// The converters move a rectangle [y0, y1] x [x0, x1] of the stored planes (pitch = cols) to / from the record array.
+template <typename T>
+__global__ void planes_to_records_kernel(PlanePtrs7 src, T* __restrict__ rec, int cols, int x0, int y0, int w, int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / w;
+    const int64_t f = (y0 + r) * cols + x0 + (i - r * w);
+    T v[8];
+#pragma unroll
+    for (int k = 0; k < kLayerPlanes; ++k) v[k] = static_cast<const T*>(src.p[k])[f];
+    v[7] = static_cast<T>(0);
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    V* out = reinterpret_cast<V*>(rec + f * 8);
+    const V* in = reinterpret_cast<const V*>(v);
+#pragma unroll
+    for (int q = 0; q < static_cast<int>(8 * sizeof(T) / sizeof(V)); ++q) out[q] = in[q];
+  }
+}
+template <typename T>
+__global__ void records_to_planes_kernel(PlanePtrs7 dst, const T* __restrict__ rec, int cols, int x0, int y0, int w, int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / w;
+    const int64_t f = (y0 + r) * cols + x0 + (i - r * w);
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    T v[8];
+    V* tmp = reinterpret_cast<V*>(v);
+    const V* in = reinterpret_cast<const V*>(rec + f * 8);
+#pragma unroll
+    for (int q = 0; q < static_cast<int>(8 * sizeof(T) / sizeof(V)); ++q) tmp[q] = in[q];
+#pragma unroll
+    for (int k = 0; k < kLayerPlanes; ++k) static_cast<T*>(dst.p[k])[f] = v[k];
   }
 }
 
@@ -151,6 +193,34 @@ void download_aos(pb_context* ctx, const pb_planes& pl, int p0, int ch, double* 
     download_t<double>(ctx, pl, p0, ch, host);
   else
     download_t<float>(ctx, pl, p0, ch, host);
+}
+
+void planes_to_records(pb_context* ctx, const pb_planes& pl, void* records, int x0, int y0, int x1, int y1) {
+  if (x1 < x0 || y1 < y0) return;
+  PlanePtrs7 pp;
+  for (int k = 0; k < kLayerPlanes; ++k) pp.p[k] = pl.plane(k);
+  const int w = x1 - x0 + 1;
+  const int64_t n = static_cast<int64_t>(w) * (y1 - y0 + 1);
+  if (ctx->precision == PB_F64)
+    planes_to_records_kernel<double><<<grid_for(ctx, n), 256, 0, ctx->stream>>>(pp, static_cast<double*>(records), pl.cols, x0, y0, w, n);
+  else
+    planes_to_records_kernel<float><<<grid_for(ctx, n), 256, 0, ctx->stream>>>(pp, static_cast<float*>(records), pl.cols, x0, y0, w, n);
+  PB_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+void records_to_planes(pb_context* ctx, const void* records, const pb_planes& pl, int x0, int y0, int x1, int y1) {
+  if (x1 < x0 || y1 < y0) return;
+  PlanePtrs7 pp;
+  for (int k = 0; k < kLayerPlanes; ++k) pp.p[k] = pl.plane(k);
+  const int w = x1 - x0 + 1;
+  const int64_t n = static_cast<int64_t>(w) * (y1 - y0 + 1);
+  if (ctx->precision == PB_F64)
+    records_to_planes_kernel<double><<<grid_for(ctx, n), 256, 0, ctx->stream>>>(pp, static_cast<const double*>(records), pl.cols, x0, y0, w, n);
+  else
+    records_to_planes_kernel<float><<<grid_for(ctx, n), 256, 0, ctx->stream>>>(pp, static_cast<const float*>(records), pl.cols, x0, y0, w, n);
+  PB_CUDA(cudaGetLastError());
+  ctx->launches++;
 }
 
 void copy_planes(pb_context* ctx, const pb_planes& src, pb_planes& dst, int nplanes) {

@@ -1,7 +1,7 @@
 """torch.distributed glue for one canvas sharded into row bands over the GPUs of a node (one process per GPU).
 
-Plumbing only: it creates this rank's band canvas, exchanges CUDA IPC handles of the canvas / snapshot / dirty-map /
-flag allocations with `all_gather_object`, maps the peers' memory (NVLink) and fills the `pb_dist_desc` that
+Plumbing only: it creates this rank's band canvas, exchanges CUDA IPC handles of the brush's canvas-record / snapshot /
+dirty-map / flag allocations with `all_gather_object`, maps the peers' memory (NVLink) and fills the `pb_dist_desc` that
 `pb_fbrush_stroke_batch_dist` consumes. The rendering itself is the C ABI / CUDA library.
 """
 import ctypes as C
@@ -53,21 +53,18 @@ class DistCanvas:
     def attach(self, brush):
         """Exchange the peer mappings for this (canvas, brush) pair. Collective: every rank must call it."""
         lib = api.lib()
-        cbase, cstride = _VP(), C.c_int64()
-        api._chk(lib.pb_canvas_storage(self.canvas.h, C.byref(cbase), C.byref(cstride)))
-        sbase, sstride, dbase, fbase = _VP(), C.c_int64(), _VP(), _VP()
-        api._chk(lib.pb_fbrush_dist_storage(brush.h, self.canvas.h, C.byref(sbase), C.byref(sstride), C.byref(dbase), C.byref(fbase)))
-        mine = dict(canvas=self._export(cbase.value), cstride=cstride.value, snapshot=self._export(sbase.value), sstride=sstride.value,
-                    dirty=self._export(dbase.value), flags=self._export(fbase.value))
+        wbase, sbase, dbase, fbase = _VP(), _VP(), _VP(), _VP()
+        api._chk(lib.pb_fbrush_dist_storage(brush.h, self.canvas.h, C.byref(wbase), C.byref(sbase), C.byref(dbase), C.byref(fbase)))
+        mine = dict(canvas=self._export(wbase.value), snapshot=self._export(sbase.value), dirty=self._export(dbase.value),
+                    flags=self._export(fbase.value))
         everyone = [None] * self.world
         self.dist.all_gather_object(everyone, mine)
         d = pb_dist_desc()
         d.world, d.rank, d.rows_per_band = self.world, self.rank, self.rpb
-        own = dict(canvas=cbase.value, snapshot=sbase.value, dirty=dbase.value, flags=fbase.value)
+        own = dict(canvas=wbase.value, snapshot=sbase.value, dirty=dbase.value, flags=fbase.value)
         for r, e in enumerate(everyone):
             for key, arr in (("canvas", d.canvas_base), ("snapshot", d.snapshot_base), ("dirty", d.dirty_base), ("flags", d.flags_base)):
                 arr[r] = own[key] if r == self.rank else self._import(e[key])
-            d.canvas_stride[r], d.snapshot_stride[r] = e["cstride"], e["sstride"]
         self._desc[id(brush)] = d
         self.dist.barrier()
         return d
@@ -77,12 +74,14 @@ class DistCanvas:
         d = self._desc.get(id(brush)) or self.attach(brush)
         strokes = np.ascontiguousarray(strokes, dtype=api.STROKE_DTYPE)
         cx, cy, theta = api._f64(cx), api._f64(cy), api._f64(theta)
-        self.ctx.synchronize()
-        self.dist.barrier()  # every band is ready (cleared / snapshot taken) before any kernel touches peer rows
-        api._chk(api.lib().pb_fbrush_stroke_batch_dist(brush.h, self.canvas.h, C.byref(d), C.c_int64(len(strokes)),
-                                                        strokes.ctypes.data_as(_VP), C.c_int64(len(cx)), api._p(cx), api._p(cy), api._p(theta)))
+        lib = api.lib()
+        api._chk(lib.pb_fbrush_dist_begin(brush.h, self.canvas.h))  # planes -> records of this band (synchronises the stream)
+        self.dist.barrier()  # every band is ready (cleared / snapshot taken / converted) before any kernel touches peer rows
+        api._chk(lib.pb_fbrush_stroke_batch_dist(brush.h, self.canvas.h, C.byref(d), C.c_int64(len(strokes)),
+                                                 strokes.ctypes.data_as(_VP), C.c_int64(len(cx)), api._p(cx), api._p(cy), api._p(theta)))
         self.ctx.synchronize()
         self.dist.barrier()  # all GPUs have finished writing into each other's bands
+        api._chk(lib.pb_fbrush_dist_end(brush.h, self.canvas.h))  # records -> planes
 
     def close(self):
         self.ctx.synchronize()

@@ -10,7 +10,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rows = bench.ROWS * world
-rec, cx, cy, th, radii = bench.build_workload(n_per * world, rows=rows)
+_, rec, cx, cy, th, radii = bench.build_workload(n_per * world, rows=rows)
 if mode == "confined":
     keep = []
     rpb = (rows + world - 1) // world

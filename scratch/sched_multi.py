@@ -6,7 +6,7 @@ import bench
 from painty_b200 import assets, api
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 n = 10000 * world; rows, cols = 2160 * world, 3840; rpb = 2160
-rec, cx, cy, th, radii = bench.build_workload(n, rows=rows)
+_, rec, cx, cy, th, radii = bench.build_workload(n, rows=rows)
 R = rec["radius"].astype(float); M = rec["n_imprints"].astype(np.int64); F = rec["first_imprint"].astype(np.int64)
 geo = {}
 def g(r):

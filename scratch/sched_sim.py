@@ -5,7 +5,7 @@ from painty_b200 import assets
 n = int(sys.argv[1]) if len(sys.argv)>1 else 10000
 world = int(sys.argv[2]) if len(sys.argv)>2 else 1
 rows, cols, tile = 2160*world, 3840, 64
-rec, cx, cy, th, radii = bench.build_workload(n, rows=rows)
+_, rec, cx, cy, th, radii = bench.build_workload(n, rows=rows)
 tx, ty = (cols+tile-1)//tile, (rows+tile-1)//tile
 last = -np.ones((ty,tx), dtype=np.int64); ring = [[[] for _ in range(tx)] for _ in range(ty)]
 def tmodel(r): return np.interp(r, [11,30,64,112,151,200], [5.3,6.0,10,16,27,45])*1e-6

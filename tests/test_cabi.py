@@ -306,62 +306,163 @@ def test_null_handles_are_errors_not_crashes(built_lib):
         assert getattr(lib, name)(null) == 0, name
 
 
-def test_ring_word_enumeration_matches_the_reference_ring(built_lib):
-    """The snapshot ring pass reads the dirty map in 4-pixel words. The device enumerates only the words that hold a
-    ring pixel candidate: every word of the allowed rows outside the footprint box rows, and on box rows the words not
-    completely inside the open interior (FootprintBrush.hxx:298-316: allowed box minus open interior). The same code
-    runs here on the host (pb_ring_words) against a brute-force enumeration, for random and degenerate geometries."""
+def _ring_items(lib, box, allowed, prev=None, pitch=240):
+    import ctypes as C
+
+    b, a = (C.c_int32 * 4)(*box), (C.c_int32 * 4)(*allowed)
+    pb = pa = None
+    if prev is not None:
+        pb, pa = (C.c_int32 * 4)(*prev[0]), (C.c_int32 * 4)(*prev[1])
+    n = C.c_int64(0)
+    dummy = (C.c_int32 * 1)()
+    assert lib.pb_ring_rects(b, a, pb, pa, pitch, C.c_int64(0), dummy, dummy, C.byref(n)) == 0
+    rows = (C.c_int32 * max(n.value, 1))()
+    words = (C.c_int32 * max(n.value, 1))()
+    assert lib.pb_ring_rects(b, a, pb, pa, pitch, C.c_int64(n.value), rows, words, C.byref(n)) == 0
+    return list(zip(rows[:n.value], words[:n.value]))
+
+
+def _ring_pixels(box, allowed):
+    """FootprintBrush.hxx:298-316: allowed box minus open interior, as a set of (row, col)."""
+    tlx, tly, brx, bry = box
+    ax0, ay0, ax1, ay1 = allowed
+    return {(row, col) for row in range(ay0, ay1 + 1) for col in range(ax0, ax1 + 1)
+            if not (tly < row < bry and tlx < col < brx)}
+
+
+def _covered(items, pitch):
+    """Pixels (row, col) of the item's own row that the 4 bytes of each flat dirty-map word cover."""
+    out = set()
+    for row, w in items:
+        for b in range(4):
+            col = 4 * w + b - row * pitch
+            if 0 <= col < pitch:
+                out.add((row, col))
+    return out
+
+
+def _geom(cx, cy, wr, rad, rows, cols):
+    box = (int(cx - wr), int(cy - wr), int(cx + wr), int(cy + wr))
+    allowed = (max(int(cx - wr - rad), 0), max(int(cy - wr - rad), 0), min(int(cx + wr + rad), cols - 1), min(int(cy + wr + rad), rows - 1))
+    return box, allowed
+
+
+def test_ring_enumeration_covers_the_reference_ring(built_lib):
+    """The snapshot ring pass reads the flat dirty map in aligned 4-pixel words, rectangle by rectangle
+    (imprint_geom.hpp: ring_rects). Full pass: the words must cover every pixel of the reference's ring (allowed box minus
+    open interior) and stay inside the allowed rows; only a thin margin of interior pixels may be read. The same code
+    the device runs is evaluated here on the host (pb_ring_rects), for random and degenerate geometries and for canvas
+    widths that are not a multiple of 4 (rows then start at any word alignment)."""
+    from painty_b200 import api
+
+    lib = api.lib()
+    rng = np.random.default_rng(3)
+    cases = []
+    for _ in range(200):
+        rows, cols = 180, int(rng.choice([240, 241, 243, 250]))
+        cases.append(_geom(rng.uniform(-60, 260), rng.uniform(-60, 200), int(rng.integers(0, 40)), int(rng.integers(0, 40)), rows, cols) + (cols,))
+    cases += [((5, 5, 5, 5), (0, 0, 20, 20), 240), ((5, 5, 6, 6), (3, 3, 9, 9), 240), ((0, 0, 100, 100), (10, 10, 50, 50), 240),
+              ((10, 10, 50, 50), (10, 10, 50, 50), 240), ((-30, -30, 10, 10), (0, 0, 40, 40), 240), ((10, 10, 20, 20), (30, 30, 20, 20), 240)]
+    total = interior_read = 0
+    for box, allowed, pitch in cases:
+        items = _ring_items(lib, box, allowed, None, pitch)
+        assert len(items) - len(set(items)) <= 2 * (box[3] - box[1] + 1) + 4  # only left/right words of narrow interiors repeat
+        want = _ring_pixels(box, allowed)
+        got = _covered(items, pitch)
+        assert want <= got, (box, allowed, pitch)
+        assert all(allowed[1] <= row <= allowed[3] for row, _ in items)
+        total += len(items)
+        interior_read += len(got - want)
+    assert total > 10000 and interior_read < 12 * total  # <= a few bytes per word outside the ring
+
+
+def test_incremental_ring_covers_what_entered_the_ring(built_lib):
+    """Incremental pass: given the previous imprint's geometry the words must cover ring(now) minus ring(previous) — the
+    only pixels that can be dirty when the previous pass left its ring clean and the previous imprint touched nothing
+    outside its open interior — for small steps, large jumps and jumps beyond the whole box."""
+    from painty_b200 import api
+
+    lib = api.lib()
+    rng = np.random.default_rng(5)
+    rows, cols = 200, 260
+    total_full = total_inc = 0
+    for it in range(250):
+        wr, rad = int(rng.integers(1, 30)), int(rng.integers(0, 30))
+        cx, cy = rng.uniform(-40, cols + 40), rng.uniform(-40, rows + 40)
+        step = [1.5, 1.5, 6.0, 40.0, 400.0][it % 5]
+        nx, ny = cx + rng.uniform(-step, step), cy + rng.uniform(-step, step)
+        prev, now = _geom(cx, cy, wr, rad, rows, cols), _geom(nx, ny, wr, rad, rows, cols)
+        items = _ring_items(lib, now[0], now[1], prev, cols)
+        want = _ring_pixels(*now) - _ring_pixels(*prev)
+        got = _covered(items, cols)
+        assert want <= got, (prev, now)
+        assert all(now[1][1] <= row <= now[1][3] for row, _ in items)
+        total_inc += len(items)
+        total_full += len(_ring_items(lib, now[0], now[1], None, cols))
+    assert total_inc < total_full  # and it is cheaper than rescanning everything
+
+
+def _forward_hits(cx, cy, theta, wr, rows, cols):
+    """Brute-force restatement of the reference's loop (FootprintBrush.hxx:88-114): every (row, col) of the footprint box
+    -> (canvas pixel, map cell), in row-major order. Returns {cell: [(px, py), ...]}."""
+    c, s = math.cos(-theta), math.sin(-theta)
+    r = np.arange(-wr, wr + 1)
+    row, col = np.meshgrid(r, r, indexing="ij")
+    rc = col * c - row * s
+    rr = col * s + row * c
+    half_away = lambda x: np.sign(x) * np.floor(np.abs(x) + 0.5)  # std::round
+    mx, my = half_away(rc + wr).astype(np.int64), half_away(rr + wr).astype(np.int64)
+    px, py = np.trunc(col + cx).astype(np.int64), np.trunc(row + cy).astype(np.int64)
+    ok = (py >= 0) & (px >= 0) & (px < cols) & (py < rows)
+    out = {}
+    for a, b, x, y in zip(mx[ok], my[ok], px[ok], py[ok]):
+        out.setdefault((int(a), int(b)), []).append((int(x), int(y)))
+    return out
+
+
+def test_hit_finder_matches_the_forward_mapping(built_lib):
+    """The imprint kernel inverts the reference's pixel -> cell mapping: per cell, the <= 2 canvas pixels whose rotated and
+    rounded position is that cell. Both device paths are evaluated on the host (pb_imprint_hits): the exact f64 test must
+    reproduce the brute-force forward mapping for every cell, and the single-precision test must either agree or defer
+    (n = -1) — never decide differently — over random centres and angles, exact diagonals and integer centres."""
     import ctypes as C
 
     from painty_b200 import api
 
     lib = api.lib()
-    rng = np.random.default_rng(3)
-
-    def device_words(box, allowed):
-        b = (C.c_int32 * 4)(*box)
-        a = (C.c_int32 * 4)(*allowed)
-        n = C.c_int64(0)
-        dummy = (C.c_int32 * 1)()
-        assert lib.pb_ring_words(b, a, C.c_int64(0), dummy, dummy, C.byref(n)) == 0
-        rows = (C.c_int32 * max(n.value, 1))()
-        words = (C.c_int32 * max(n.value, 1))()
-        assert lib.pb_ring_words(b, a, C.c_int64(n.value), rows, words, C.byref(n)) == 0
-        return list(zip(rows[:n.value], words[:n.value]))
-
-    def expected_words(box, allowed):
-        tlx, tly, brx, bry = box
-        ax0, ay0, ax1, ay1 = allowed
-        out = []
-        if ax1 < ax0 or ay1 < ay0:
-            return out
-        for row in range(ay0, ay1 + 1):
-            for wi in range(ax0 >> 2, (ax1 >> 2) + 1):
-                inside = tly < row < bry and all(tlx < col < brx for col in range(4 * wi, 4 * wi + 4))
-                if not inside:
-                    out.append((row, wi))
-        return out
-
-    cases = []
-    for _ in range(300):
-        wr = int(rng.integers(0, 40))
-        rad = int(rng.integers(0, 40))
-        cx, cy = int(rng.integers(-60, 260)), int(rng.integers(-60, 200))
-        rows, cols = 180, 240
-        box = (cx - wr, cy - wr, cx + wr, cy + wr)
-        allowed = (max(cx - wr - rad, 0), max(cy - wr - rad, 0), min(cx + wr + rad, cols - 1), min(cy + wr + rad, rows - 1))
-        cases.append((box, allowed))
-    cases += [((5, 5, 5, 5), (0, 0, 20, 20)), ((5, 5, 6, 6), (3, 3, 9, 9)), ((0, 0, 100, 100), (10, 10, 50, 50)),
-              ((10, 10, 50, 50), (10, 10, 50, 50)), ((-30, -30, 10, 10), (0, 0, 40, 40)), ((10, 10, 20, 20), (30, 30, 20, 20))]
-    total = skipped = 0
-    for box, allowed in cases:
-        got, want = device_words(box, allowed), expected_words(box, allowed)
-        assert len(got) == len(set(got)), (box, allowed)  # every word once
-        assert set(got) == set(want), (box, allowed)
-        total += len(got)
-        if allowed[2] >= allowed[0] and allowed[3] >= allowed[1]:
-            skipped += ((allowed[2] >> 2) - (allowed[0] >> 2) + 1) * (allowed[3] - allowed[1] + 1) - len(got)
-    assert total > 10000 and skipped > 10000  # the interior really is left out
+    rng = np.random.default_rng(11)
+    I32 = C.POINTER(C.c_int32)
+    cases = [(rng.uniform(-30, 330), rng.uniform(-30, 250), rng.uniform(-np.pi, np.pi), int(rng.choice([8, 21, 45, 91]))) for _ in range(24)]
+    cases += [(100.0, 80.0, 0.0, 21), (100.5, 80.5, np.pi / 2, 21), (100.0, 80.0, np.pi / 4, 45), (-3.25, -7.75, 0.3, 21),
+              (12.0, 9.0, -np.pi / 4, 21), (100.25, 80.0, np.pi, 21), (299.999999, 219.0000001, 1.1, 21)]
+    deferred = decided = 0
+    for cx, cy, theta, wr in cases:
+        rows, cols = 220, 300
+        side = 2 * wr + 1
+        my, mx = [a.ravel().astype(np.int32) for a in np.meshgrid(np.arange(side), np.arange(side), indexing="ij")]
+        keep = np.hypot(np.abs(mx - wr) + 0.5, np.abs(my - wr) + 0.5) <= wr - 2  # the cells a compact footprint can hold
+        mx, my = np.ascontiguousarray(mx[keep]), np.ascontiguousarray(my[keep])
+        n = len(mx)
+        want = _forward_hits(cx, cy, theta, wr, rows, cols)
+        res = {}
+        for mode in (0, 1):
+            nh, px, py = np.zeros(n, np.int32), np.zeros(2 * n, np.int32), np.zeros(2 * n, np.int32)
+            eps = 1e-6 * wr + 2e-5
+            assert lib.pb_imprint_hits(C.c_double(cx), C.c_double(cy), C.c_double(theta), wr, rows, cols, C.c_int64(n),
+                                       mx.ctypes.data_as(I32), my.ctypes.data_as(I32), mode, C.c_double(eps), -1,
+                                       nh.ctypes.data_as(I32), px.ctypes.data_as(I32), py.ctypes.data_as(I32)) == 0
+            res[mode] = (nh, px.reshape(n, 2), py.reshape(n, 2))
+        for i in range(n):
+            w = want.get((int(mx[i]), int(my[i])), [])
+            nh, px, py = res[0]
+            assert [(int(px[i, j]), int(py[i, j])) for j in range(nh[i])] == w, ("exact", cx, cy, theta, wr, mx[i], my[i])
+            nh, px, py = res[1]
+            if nh[i] < 0:
+                deferred += 1
+            else:
+                decided += 1
+                assert [(int(px[i, j]), int(py[i, j])) for j in range(nh[i])] == w, ("fast", cx, cy, theta, wr, mx[i], my[i])
+    assert decided > 50 * max(deferred, 1) or deferred < 0.03 * decided  # the fast path decides almost everything
 
 
 def _emulate_queues(n, seg_first, seg_off, ps, pn, order, pool, run, slots, rng):

@@ -308,7 +308,7 @@ def test_fp32_mode_tracks_fp64_mode_on_the_4k_workload(built_lib):
     import bench
     from painty_b200 import api
 
-    rec, cx, cy, th, radii = bench.build_workload(600)
+    _, rec, cx, cy, th, radii = bench.build_workload(600)
     out = []
     for prec in (api.F32, api.F64):
         ctx = api.Context(0, prec)
