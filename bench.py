@@ -500,6 +500,7 @@ def main():
             ex = info["expanded"][i]  # the oracle's own expansion must equal the library's, bit for bit
             assert np.array_equal(ex[0], px_[-1]) and np.array_equal(ex[1], py_[-1]) and np.array_equal(ex[2], pt_[-1])
         cv.clear()
+        br.updateSnapshot(cv)  # the CPU sample starts with a fresh brush: its first imprint copies the whole canvas (:281-284)
         br.stroke_batch(cv, prec, np.concatenate(px_), np.concatenate(py_), np.concatenate(pt_))
         got = cv.compose()
         wet = cv.download("V")["V"] > 0

@@ -163,6 +163,15 @@ int pb_canvas_compose_band_device(pb_canvas* c, void* d_out, int64_t plane_strid
  *     out = rows*cols*3 uint8 / uint16 (host). srgb = 0 skips the sRGB conversion (convertTo_sRGB = false). */
 int pb_canvas_compose_qrgb32(pb_canvas* c, uint32_t* out);
 int pb_canvas_compose_bgr(pb_canvas* c, int bits, int srgb, void* out);
+/* The sbr planner's canvas read-back prep on the device (painty/sbr/src/PictureTargetSbrPainter.cxx:334-341):
+ * ScaledMat(convertColor(getLinearRgbImage(), rgb_2_CIELab), out_rows, out_cols) = compose -> ColorConverter::rgb2lab
+ * (core/Color.hxx:248-252, D65) -> cv::resize(INTER_LANCZOS4) (image/Mat.hxx:141-147) evaluated like OpenCV does for a
+ * CV_64FC3 image (separable 8-tap passes, float weights, double sums). out = out_rows*out_cols*3 doubles (host AoS).
+ * Only the down-scaled Lab image crosses PCIe. Full canvases only. */
+int pb_canvas_compose_lab_scaled(pb_canvas* c, int out_rows, int out_cols, double* out);
+/* Test hook (host only): the tap offsets (dst entries: first source index + 3) and weights (dst*8 floats) of one axis of
+ * that resize. */
+int pb_lanczos4_taps(int src, int dst, int32_t* offsets, float* weights);
 /* Renderer::render(canvas) (renderer/Renderer.hxx:60-156): compose + directional-light relighting (Beckmann /
  * Cook-Torrance, the wet layer's thickness as height field, 5-tap BORDER_REFLECT normal) fused in one kernel; host
  * AoS f64 out, clamped to [0,1] like the reference. Full canvases only (the stencil needs the neighbouring rows). */
@@ -281,6 +290,14 @@ int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* 
 /* thickness map: rows*cols host f64 (BrushStrokeSample::getThicknessMap). */
 int pb_tbrush_create(pb_context* ctx, int map_rows, int map_cols, const double* thickness_map, pb_tbrush** out);
 int pb_tbrush_destroy(pb_tbrush* b);
+/* Brush-texture atlas. The sbr renderer picks a thickness texture per stroke from data/textures
+ * (renderer/src/TextureBrushDictionary.cxx:25-69; gray, min-max normalised by the loader, :71-79); on the CPU path that is
+ * BrushStrokeSample::setThicknessMap (renderer/BrushStrokeSample.hxx:25) before paintStroke. Textures live in HBM next to
+ * the constructor's sample map (id 0); pb_tbrush_add_texture returns ids 1, 2, ... in call order. A batch names the
+ * texture per stroke (pb_tstroke.texture_id); pb_tbrush_paint_stroke uses the one chosen with pb_tbrush_select_texture. */
+int pb_tbrush_add_texture(pb_tbrush* b, int map_rows, int map_cols, const double* thickness_map, int* texture_id);
+int pb_tbrush_select_texture(pb_tbrush* b, int texture_id);
+int pb_tbrush_texture_count(const pb_tbrush* b);
 int pb_tbrush_set_radius(pb_tbrush* b, double radius); /* TextureBrush.hxx:33-41 */
 int pb_tbrush_dip(pb_tbrush* b, const double K[3], const double S[3]);
 int pb_tbrush_set_thickness_scale(pb_tbrush* b, double scale); /* BrushBase.hxx:24-30 */
@@ -297,11 +314,32 @@ typedef struct pb_tstroke {
   double thickness_scale;
   int64_t first_vertex; /* into path_xy (pairs) */
   int32_t n_vertices;
-  int32_t reserved;
+  int32_t texture_id; /* thickness texture of this stroke: 0 = the constructor's sample map, k = pb_tbrush_add_texture's id */
 } pb_tstroke;
 int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const pb_tstroke* strokes, int64_t n_vertices,
                            const double* path_xy);
 int pb_tbrush_counters(pb_tbrush* b, uint64_t* pixels);
+
+
+/* ---- TextureBrushDictionary (host only) --------------------------------------------------------------- */
+/* renderer/src/TextureBrushDictionary.cxx: the textures of data/textures are named <size>_<lengthClass>_<nn>.png and
+ * grouped by (size key, length key), both ascending (:103-118); per size group the average texture height
+ * (_avgSizes, :120-137) and per (size, length) group the average texture width (_avgTexLength, :139-164) are kept.
+ * pb_texdict_create takes, per texture, its two file-name keys and its rows / cols; entry i of the dictionary is texture
+ * i of the caller (e.g. pb_tbrush_add_texture id i + 1). */
+typedef struct pb_texdict pb_texdict;
+int pb_texdict_create(int n, const int32_t* size_key, const int32_t* length_key, const int32_t* rows, const int32_t* cols,
+                      pb_texdict** out);
+int pb_texdict_destroy(pb_texdict* d);
+/* TextureBrushDictionary::lookup (:25-69) up to the random draw: stroke length = polyline length of path (n*2 doubles),
+ * size group = nearest average height to brush_size, length group = nearest average width to the stroke length — with the
+ * reference's quirks kept (the running minima start at _avgSizes[0] / _avgTexLength[i0][0] as VALUES, not distances, and
+ * the defaults are i0 = 0, i1 = 1; the length loop runs over the number of SIZE groups, clamped here to the group's own
+ * length classes where the reference would index out of range). Writes the group indices and up to `capacity` candidate
+ * entries; *n_candidates receives their number (an empty group fails like the reference's runtime_error). The reference
+ * then draws one candidate with std::random_device (:61-66) — the caller draws and records the pick in its stroke list. */
+int pb_texdict_lookup(const pb_texdict* d, int n, const double* path_xy, double brush_size, int32_t* size_group,
+                      int32_t* length_group, int capacity, int32_t* candidates, int32_t* n_candidates);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,9 @@ Run in the build container (where /root/reference exists):  python oracle/bake_a
 Writes tests/golden/assets/painty_assets.npz with the raw integer pixel data of
   * data/footprint/footprint.png      (1024x1024 gray u8; FootprintBrush.hxx:49)
   * data/sample_0/thickness_map.png   (171x800 gray u16; BrushStrokeSample.cxx:164)
+  * data/textures/*.png               (236 brush textures, gray u16 whose two bytes are equal -> stored as u8;
+                                       renderer/src/TextureBrushDictionary.cxx:81-118) -> painty_textures.npz
+  * data/canvas_patterns/0.png        (2048x2048 RGB u8; renderer/src/CanvasGpu.cxx:27-40) -> painty_textures.npz
 and the three JSON palettes (mixer/src/Serialization.cxx:26-53 format [{"K":[3],"S":[3]}]) as
 f64 arrays. No reference *source* is copied; these are the data files the hot path consumes.
 Linearisation (Color.hxx:189-195) and LANCZOS4 resizing are done at load time by
@@ -32,6 +35,16 @@ def main():
         pal[name.replace("-", "_") + "_S"] = np.array([p["S"] for p in j], dtype=np.float64)
     np.savez_compressed(os.path.join(OUT, "painty_assets.npz"), footprint_u8=fp, thickness_u16=tm, **pal)
     print("wrote", os.path.join(OUT, "painty_assets.npz"), os.path.getsize(os.path.join(OUT, "painty_assets.npz")), "bytes")
+    tex = {}
+    for name in sorted(os.listdir(f"{REF}/textures")):
+        g = cv2.imread(f"{REF}/textures/{name}", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_GRAYSCALE)
+        assert g.dtype == np.uint16 and ((g >> 8) == (g & 0xFF)).all()  # v * 257: the u8 high byte restores the u16 exactly
+        tex["tex_" + name[:-4]] = (g >> 8).astype(np.uint8)
+    pat = cv2.cvtColor(cv2.imread(f"{REF}/canvas_patterns/0.png", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+    assert pat.dtype == np.uint8 and pat.shape == (2048, 2048, 3)
+    path = os.path.join(OUT, "painty_textures.npz")
+    np.savez_compressed(path, canvas_pattern_u8=pat, **tex)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(tex), "textures")
 
 
 if __name__ == "__main__":

@@ -137,6 +137,24 @@ class Cpu:
         self.fn("qrgb32", None, [C.c_int64, _PD, C.c_void_p])(out.size, _p(rgb), out.ctypes.data_as(C.c_void_p))
         return out
 
+    def rgb2lab(self, rgb):
+        """linear RGB [.., 3] f64 -> CIELab (D65) like convertColor(rgb_2_CIELab) (Color.hxx:248-252)."""
+        rgb = _f64(rgb)
+        out = np.empty_like(rgb)
+        self.fn("rgb2lab", None, [C.c_int64, _PD, _PD])(rgb.size // 3, _p(rgb), _p(out))
+        return out
+
+    def lab_scaled(self, rgb, rows, cols):
+        """The planner's read-back prep (PictureTargetSbrPainter.cxx:334-341): ScaledMat(convertColor(rgb, rgb_2_CIELab),
+        rows, cols) — the colour conversion by this checker, cv::resize(INTER_LANCZOS4) by the container's cv2 (OpenCV is
+        the reference's own resize; the three channels are resized independently)."""
+        import cv2
+
+        lab = self.rgb2lab(rgb)
+        if lab.shape[:2] == (rows, cols):
+            return lab
+        return np.ascontiguousarray(cv2.resize(lab, (cols, rows), interpolation=cv2.INTER_LANCZOS4))
+
     def bgr(self, rgb, bits=8, srgb=True):
         """io::imSave's pixel path (port only: cv::Mat::convertTo is restated, OpenCV is not available)."""
         rgb = _f64(rgb)

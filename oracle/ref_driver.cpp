@@ -249,6 +249,17 @@ void ref_qrgb32(int64_t n, const double* rgb, uint32_t* out) {
   }
 }
 
+// The planner's read-back prep, colour part: convertColor(rgb, rgb_2_CIELab) = ColorConverter<double>::rgb2lab per pixel
+// (painty/sbr/src/PictureTargetSbrPainter.cxx:338-340, painty/core/Color.hxx:248-252); AoS f64 in and out.
+void ref_rgb2lab(int64_t n, const double* rgb, double* lab) {
+  painty::ColorConverter<double> converter;
+  for (int64_t i = 0; i < n; ++i) {
+    vec3 v(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]), o;
+    converter.rgb2lab(v, o);
+    for (size_t c = 0; c < 3; ++c) lab[3 * i + static_cast<int64_t>(c)] = o[c];
+  }
+}
+
 // ---- Canvas -------------------------------------------------------------------------------------
 void* ref_canvas_create(int rows, int cols) {
   auto* c = new Canvas(rows, cols);

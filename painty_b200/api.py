@@ -31,12 +31,12 @@ class pb_stroke(C.Structure):
 
 class pb_tstroke(C.Structure):
     _fields_ = [("radius", C.c_double), ("K", C.c_double * 3), ("S", C.c_double * 3), ("thickness_scale", C.c_double),
-                ("first_vertex", C.c_int64), ("n_vertices", C.c_int32), ("reserved", C.c_int32)]
+                ("first_vertex", C.c_int64), ("n_vertices", C.c_int32), ("texture_id", C.c_int32)]
 
 
 STROKE_DTYPE = np.dtype([("radius", "<f8"), ("K", "<f8", 3), ("S", "<f8", 3), ("first_imprint", "<i8"), ("n_imprints", "<i8")])
 TSTROKE_DTYPE = np.dtype([("radius", "<f8"), ("K", "<f8", 3), ("S", "<f8", 3), ("thickness_scale", "<f8"),
-                          ("first_vertex", "<i8"), ("n_vertices", "<i4"), ("reserved", "<i4")])
+                          ("first_vertex", "<i8"), ("n_vertices", "<i4"), ("texture_id", "<i4")])
 assert STROKE_DTYPE.itemsize == C.sizeof(pb_stroke) and TSTROKE_DTYPE.itemsize == C.sizeof(pb_tstroke)
 
 _lib = None
@@ -302,6 +302,12 @@ class Canvas:
         assert R0.shape == (self.store_rows, self.cols, 3)
         _chk(lib().pb_canvas_set_background(self.h, _p(R0)))
 
+    def compose_lab_scaled(self, rows, cols):
+        """The sbr planner's read-back prep on the device: compose -> CIELab -> LANCZOS4 resize to rows x cols (host AoS f64)."""
+        out = np.empty((rows, cols, 3))
+        _chk(lib().pb_canvas_compose_lab_scaled(self.h, int(rows), int(cols), _p(out)))
+        return out
+
     def dryCanvas(self):
         _chk(lib().pb_canvas_dry(self.h))
 
@@ -477,6 +483,40 @@ class FootprintBrush:
         return {k: float(v) for k, v in zip(keys, out)}
 
 
+def lanczos4_taps(src, dst):
+    """(offsets[dst], weights[dst, 8]) of one axis of cv::resize(INTER_LANCZOS4) as the library evaluates it (host only)."""
+    ofs = np.zeros(dst, dtype=np.int32)
+    w = np.zeros((dst, 8), dtype=np.float32)
+    _chk(lib().pb_lanczos4_taps(int(src), int(dst), ofs.ctypes.data_as(_VP), w.ctypes.data_as(_VP)))
+    return ofs, w
+
+
+class TextureBrushDictionary:
+    """Host-side painty::TextureBrushDictionary (renderer/src/TextureBrushDictionary.cxx): groups of brush textures by
+    (size key, length key) and the lookup rule up to the random draw, which the caller makes and records."""
+
+    def __init__(self, size_keys, length_keys, rows, cols):
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        sk, lk, r, c = i32(size_keys), i32(length_keys), i32(rows), i32(cols)
+        self.h = _VP()
+        _chk(lib().pb_texdict_create(len(sk), sk.ctypes.data_as(_VP), lk.ctypes.data_as(_VP), r.ctypes.data_as(_VP),
+                                     c.ctypes.data_as(_VP), C.byref(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib().pb_texdict_destroy(self.h)
+            self.h = None
+
+    def lookup(self, path, brush_size):
+        """-> (size group, length group, candidate entry indices)."""
+        path = _f64(path).reshape(-1, 2)
+        i0, i1, n = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        cand = np.zeros(256, dtype=np.int32)
+        _chk(lib().pb_texdict_lookup(self.h, len(path), _p(path), C.c_double(brush_size), C.byref(i0), C.byref(i1), len(cand),
+                                     cand.ctypes.data_as(_VP), C.byref(n)))
+        return i0.value, i1.value, cand[:n.value].copy()
+
+
 class TextureBrush:
     """painty::TextureBrush<vec3> with smudge disabled (renderer/TextureBrush.hxx)."""
 
@@ -502,6 +542,17 @@ class TextureBrush:
 
     def enableSmudge(self, enable):
         lib().pb_tbrush_enable_smudge(self.h, int(bool(enable)))
+
+    def addTexture(self, thickness_map):
+        """Upload one more thickness texture (TextureBrushDictionary entry); returns its id for pb_tstroke.texture_id."""
+        tm = _f64(thickness_map)
+        tid = C.c_int(0)
+        _chk(lib().pb_tbrush_add_texture(self.h, tm.shape[0], tm.shape[1], _p(tm), C.byref(tid)))
+        return tid.value
+
+    def selectTexture(self, texture_id):
+        """The texture paintStroke samples (BrushStrokeSample::setThicknessMap's role); 0 = the constructor's map."""
+        _chk(lib().pb_tbrush_select_texture(self.h, int(texture_id)))
 
     def paintStroke(self, path, canvas):
         path = _f64(path).reshape(-1, 2)

@@ -7,6 +7,8 @@ Reference behaviour mirrored (citations relative to /root/reference):
   * FootprintBrush::setRadius (width/sizeMap/pad)    painty/renderer/FootprintBrush.hxx:46-63
   * ScaledMat = cv::resize(INTER_LANCZOS4)           painty/image/Mat.hxx:141-147
   * PaddedMat                                        painty/image/Mat.hxx:116-129
+  * TextureBrushDictionary::loadHeightMap            painty/renderer/src/TextureBrushDictionary.cxx:71-79
+  * CanvasGpu::clear (canvas pattern substrate)      painty/renderer/src/CanvasGpu.cxx:27-40
 """
 import functools
 import math
@@ -39,6 +41,39 @@ def footprint_full():
 def thickness_map():
     """171x800 f64 linearised stroke thickness sample (BrushStrokeSample.cxx:164)."""
     return np.ascontiguousarray(srgb_to_linear(_npz()["thickness_u16"].astype(np.float64) * (1.0 / 0xFFFF)))
+
+
+_TEXTURES = os.path.join(os.path.dirname(_ASSETS), "painty_textures.npz")
+
+
+@functools.lru_cache(maxsize=1)
+def brush_textures():
+    """The brush-texture dictionary's inputs: list of (name, size key, length key, height map f64) for data/textures in
+    file-name order. loadHeightMap = imRead(gray, no sRGB) = u16 * (1/0xffff) as f64, then cv::normalize(NORM_MINMAX, 0, 1)
+    (TextureBrushDictionary.cxx:71-79); evaluated with the container's cv2 like the LANCZOS4 footprints."""
+    import cv2
+
+    z = np.load(_TEXTURES)
+    out = []
+    for key in sorted(k for k in z.files if k.startswith("tex_")):
+        u16 = z[key].astype(np.uint16) * np.uint16(257)
+        gray = u16.astype(np.float64) * (1.0 / 0xFFFF)
+        gray = cv2.normalize(gray, None, 0.0, 1.0, cv2.NORM_MINMAX)
+        tok = key[4:].split("_")
+        out.append((key[4:], int(tok[0]), int(tok[1]), np.ascontiguousarray(gray)))
+    return out
+
+
+def canvas_pattern(rows, cols):
+    """Substrate reflectance R0 of the sbr renderer's canvas (CanvasGpu.cxx:27-40): canvas_patterns/0.png read as linear RGB
+    (u8 / 0xff, srgb2rgb), converted to float32, LANCZOS4-scaled to the canvas size (ScaledMat); returned as f64 [rows,cols,3]."""
+    import cv2
+
+    pat = np.load(_TEXTURES)["canvas_pattern_u8"]
+    lin = srgb_to_linear(pat.astype(np.float64) * (1.0 / 0xFF)).astype(np.float32)
+    if lin.shape[:2] != (rows, cols):
+        lin = cv2.resize(lin, (cols, rows), interpolation=cv2.INTER_LANCZOS4)
+    return np.ascontiguousarray(lin.astype(np.float64))
 
 
 def palette(name="lindemeier_measured"):

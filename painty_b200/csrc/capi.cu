@@ -136,8 +136,14 @@ struct pb_tbrush {
   double radius   = 0.0;
   double thickness_scale = 1.0;                                        // BrushBase.hxx:45
   double paintK[3] = {0.1, 0.1, 0.1}, paintS[3] = {0.1, 0.1, 0.1};      // TextureBrush.hxx:29-31
-  int map_rows = 0, map_cols = 0;
-  double* d_map = nullptr;
+  // thickness textures: [0] = the stroke sample handed to the constructor (BrushStrokeSample::getThicknessMap), the
+  // others were added with pb_tbrush_add_texture (the brush-texture dictionary of TextureBrushDictionary.cxx)
+  struct Texture {
+    int rows = 0, cols = 0;
+    double* d_map = nullptr;
+  };
+  std::vector<Texture> textures;
+  int current_texture = 0;  // used by pb_tbrush_paint_stroke (BrushStrokeSample::setThicknessMap's role)
   unsigned long long* d_counters = nullptr;  // [0] deposited stroke-pixels, [1] scratch: max thickness bits
   // Smudge (renderer/Smudge.hxx): two ping-pong pickup windows of size x size, state carried across strokes
   bool use_smudge       = false;  // the reference defaults to true (TextureBrush.hxx:236), see INTEGRATION.md
@@ -1124,6 +1130,93 @@ int pb_canvas_render(pb_canvas* c, double* out) {
   planes_free_temp(r);
   PB_API_END
 }
+namespace {
+// OpenCV's INTER_LANCZOS4 taps for one axis of a (src -> dst) resize, exactly as cv::resize prepares them for a
+// floating-point image (modules/imgproc/src/resize.cpp: fx = (float)((d + 0.5) * scale - 0.5), s = floor(fx), and
+// interpolateLanczos4 — single-precision intermediate x + 3 - i, double sin/cos of the first angle rotated by 45 degrees per
+// tap, weights normalised in float). tests/test_oracle.py pins this against cv2.resize bit for bit.
+void lanczos4_taps(int src, int dst, std::vector<int>& ofs, std::vector<float>& w) {
+  static const double s45    = 0.70710678118654752440084436210485;
+  static const double cs[][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+  const double pi    = 3.1415926535897932384626433832795;
+  const double scale = static_cast<double>(src) / dst;
+  ofs.resize(static_cast<size_t>(dst));
+  w.resize(static_cast<size_t>(dst) * 8);
+  for (int d = 0; d < dst; ++d) {
+    float fx     = static_cast<float>((d + 0.5) * scale - 0.5);
+    const int sx = static_cast<int>(std::floor(fx));
+    fx -= static_cast<float>(sx);
+    ofs[static_cast<size_t>(d)] = sx;
+    float* c        = &w[static_cast<size_t>(d) * 8];
+    const float x3  = fx + 3.0f;
+    const double y0 = -x3 * pi * 0.25, s0 = std::sin(y0), c0 = std::cos(y0);
+    float sum       = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      const float y0_ = x3 - static_cast<float>(i);
+      if (std::fabs(y0_) >= 1e-6f) {
+        const double y = -y0_ * pi * 0.25;
+        c[i]           = static_cast<float>((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+      } else {
+        c[i] = 1e30f;
+      }
+      sum += c[i];
+    }
+    sum = 1.f / sum;
+    for (int i = 0; i < 8; ++i) c[i] *= sum;
+  }
+}
+}  // namespace
+int pb_lanczos4_taps(int src, int dst, int32_t* offsets, float* weights) {
+  PB_API_BEGIN
+  PB_REQUIRE(src > 0 && dst > 0 && offsets && weights, "pb_lanczos4_taps: bad arguments");
+  std::vector<int> o;
+  std::vector<float> w;
+  lanczos4_taps(src, dst, o, w);
+  std::copy(o.begin(), o.end(), offsets);
+  std::copy(w.begin(), w.end(), weights);
+  PB_API_END
+}
+int pb_canvas_compose_lab_scaled(pb_canvas* c, int out_rows, int out_cols, double* out) {
+  PB_API_BEGIN
+  PB_REQUIRE(c != nullptr && out != nullptr, "pb_canvas_compose_lab_scaled: null argument");
+  PB_REQUIRE(out_rows > 0 && out_cols > 0, "pb_canvas_compose_lab_scaled: empty output");
+  pb_context* ctx = c->pl.ctx;
+  DeviceGuard g(ctx);
+  PB_REQUIRE(c->store_first == 0 && c->pl.rows == c->rows, "pb_canvas_compose_lab_scaled needs a full canvas (not a band)");
+  const int rows = c->pl.rows, cols = c->pl.cols;
+  pb_planes lab;
+  planes_alloc_temp(ctx, lab, rows, cols, 3);
+  try {
+    void* o[3] = {lab.plane(0), lab.plane(1), lab.plane(2)};
+    km_compose_lab(ctx, c->pl.n(), compose_args(c->pl, c->pl, PR, o, 0, ctx->esize()));
+    const size_t n_out = static_cast<size_t>(out_rows) * out_cols * 3;
+    DevBuf<double> d_out(ctx, n_out);
+    if (out_rows == rows && out_cols == cols) {  // cv::resize copies when the size does not change
+      lab_planes_to_aos(ctx, o, c->pl.n(), d_out.p);
+    } else {
+      std::vector<int> xofs, yofs;
+      std::vector<float> alpha, beta;
+      lanczos4_taps(cols, out_cols, xofs, alpha);
+      lanczos4_taps(rows, out_rows, yofs, beta);
+      DevBuf<int> d_x(ctx, xofs.size()), d_y(ctx, yofs.size());
+      DevBuf<float> d_a(ctx, alpha.size()), d_b(ctx, beta.size());
+      DevBuf<double> d_tmp(ctx, static_cast<size_t>(rows) * out_cols * 3);
+      d_x.upload(xofs.data(), xofs.size());
+      d_y.upload(yofs.data(), yofs.size());
+      d_a.upload(alpha.data(), alpha.size());
+      d_b.upload(beta.data(), beta.size());
+      lab_resize_lanczos4(ctx, o, rows, cols, out_rows, out_cols, d_x.p, d_a.p, d_y.p, d_b.p, d_tmp.p, d_out.p);
+      PB_CUDA(cudaStreamSynchronize(ctx->stream));  // the host tap vectors were uploaded asynchronously
+    }
+    PB_CUDA(cudaMemcpyAsync(out, d_out.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+  } catch (...) {
+    planes_free_temp(lab);
+    throw;
+  }
+  planes_free_temp(lab);
+  PB_API_END
+}
 int pb_canvas_compose_qrgb32(pb_canvas* c, uint32_t* out) {
   PB_API_BEGIN
   PB_REQUIRE(c != nullptr, "pb_canvas_compose_qrgb32: null handle");
@@ -1582,10 +1675,11 @@ void smudge_strokes(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const pb_tstr
     L.cols        = c->cols;
     L.store_first = c->store_first;
     L.store_rows  = c->pl.rows;
-    L.map         = b->d_map;
-    L.map_rows    = b->map_rows;
-    L.map_cols    = b->map_cols;
     DevTStroke& d = L.stroke;
+    PB_REQUIRE(in.texture_id >= 0 && static_cast<size_t>(in.texture_id) < b->textures.size(), "stroke texture id out of range");
+    d.map      = b->textures[static_cast<size_t>(in.texture_id)].d_map;
+    d.map_rows = b->textures[static_cast<size_t>(in.texture_id)].rows;
+    d.map_cols = b->textures[static_cast<size_t>(in.texture_id)].cols;
     for (int i = 0; i < 3; ++i) {
       d.K[i] = in.K[i];
       d.S[i] = in.S[i];
@@ -1641,6 +1735,19 @@ void smudge_strokes(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const pb_tstr
 }
 }  // namespace
 
+namespace {
+pb_tbrush::Texture upload_texture(pb_context* ctx, int rows, int cols, const double* map) {
+  pb_tbrush::Texture t;
+  t.rows = rows;
+  t.cols = cols;
+  const size_t bytes = sizeof(double) * static_cast<size_t>(rows) * cols;
+  PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&t.d_map), bytes));
+  PB_CUDA(cudaMemcpyAsync(t.d_map, map, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));  // the host buffer is the caller's
+  return t;
+}
+}  // namespace
+
 int pb_tbrush_create(pb_context* ctx, int map_rows, int map_cols, const double* thickness_map, pb_tbrush** out) {
   PB_API_BEGIN
   PB_REQUIRE(ctx != nullptr, "pb_tbrush_create: null handle");
@@ -1648,10 +1755,7 @@ int pb_tbrush_create(pb_context* ctx, int map_rows, int map_cols, const double* 
   PB_REQUIRE(map_rows > 0 && map_cols > 0 && thickness_map != nullptr, "texture brush needs a thickness map");
   auto b      = std::make_unique<pb_tbrush>();
   b->ctx      = ctx;
-  b->map_rows = map_rows;
-  b->map_cols = map_cols;
-  PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_map), sizeof(double) * map_rows * map_cols));
-  PB_CUDA(cudaMemcpyAsync(b->d_map, thickness_map, sizeof(double) * map_rows * map_cols, cudaMemcpyHostToDevice, ctx->stream));
+  b->textures.push_back(upload_texture(ctx, map_rows, map_cols, thickness_map));
   PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_counters), 2 * sizeof(unsigned long long)));
   PB_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
   PB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1663,7 +1767,7 @@ int pb_tbrush_destroy(pb_tbrush* b) {
   if (b) {
     DeviceGuard g(b->ctx);
     PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
-    cudaFree(b->d_map);
+    for (auto& t : b->textures) cudaFree(t.d_map);
     cudaFree(b->d_counters);
     planes_free(b->smudge_map[0]);
     planes_free(b->smudge_map[1]);
@@ -1671,6 +1775,23 @@ int pb_tbrush_destroy(pb_tbrush* b) {
   }
   PB_API_END
 }
+int pb_tbrush_add_texture(pb_tbrush* b, int map_rows, int map_cols, const double* thickness_map, int* texture_id) {
+  PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_tbrush_add_texture: null handle");
+  PB_REQUIRE(map_rows > 0 && map_cols > 0 && thickness_map != nullptr, "pb_tbrush_add_texture: empty texture");
+  DeviceGuard g(b->ctx);
+  b->textures.push_back(upload_texture(b->ctx, map_rows, map_cols, thickness_map));
+  if (texture_id) *texture_id = static_cast<int>(b->textures.size()) - 1;
+  PB_API_END
+}
+int pb_tbrush_select_texture(pb_tbrush* b, int texture_id) {
+  PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_tbrush_select_texture: null handle");
+  PB_REQUIRE(texture_id >= 0 && static_cast<size_t>(texture_id) < b->textures.size(), "texture id out of range");
+  b->current_texture = texture_id;
+  PB_API_END
+}
+int pb_tbrush_texture_count(const pb_tbrush* b) { return b ? static_cast<int>(b->textures.size()) : 0; }
 int pb_tbrush_set_radius(pb_tbrush* b, double radius) {
   PB_API_BEGIN
   PB_REQUIRE(b != nullptr, "pb_tbrush_set_radius: null handle");
@@ -1745,6 +1866,10 @@ int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const 
       d.S[i] = in.S[i];
     }
     d.thickness_scale = in.thickness_scale;
+    PB_REQUIRE(in.texture_id >= 0 && static_cast<size_t>(in.texture_id) < b->textures.size(), "stroke texture id out of range");
+    d.map             = b->textures[static_cast<size_t>(in.texture_id)].d_map;
+    d.map_rows        = b->textures[static_cast<size_t>(in.texture_id)].rows;
+    d.map_cols        = b->textures[static_cast<size_t>(in.texture_id)].cols;
     d.poly_begin      = static_cast<int32_t>(poly.size());
     d.item_begin      = n_items;
     d.tx0 = d.ty0 = 0;
@@ -1791,9 +1916,6 @@ int pb_tbrush_stroke_batch(pb_tbrush* b, pb_canvas* c, int64_t n_strokes, const 
   L.cols        = c->cols;
   L.store_first = c->store_first;
   L.store_rows  = c->pl.rows;
-  L.map         = b->d_map;
-  L.map_rows    = b->map_rows;
-  L.map_cols    = b->map_cols;
   L.strokes     = d_strokes.p;
   L.n_strokes   = n_strokes;
   L.poly        = d_poly.p;
@@ -1821,6 +1943,7 @@ int pb_tbrush_paint_stroke(pb_tbrush* b, pb_canvas* c, int n, const double* path
   s.thickness_scale = b->thickness_scale;
   s.first_vertex    = 0;
   s.n_vertices      = n;
+  s.texture_id      = b->current_texture;
   return pb_tbrush_stroke_batch(b, c, 1, &s, n, path_xy);
 }
 int pb_tbrush_counters(pb_tbrush* b, uint64_t* pixels) {
@@ -1831,6 +1954,84 @@ int pb_tbrush_counters(pb_tbrush* b, uint64_t* pixels) {
   PB_CUDA(cudaMemcpyAsync(&h, b->d_counters, sizeof(h), cudaMemcpyDeviceToHost, b->ctx->stream));
   PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
   if (pixels) *pixels = h;
+  PB_API_END
+}
+
+// ---- TextureBrushDictionary (host only) ----------------------------------------------------------------------------
+struct pb_texdict {
+  // groups[i0][i1] = entries, size keys and length keys ascending (std::map order, TextureBrushDictionary.cxx:92-118)
+  std::vector<std::vector<std::vector<int32_t>>> groups;
+  std::vector<double> avg_sizes;                // :120-137
+  std::vector<std::vector<double>> avg_length;  // :139-164
+};
+int pb_texdict_create(int n, const int32_t* size_key, const int32_t* length_key, const int32_t* rows, const int32_t* cols,
+                      pb_texdict** out) {
+  PB_API_BEGIN
+  PB_REQUIRE(n > 0 && size_key && length_key && rows && cols && out, "pb_texdict_create: bad arguments");
+  std::map<uint32_t, std::map<uint32_t, std::vector<int32_t>>> m;
+  for (int i = 0; i < n; ++i) m[static_cast<uint32_t>(size_key[i])][static_cast<uint32_t>(length_key[i])].push_back(i);
+  auto d = std::make_unique<pb_texdict>();
+  for (const auto& e : m) {
+    d->groups.emplace_back();
+    for (const auto& a : e.second) d->groups.back().push_back(a.second);
+  }
+  d->avg_sizes.assign(d->groups.size(), 0.0);
+  d->avg_length.resize(d->groups.size());
+  for (size_t i = 0; i < d->groups.size(); ++i) {
+    uint32_t count = 0;
+    d->avg_length[i].assign(d->groups[i].size(), 0.0);
+    for (size_t j = 0; j < d->groups[i].size(); ++j) {
+      uint32_t cj = 0;
+      for (const int32_t t : d->groups[i][j]) {
+        d->avg_sizes[i] += static_cast<double>(rows[t]);
+        d->avg_length[i][j] += static_cast<double>(cols[t]);
+        ++count;
+        ++cj;
+      }
+      d->avg_length[i][j] *= (1.0 / static_cast<double>(cj));
+    }
+    d->avg_sizes[i] *= (1.0 / static_cast<double>(count));
+  }
+  *out = d.release();
+  PB_API_END
+}
+int pb_texdict_destroy(pb_texdict* d) {
+  delete d;
+  return 0;
+}
+int pb_texdict_lookup(const pb_texdict* d, int n, const double* path_xy, double brush_size, int32_t* size_group,
+                      int32_t* length_group, int capacity, int32_t* candidates, int32_t* n_candidates) {
+  PB_API_BEGIN
+  PB_REQUIRE(d != nullptr && n >= 1 && path_xy != nullptr, "pb_texdict_lookup: bad arguments");
+  double length = 0.0;  // :27-30
+  for (int i = 0; i + 1 < n; ++i) {
+    const double dx = path_xy[2 * i] - path_xy[2 * i + 2], dy = path_xy[2 * i + 1] - path_xy[2 * i + 3];
+    length += std::sqrt(dx * dx + dy * dy);
+  }
+  uint32_t i0 = 0, i1 = 1;  // :32-33
+  double mr = d->avg_sizes[0];
+  for (uint32_t i = 0; i < d->avg_sizes.size(); ++i) {  // :36-43
+    const double dd = std::abs(d->avg_sizes[i] - brush_size);
+    if (dd < mr) {
+      mr = dd;
+      i0 = i;
+    }
+  }
+  double ml = d->avg_length[i0][0];
+  const size_t n_len = std::min(d->avg_sizes.size(), d->avg_length[i0].size());  // the reference reads out of range beyond
+  for (uint32_t i = 0; i < n_len; ++i) {                                         // :46-53
+    const double dd = std::abs(d->avg_length[i0][i] - length);
+    if (dd < ml) {
+      ml = dd;
+      i1 = i;
+    }
+  }
+  PB_REQUIRE(i1 < d->groups[i0].size() && !d->groups[i0][i1].empty(), "no candidate found");  // :57-59
+  const auto& cand = d->groups[i0][i1];
+  if (size_group) *size_group = static_cast<int32_t>(i0);
+  if (length_group) *length_group = static_cast<int32_t>(i1);
+  if (n_candidates) *n_candidates = static_cast<int32_t>(cand.size());
+  for (int k = 0; k < capacity && k < static_cast<int>(cand.size()) && candidates; ++k) candidates[k] = cand[static_cast<size_t>(k)];
   PB_API_END
 }
 

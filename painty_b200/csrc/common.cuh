@@ -122,6 +122,11 @@ void km_compose_stacked(pb_context* ctx, int64_t n, const StackArgs& a);
 void km_compose_display(pb_context* ctx, int64_t n, const ComposeArgs& a, int mode, bool srgb, void* out);
 // Renderer::render: R = light(KM(K,S,V over R0), height = V), rows x cols image, R planes out
 void km_render(pb_context* ctx, int rows, int cols, const ComposeArgs& a);
+// planner read-back prep: compose + CIELab into a.R (3 planes of the element type), then OpenCV's LANCZOS4 resize
+void km_compose_lab(pb_context* ctx, int64_t n, const ComposeArgs& a);
+void lab_resize_lanczos4(pb_context* ctx, void* const lab[3], int rows, int cols, int orows, int ocols, const int* d_xofs,
+                         const float* d_alpha, const int* d_yofs, const float* d_beta, double* d_tmp, double* d_out);
+void lab_planes_to_aos(pb_context* ctx, void* const lab[3], int64_t n, double* d_out);
 // Canvas::dryCanvas: h += V; R0 = KM(K,S,R0,V); K=S=V=0
 void km_dry(pb_context* ctx, int64_t n, void* const planes[11]);
 

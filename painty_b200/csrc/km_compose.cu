@@ -237,6 +237,92 @@ __global__ void __launch_bounds__(256) km_compose_display_kernel(ComposePtrs<T> 
   }
 }
 
+// ---- planner read-back prep: compose -> CIELab -> LANCZOS4 down-scale --------------------------
+// ColorConverter::rgb2lab (core/Color.hxx:248-252): rgb2xyz with the sRGB D65 matrix (:169-176), xyz2lab (:89-93) with
+// f(t) = t > (6/29)^3 ? t^(1/3) : (1/3)(29/6)^2 t + 4/29 (:786-790), white point D65 (:48-50). FP64 keeps the reference's
+// operation order and pow(t, 1/3); FP32 uses cbrtf.
+__device__ __forceinline__ double lab_f(double t) {
+  return t > 0.008856451679035631 ? pow(t, 1. / 3.) : 7.787037037037035 * t + (4. / 29.);
+}
+__device__ __forceinline__ float lab_f(float t) { return t > 0.008856451679035631f ? cbrtf(t) : fmaf(7.787037037037035f, t, 4.f / 29.f); }
+template <typename T>
+__device__ __forceinline__ void rgb_to_lab(const T rgb[3], T lab[3]) {
+  const T X = static_cast<T>(0.4124564) * rgb[0] + static_cast<T>(0.3575761) * rgb[1] + static_cast<T>(0.1804375) * rgb[2];
+  const T Y = static_cast<T>(0.2126729) * rgb[0] + static_cast<T>(0.7151522) * rgb[1] + static_cast<T>(0.0721750) * rgb[2];
+  const T Z = static_cast<T>(0.0193339) * rgb[0] + static_cast<T>(0.1191920) * rgb[1] + static_cast<T>(0.9503041) * rgb[2];
+  const T fx = lab_f(X / static_cast<T>(0.95047)), fy = lab_f(Y / static_cast<T>(1.00000)), fz = lab_f(Z / static_cast<T>(1.08883));
+  lab[0] = static_cast<T>(116.) * fy - static_cast<T>(16.);
+  lab[1] = static_cast<T>(500.) * (fx - fy);
+  lab[2] = static_cast<T>(200.) * (fy - fz);
+}
+
+// compose + Lab, one pixel per thread; the Lab image stays on the device (3 planes of T)
+template <typename T>
+__global__ void __launch_bounds__(256) km_compose_lab_kernel(ComposePtrs<T> a, int64_t n) {
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  T r[3] = {__ldcs(a.R0[0] + o), __ldcs(a.R0[1] + o), __ldcs(a.R0[2] + o)};
+  km_pixel(__ldcs(a.K[0] + o), __ldcs(a.K[1] + o), __ldcs(a.K[2] + o), __ldcs(a.S[0] + o), __ldcs(a.S[1] + o), __ldcs(a.S[2] + o),
+           __ldcs(a.V + o), r[0], r[1], r[2]);
+  T lab[3];
+  rgb_to_lab(r, lab);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) a.R[c][o] = lab[c];
+}
+
+// cv::resize(INTER_LANCZOS4) as OpenCV evaluates it for a CV_64F image (the reference's ScaledMat, image/Mat.hxx:141-147):
+// separable 8-tap passes, horizontal first; tap j of output column dx reads source column clamp(xofs[dx] - 3 + j) with the
+// single-precision weight alpha[dx][j]; products and the left-to-right sums are double. Offsets and weights come from the
+// host (lanczos4_taps in capi.cu). Horizontal pass: Lab planes (T) -> tmp[c][row][dx] (double).
+template <typename T>
+__global__ void __launch_bounds__(256) lanczos4_h_kernel(const T* l0, const T* l1, const T* l2, int rows, int cols, int ocols,
+                                                         const int* __restrict__ xofs, const float* __restrict__ alpha, double* tmp) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(rows) * ocols) return;
+  const int row = static_cast<int>(i / ocols), dx = static_cast<int>(i - static_cast<int64_t>(row) * ocols);
+  const int sx = xofs[dx] - 3;
+  const T* src[3] = {l0, l1, l2};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const T* S = src[c] + static_cast<int64_t>(row) * cols;
+    double v   = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int x    = min(max(sx + j, 0), cols - 1);
+      const double p = static_cast<double>(S[x]) * static_cast<double>(alpha[dx * 8 + j]);
+      v              = j == 0 ? p : v + p;
+    }
+    tmp[(static_cast<int64_t>(c) * rows + row) * ocols + dx] = v;
+  }
+}
+// Vertical pass: out[dy][dx][c] (AoS double, the layout of the Mat3d the planner receives)
+__global__ void __launch_bounds__(256) lanczos4_v_kernel(const double* tmp, int rows, int ocols, int orows, const int* __restrict__ yofs,
+                                                         const float* __restrict__ beta, double* out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(orows) * ocols) return;
+  const int dy = static_cast<int>(i / ocols), dx = static_cast<int>(i - static_cast<int64_t>(dy) * ocols);
+  const int sy = yofs[dy] - 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int y    = min(max(sy + k, 0), rows - 1);
+      const double p = tmp[(static_cast<int64_t>(c) * rows + y) * ocols + dx] * static_cast<double>(beta[dy * 8 + k]);
+      v              = k == 0 ? p : v + p;
+    }
+    out[i * 3 + c] = v;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) planes_to_aos_f64_kernel(const T* l0, const T* l1, const T* l2, int64_t n, double* out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[3 * i]     = static_cast<double>(l0[i]);
+  out[3 * i + 1] = static_cast<double>(l1[i]);
+  out[3 * i + 2] = static_cast<double>(l2[i]);
+}
+
 // Renderer::render (renderer/Renderer.hxx:60-156) per pixel, after the fused compose. Operation order follows the
 // reference (3-vector reductions left to right). T = float uses the single-precision libm-equivalents.
 template <typename T>
@@ -460,6 +546,55 @@ void km_compose_display(pb_context* ctx, int64_t n, const ComposeArgs& a, int mo
     p.V = static_cast<const float*>(a.V);
     km_compose_display_kernel<float><<<blocks, 256, 0, ctx->stream>>>(p, n, mode, srgb, out);
   }
+  PB_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+template <typename T>
+static void compose_lab_t(pb_context* ctx, int64_t n, const ComposeArgs& a) {
+  ComposePtrs<T> p;
+  for (int c = 0; c < 3; ++c) {
+    p.K[c]  = static_cast<const T*>(a.K[c]);
+    p.S[c]  = static_cast<const T*>(a.S[c]);
+    p.R0[c] = static_cast<const T*>(a.R0[c]);
+    p.R[c]  = static_cast<T*>(a.R[c]);
+  }
+  p.V = static_cast<const T*>(a.V);
+  km_compose_lab_kernel<T><<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(p, n);
+  PB_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+void km_compose_lab(pb_context* ctx, int64_t n, const ComposeArgs& a) {
+  if (n <= 0) return;
+  if (ctx->precision == PB_F64)
+    compose_lab_t<double>(ctx, n, a);
+  else
+    compose_lab_t<float>(ctx, n, a);
+}
+void lab_resize_lanczos4(pb_context* ctx, void* const lab[3], int rows, int cols, int orows, int ocols, const int* d_xofs,
+                         const float* d_alpha, const int* d_yofs, const float* d_beta, double* d_tmp, double* d_out) {
+  const int64_t nh = static_cast<int64_t>(rows) * ocols, nv = static_cast<int64_t>(orows) * ocols;
+  if (ctx->precision == PB_F64)
+    lanczos4_h_kernel<double><<<static_cast<unsigned>((nh + 255) / 256), 256, 0, ctx->stream>>>(
+        static_cast<const double*>(lab[0]), static_cast<const double*>(lab[1]), static_cast<const double*>(lab[2]), rows, cols, ocols,
+        d_xofs, d_alpha, d_tmp);
+  else
+    lanczos4_h_kernel<float><<<static_cast<unsigned>((nh + 255) / 256), 256, 0, ctx->stream>>>(
+        static_cast<const float*>(lab[0]), static_cast<const float*>(lab[1]), static_cast<const float*>(lab[2]), rows, cols, ocols, d_xofs,
+        d_alpha, d_tmp);
+  PB_CUDA(cudaGetLastError());
+  lanczos4_v_kernel<<<static_cast<unsigned>((nv + 255) / 256), 256, 0, ctx->stream>>>(d_tmp, rows, ocols, orows, d_yofs, d_beta, d_out);
+  PB_CUDA(cudaGetLastError());
+  ctx->launches += 2;
+}
+void lab_planes_to_aos(pb_context* ctx, void* const lab[3], int64_t n, double* d_out) {
+  if (n <= 0) return;
+  if (ctx->precision == PB_F64)
+    planes_to_aos_f64_kernel<double><<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(
+        static_cast<const double*>(lab[0]), static_cast<const double*>(lab[1]), static_cast<const double*>(lab[2]), n, d_out);
+  else
+    planes_to_aos_f64_kernel<float><<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(
+        static_cast<const float*>(lab[0]), static_cast<const float*>(lab[1]), static_cast<const float*>(lab[2]), n, d_out);
   PB_CUDA(cudaGetLastError());
   ctx->launches++;
 }

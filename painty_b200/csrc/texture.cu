@@ -195,9 +195,9 @@ __global__ void __launch_bounds__(256) texture_kernel(const TextureLaunch L) {
       double u, v;
       mvc(s_poly, s_uv, st.n_poly, static_cast<double>(x), static_cast<double>(y), u, v);
       if (u < 0.0 || u > 1.0 || v < 0.0 || v > 1.0) continue;
-      u *= L.map_cols;
-      v *= L.map_rows;
-      const double Vtex = st.thickness_scale * bilinear(L.map, L.map_rows, L.map_cols, u, v);
+      u *= st.map_cols;
+      v *= st.map_rows;
+      const double Vtex = st.thickness_scale * bilinear(st.map, st.map_rows, st.map_cols, u, v);
       if (!(Vtex > 0.0)) continue;
       const int s = x - st.x0, t = y - st.y0;
       if (!(s >= 0 && t >= 0 && s < st.local_cols && t < st.local_rows)) continue;  // :163-164
@@ -250,9 +250,9 @@ __global__ void __launch_bounds__(256) thickness_kernel(const SmudgeLaunch L) {
     double u, v;
     mvc(s_poly, s_uv, st.n_poly, static_cast<double>(x), static_cast<double>(y), u, v);
     if (u < 0.0 || u > 1.0 || v < 0.0 || v > 1.0) continue;
-    u *= L.map_cols;
-    v *= L.map_rows;
-    const double Vtex = st.thickness_scale * bilinear(L.map, L.map_rows, L.map_cols, u, v);
+    u *= st.map_cols;
+    v *= st.map_rows;
+    const double Vtex = st.thickness_scale * bilinear(st.map, st.map_rows, st.map_cols, u, v);
     if (!(Vtex > 0.0)) continue;
     const int s = x - st.x0, t = y - st.y0;
     if (!(s >= 0 && t >= 0 && s < st.local_cols && t < st.local_rows)) continue;

@@ -16,13 +16,15 @@ struct DevTStroke {
   int32_t poly_begin, n_poly;
   int32_t tx0, ty0, tx1, ty1;  // canvas tiles covered by the bounding box (inclusive); empty if tx1 < tx0
   int64_t item_begin;          // first work item (stroke, tile) of this stroke
+  // the stroke's thickness texture (f64 row-major): the brush's own sample map or an entry of its texture atlas
+  // (TextureBrushDictionary.cxx:25-79 picks one per stroke)
+  const double* map;
+  int32_t map_rows, map_cols;
 };
 
 struct TextureLaunch {
   void* canvas[kLayerPlanes];
   int rows, cols, store_first, store_rows;
-  const double* map;  // thickness map, f64 row-major
-  int map_rows, map_cols;
   const DevTStroke* strokes;
   int64_t n_strokes;
   const double2* poly;
@@ -49,8 +51,6 @@ struct DevSmudgeStep {
 struct SmudgeLaunch {
   void* canvas[kLayerPlanes];
   int rows, cols, store_first, store_rows;
-  const double* map;  // stroke texture (thickness sample), f64
-  int map_rows, map_cols;
   DevTStroke stroke;  // one stroke at a time: the smudge state chains strokes serially
   const double2* poly;
   const double2* uv;

@@ -570,3 +570,99 @@ def test_claim_order_protocol_never_deadlocks_on_eight_gpus(built_lib):
         assert _emulate_queues(n, seg_first, seg_off, ps, pn, order, pool, run, slots, np.random.default_rng(trial)) == n
     # the check has teeth: reversing the queues makes later strokes wait for strokes stuck behind them
     assert _emulate_queues(n, seg_first, seg_off, ps, pn, order[::-1], pool, run[::-1] * 0, [[2]] * world, np.random.default_rng(0)) < n
+
+
+def _dictionary_restatement(tex):
+    """Plain-Python restatement of TextureBrushDictionary::createBrushTexturesFromFolder / lookup
+    (renderer/src/TextureBrushDictionary.cxx:25-69, 81-164) for the test: returns lookup(path, brush_size)."""
+    sizes = sorted(set(t[1] for t in tex))
+    groups = []
+    for s in sizes:
+        lens = sorted(set(t[2] for t in tex if t[1] == s))
+        groups.append([[i for i, t in enumerate(tex) if t[1] == s and t[2] == l] for l in lens])
+    avg_sizes = [sum(tex[i][3].shape[0] for g in gs for i in g) * (1.0 / sum(len(g) for g in gs)) for gs in groups]
+    avg_len = [[sum(tex[i][3].shape[1] for i in g) * (1.0 / len(g)) for g in gs] for gs in groups]
+
+    def lookup(path, brush_size):
+        length = sum(math.hypot(path[i][0] - path[i + 1][0], path[i][1] - path[i + 1][1]) for i in range(len(path) - 1))
+        i0, i1 = 0, 1
+        mr = avg_sizes[0]
+        for i in range(len(avg_sizes)):
+            d = abs(avg_sizes[i] - brush_size)
+            if d < mr:
+                mr, i0 = d, i
+        ml = avg_len[i0][0]
+        for i in range(min(len(avg_sizes), len(avg_len[i0]))):
+            d = abs(avg_len[i0][i] - length)
+            if d < ml:
+                ml, i1 = d, i
+        return i0, i1, groups[i0][i1]
+
+    return lookup
+
+
+def test_texture_dictionary_lookup_rule(built_lib):
+    """pb_texdict_* == the restatement above on the shipped 236 textures (5 size keys x 5 length keys), incl. the
+    reference's quirk that the running minima start from VALUES (so small brushes / short strokes keep the defaults)."""
+    from painty_b200 import api, assets
+
+    tex = assets.brush_textures()
+    assert len(tex) == 236 and sorted(set(t[1] for t in tex)) == [1, 2, 4, 10, 14]
+    for _, _, _, m in tex[::17]:
+        assert m.dtype == np.float64 and m.min() == 0.0 and abs(m.max() - 1.0) < 1e-15  # cv::normalize(NORM_MINMAX)
+    dic = api.TextureBrushDictionary([t[1] for t in tex], [t[2] for t in tex], [t[3].shape[0] for t in tex],
+                                     [t[3].shape[1] for t in tex])
+    want = _dictionary_restatement(tex)
+    r = np.random.default_rng(5)
+    seen = set()
+    for _ in range(300):
+        n = int(r.integers(2, 20))
+        path = r.uniform(0, 4000, 2) + np.cumsum(r.normal(0, r.uniform(1, 120), (n, 2)), axis=0)
+        size = float(r.uniform(1, 400))
+        i0, i1, cand = dic.lookup(path, size)
+        w0, w1, wc = want(path, size)
+        assert (i0, i1) == (w0, w1) and list(cand) == wc
+        seen.add((i0, i1))
+    assert len(seen) >= 10
+    # defaults survive when nothing beats the seeds: i0 = 0, i1 = 1
+    assert dic.lookup([(0, 0), (1e9, 0)], 1e9)[:2] == (0, 1)
+
+
+def test_canvas_pattern_asset():
+    """canvas_patterns/0.png as CanvasGpu::clear prepares it (CanvasGpu.cxx:27-40): linear RGB, float32, LANCZOS4."""
+    from painty_b200 import assets
+
+    p = assets.canvas_pattern(2048, 2048)
+    assert p.shape == (2048, 2048, 3) and p.dtype == np.float64
+    lin198 = float(np.float32(assets.srgb_to_linear(198 / 255.0)))
+    assert p.min() == lin198 and p.max() == 1.0  # the shipped pattern's sRGB values span 198..255
+    q = assets.canvas_pattern(270, 480)
+    assert q.shape == (270, 480, 3) and 0.5 < q.min() and q.max() < 1.2
+
+
+def test_lanczos4_taps_reproduce_cv2_resize(built_lib, port):
+    """The resize behind pb_canvas_compose_lab_scaled: the library's tap tables + the two separable passes (restated here in
+    numpy with the kernel's operation order) == cv2.resize(INTER_LANCZOS4) bit for bit on f64 images, for down- and
+    up-scaling incl. the sbr painter's canvas -> target-image factors; and the CIELab conversion of the port is sane."""
+    import cv2
+
+    from painty_b200 import api
+
+    r = np.random.default_rng(1)
+    for (R, C, oR, oC) in ((37, 53, 20, 31), (64, 48, 32, 24), (50, 70, 23, 33), (30, 30, 45, 50), (216, 384, 108, 192), (90, 160, 77, 102)):
+        src = r.uniform(-100, 100, (R, C, 3))
+        xo, xa = api.lanczos4_taps(C, oC)
+        yo, ya = api.lanczos4_taps(R, oR)
+        tmp = None
+        for j in range(8):
+            p = src[:, np.clip(xo - 3 + j, 0, C - 1), :] * xa[:, j].astype(np.float64)[None, :, None]
+            tmp = p if tmp is None else tmp + p
+        out = None
+        for k in range(8):
+            p = tmp[np.clip(yo - 3 + k, 0, R - 1)] * ya[:, k].astype(np.float64)[:, None, None]
+            out = p if out is None else out + p
+        assert np.array_equal(out, cv2.resize(src, (oC, oR), interpolation=cv2.INTER_LANCZOS4)), (R, C, oR, oC)
+    lab = port.rgb2lab(np.array([[1.0, 1.0, 1.0], [0.0, 0.0, 0.0], [0.2, 0.5, 0.1], [0.001, 0.002, 0.0005]]))
+    assert abs(lab[0, 0] - 100.0) < 1e-3 and abs(lab[0, 1]) < 1e-2 and abs(lab[0, 2]) < 1e-2  # D65 white
+    assert np.abs(lab[1]).max() < 1e-12
+    assert 0 < lab[3, 0] < 3  # linear branch of f

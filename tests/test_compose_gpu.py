@@ -233,3 +233,28 @@ def test_render_relighting(ctx32, ctx64, port, prec):
     cvo.set_layer(K, S, V)
     got, want = api.Renderer().render(cv), cvo.render()
     assert np.abs(got - want).max() <= (1e-10 if prec else 2e-4)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_lab_scaled_readback_prep(ctx32, ctx64, port, prec):
+    """pb_canvas_compose_lab_scaled == ScaledMat(convertColor(compose(canvas), rgb_2_CIELab), rows, cols)
+    (PictureTargetSbrPainter.cxx:334-341): FP64 within 1e-10 (Lab units), FP32 within 1e-4 of reflectance scaled to the
+    Lab range (x100) — and the same-size case is a plain conversion."""
+    from painty_b200 import api
+
+    ctx = [ctx32, ctx64][prec]
+    rows, cols = 150, 202
+    K, S, V, R0 = km_random_planes(rows, cols, seed=11, edge_cases=False)
+    V[::3, ::2] = 0.0
+    cv, cc = api.Canvas(ctx, rows, cols), port.canvas(rows, cols)
+    cv.setBackground(R0)
+    cc.set_background(R0)
+    cv.upload_layer(K, S, V)
+    cc.set_layer(K, S, V)
+    want_rgb = cc.compose()
+    tol = 1e-10 if prec else 1e-2
+    for (orows, ocols) in ((75, 101), (64, 90), (rows, cols), (200, 260)):
+        got = cv.compose_lab_scaled(orows, ocols)
+        want = port.lab_scaled(want_rgb, orows, ocols)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= tol, (orows, ocols, float(np.abs(got - want).max()))

@@ -133,3 +133,71 @@ def test_texture_brush_test_with_smudge_fixture(ctx32, ctx64, golden, prec):
     assert np.abs(R[200:300, 300:400] - golden["texs_R_crop"]).max() <= TOL[prec]
     assert np.abs(R.sum(axis=(0, 2)) - golden["texs_R_colsum"]).max() <= TOL[prec] * 768 * 3
     assert np.abs(st["V"][200:300, 300:400] - golden["texs_V_crop"]).max() <= (1e-12 if prec else 1e-5)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_per_stroke_dictionary_textures_match_oracle(ctx32, ctx64, port, prec):
+    """Config-3 semantics: every stroke samples the thickness texture the brush-texture dictionary picked for it
+    (TextureBrushDictionary.cxx:25-79) on a canvas-pattern substrate (CanvasGpu.cxx:27-40). CPU side: the reference's
+    TextureBrush::paintStroke with that texture installed as the brush's thickness map (one CPU brush per texture),
+    strokes in submission order."""
+    from painty_b200 import api, assets
+
+    ctx = [ctx32, ctx64][prec]
+    rows, cols = 240, 320
+    tex = assets.brush_textures()
+    dic = api.TextureBrushDictionary([t[1] for t in tex], [t[2] for t in tex], [t[3].shape[0] for t in tex],
+                                     [t[3].shape[1] for t in tex])
+    r = np.random.default_rng(77)
+    R0 = assets.canvas_pattern(rows, cols)
+    cv, cvo = api.Canvas(ctx, rows, cols), port.canvas(rows, cols)
+    cv.setBackground(R0)
+    cvo.set_background(R0)
+    tb = api.TextureBrush(ctx)
+    ids, cpu_brushes = {}, {}
+    n = 30
+    rec = np.zeros(n, dtype=api.TSTROKE_DTYPE)
+    verts, first, groups = [], 0, set()
+    for i in range(n):
+        K, S = r.uniform(0.05, 1.5, 3), r.uniform(0.05, 1.0, 3)
+        rad = float(r.uniform(3, 40))
+        m = int(r.integers(2, 9))
+        p0 = r.uniform(0, [cols, rows])
+        path = p0 + np.cumsum(r.normal(0, rad * 0.6, (m, 2)), axis=0)
+        i0, i1, cand = dic.lookup(path, 2.0 * rad)
+        groups.add((i0, i1))
+        pick = int(cand[int(r.integers(0, len(cand)))])  # the reference draws with std::random_device; we record the pick
+        if pick not in ids:
+            ids[pick] = tb.addTexture(tex[pick][3])
+            cpu_brushes[pick] = port.texture_brush(tex[pick][3])
+        tbo = cpu_brushes[pick]
+        tbo.set_radius(rad)
+        tbo.dip(K, S)
+        tbo.set_thickness_scale(0.05)
+        tbo.paint_stroke(cvo, path)
+        rec[i] = (rad, K, S, 0.05, first, m, ids[pick])
+        first += m
+        verts.append(path)
+    assert len(groups) >= 4  # the strokes exercise several (size, length) classes
+    tb.stroke_batch(cv, rec, np.concatenate(verts))
+    a, b = cv.download("KSV"), cvo.get()
+    if prec:
+        for k in "KSV":
+            assert np.array_equal(a[k], b[k]), k
+    assert np.abs(cv.compose() - cvo.compose()).max() <= TOL[prec]
+    # single-stroke API with a selected texture == batch entry
+    cv2_, cvo2 = api.Canvas(ctx, rows, cols), port.canvas(rows, cols)
+    some = next(iter(ids))
+    tb.selectTexture(ids[some])
+    tb.setRadius(12.0)
+    tb.dip(([.2, .3, .4], [.1, .23, .14]))
+    tb.setThicknessScale(0.3)
+    tb.paintStroke([(20, 30), (150, 120), (300, 200)], cv2_)
+    tbo = cpu_brushes[some]
+    tbo.set_radius(12.0)
+    tbo.dip([.2, .3, .4], [.1, .23, .14])
+    tbo.set_thickness_scale(0.3)
+    tbo.paint_stroke(cvo2, [(20, 30), (150, 120), (300, 200)])
+    assert np.abs(cv2_.compose() - cvo2.compose()).max() <= TOL[prec]
+    with pytest.raises(Exception):
+        tb.selectTexture(10_000)
