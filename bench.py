@@ -21,8 +21,9 @@ N > 1: one process per GPU (torchrun), weak scaling of ONE canvas: the canvas gr
 strokes of the same size distribution and is cut into N row bands, one per GPU. A stroke is executed by the GPU
 whose band holds its first imprint; where it leaves the band the kernel reads / writes the neighbour's HBM through
 NVLink peer mappings and strokes wait on completion flags of conflicting earlier strokes on any GPU
-(painty_b200/dist.py, bit-exact vs one GPU: tests/test_dist_gpu.py). The reflectance bands are assembled with one NCCL
-all_gather inside the timed step.
+(painty_b200/dist.py, bit-exact vs one GPU: tests/test_dist_gpu.py). The reflectance image is assembled inside the timed
+step by the compose kernel itself: every rank stores its band's rows straight into every rank's image over NVLink
+(pb_canvas_compose_gather) — no separate collective.
 """
 import argparse
 import json
@@ -279,9 +280,13 @@ def main():
         dc.attach(br)
     n_px = cv.store_rows * COLS
     d_R = torch.empty((3, n_px), dtype=torch.float32, device="cuda")
-    h_R = torch.empty((cv.store_rows, COLS, 3), dtype=torch.float64).pin_memory()
+    # host result of the e2e leg: the whole reflectance image (AoS f64 like Renderer::compose returns); at N > 1 it is
+    # assembled in rank 0's HBM by the compose kernels' peer stores and read back by rank 0 alone
+    h_rows = rows_total if rank == 0 else 1
+    h_R = torch.empty((h_rows, COLS, 3), dtype=torch.float64).pin_memory()
     h_R_np = h_R.numpy()
-    gathered = torch.empty((world, 3, n_px), dtype=torch.float32, device="cuda") if world > 1 else None
+    if dc is not None:
+        dc.attach_image(root=None)  # every rank receives the assembled image (all-gather semantics)
 
     def strokes_all(r=rec, x=cx, y=cy, t=th):
         if dc is not None:
@@ -308,13 +313,12 @@ def main():
         strokes_all()
         if timers is not None:
             timers[1].record(stream)
-        cv.compose_device(d_R.data_ptr(), n_px)
+        if world > 1:
+            dc.compose_gather()  # compose + band gather in one kernel: rows go straight into every rank's image over NVLink
+        else:
+            cv.compose_device(d_R.data_ptr(), n_px)
         if timers is not None:
             timers[2].record(stream)
-        if world > 1:
-            # NCCL work is ordered after the compose on the context's stream, and the stream waits for it
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gathered.view(-1), d_R.view(-1))
 
     def barrier():
         ctx.synchronize()
@@ -360,7 +364,13 @@ def main():
         cv.clear()
         br.updateSnapshot(cv)
         strokes_all()
-        cv.compose(h_R_np)
+        if world > 1:
+            dc.compose_gather()
+            dc.finish_gather()  # context sync + process-group barrier: every band has arrived
+            if rank == 0:
+                dc.download_image(h_R_np)
+        else:
+            cv.compose(h_R_np)
 
     # one warm-up pass (first use of the host-buffer path allocates staging memory), then timed passes
     e2e_steps = max(3, args.steps)
@@ -376,7 +386,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item())
     h2d = rec.nbytes + cx.nbytes * 3  # stroke records + (cx, cy, theta) per imprint (the library derives the rest)
-    d2h = n_px * 3 * 8
+    d2h = n_px * world * 3 * 8  # the assembled image, read back by rank 0
 
     # Roofline of the KM compose kernel, measured live. "in_step": events around the compose launch of every timed step
     # (behind the imprint kernel, cold L2; at N > 1 the launch also follows a host-side process-group barrier, so the
@@ -393,7 +403,8 @@ def main():
     cmp_b2b_ms = ce0.elapsed_time(ce1) / 5
     cmp_ms = cmp_in_step_ms if world == 1 else cmp_b2b_ms
     roofline_how = "events around the compose launch of every timed step" if world == 1 else \
-        "5 back-to-back launches after the timed steps (the in-step launch follows a host barrier)"
+        "5 back-to-back launches of the plain compose kernel after the timed steps (the in-step launch is the compose + gather " \
+        "kernel, NVLink bound: see gather)"
     achieved = COMPOSE_BYTES_PER_PX * n_px / (cmp_ms * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback"
     try:
@@ -406,8 +417,8 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "sbr-style 3840x%d, %d footprint strokes (%d imprints) + KM compose" % (rows_total, len(rec), len(cx)),
                    "parallelism": "single GPU" if world == 1 else
-                   "one %dx%d canvas in %d row bands (one per GPU), strokes cross bands through NVLink peer memory, NCCL all_gather of "
-                   "reflectance" % (rows_total, COLS, world),
+                   "one %dx%d canvas in %d row bands (one per GPU), strokes cross bands through NVLink peer memory, reflectance image "
+                   "assembled on every rank by the compose kernel's peer stores" % (rows_total, COLS, world),
                    "stroke_pixels_per_step": int(visited_all), "stroke_pixels_per_step_this_rank": int(visited),
                    "active_stroke_pixels_per_step_this_rank": int(active),
                    "l2": "canvas working set 8.3 Mpx x (2 x 32 B records + 1 B) = 539 MB > 126 MB L2; canvas cleared every step",
@@ -432,6 +443,11 @@ def main():
                        "imprints_per_s_this_rank": len(cx) / max(world, 1) / (imp_ms * 1e-3),
                        "active_stroke_pixels_per_s": active / (imp_ms * 1e-3),
                        "record_bytes_per_active_px": 101, "record_GBps": 101 * active / (imp_ms * 1e-3) / 1e9}
+    if world > 1:  # compose with the band-gather epilogue: (40 + 12 N) B per pixel, 12 (N - 1) of them over NVLink
+        line["gather"] = {"kernel": "km_compose_gather_kernel<float>", "ms_in_step": cmp_in_step_ms,
+                          "nvlink_bytes_out_per_rank": 12 * (world - 1) * n_px,
+                          "nvlink_GBps_out_per_rank": 12 * (world - 1) * n_px / (cmp_in_step_ms * 1e-3) / 1e9,
+                          "what": "every rank stores its band's reflectance rows into every rank's image (all-gather by peer stores)"}
     try:  # host-side share of a batch: dataflow planning, per-imprint constants, the planner's model of the step
         line["host"] = br.batch_stats()
     except Exception as exc:  # diagnostics only

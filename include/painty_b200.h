@@ -286,6 +286,20 @@ int pb_fbrush_dist_end(pb_fbrush* b, pb_canvas* c);
 int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* dist, int64_t n_strokes, const pb_stroke* strokes,
                                 int64_t n_imprints, const double* cx, const double* cy, const double* theta);
 
+/* Final assembly of the reflectance image (SURVEY.md §8e "gather of reflectance bands") without a separate collective: every
+ * rank that wants the image creates a pb_band_image (3 planes r,g,b of rows*cols elements of the context's type in ONE
+ * allocation), exports its base with pb_ipc_export and imports the others'. pb_canvas_compose_gather composes the
+ * canvas' own band (Renderer::compose) and stores the rows straight into the n_dst given images — its own and / or peers'
+ * over NVLink — at the band's position (gather to a root: n_dst = 1; all-gather: one entry per rank). All images share
+ * one plane stride (pb_band_image_device). An image is complete once every rank's call has finished: synchronise the
+ * contexts and run a process-group barrier before reading it (pb_band_image_download = host AoS f64, or the device base). */
+typedef struct pb_band_image pb_band_image;
+int pb_band_image_create(pb_context* ctx, int rows, int cols, pb_band_image** out);
+int pb_band_image_destroy(pb_band_image* im);
+int pb_band_image_device(pb_band_image* im, void** base, int64_t* plane_stride_bytes);
+int pb_band_image_download(pb_band_image* im, double* out);
+int pb_canvas_compose_gather(pb_canvas* band_canvas, int n_dst, void* const* dst_base, int64_t plane_stride_bytes);
+
 /* ---- TextureBrush -------------------------------------------------------------------------------- */
 /* thickness map: rows*cols host f64 (BrushStrokeSample::getThicknessMap). */
 int pb_tbrush_create(pb_context* ctx, int map_rows, int map_cols, const double* thickness_map, pb_tbrush** out);

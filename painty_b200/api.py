@@ -483,6 +483,37 @@ class FootprintBrush:
         return {k: float(v) for k, v in zip(keys, out)}
 
 
+class BandImage:
+    """Assembled reflectance image of a band-sharded canvas (pb_band_image): 3 planes of rows x cols in one allocation."""
+
+    def __init__(self, ctx, rows, cols):
+        self.ctx, self.rows, self.cols = ctx, rows, cols
+        self.h = _VP()
+        _chk(lib().pb_band_image_create(ctx.h, rows, cols, C.byref(self.h)))
+        base, stride = _VP(), C.c_int64(0)
+        _chk(lib().pb_band_image_device(self.h, C.byref(base), C.byref(stride)))
+        self.base, self.plane_stride_bytes = base.value, stride.value
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h and lib is not None:
+            lib().pb_band_image_destroy(self.h)
+            self.h = None
+
+    def download(self):
+        out = np.empty((self.rows, self.cols, 3))
+        _chk(lib().pb_band_image_download(self.h, _p(out)))
+        return out
+
+
+def compose_gather(canvas, images):
+    """Compose `canvas`' own band and store it into every image of `images` (BandImage objects or raw base pointers that
+    share one plane stride) at the band's rows."""
+    bases = [im.base if isinstance(im, BandImage) else int(im[0]) for im in images]
+    stride = images[0].plane_stride_bytes if isinstance(images[0], BandImage) else int(images[0][1])
+    arr = (_VP * len(bases))(*bases)
+    _chk(lib().pb_canvas_compose_gather(canvas.h, len(bases), arr, C.c_int64(stride)))
+
+
 def lanczos4_taps(src, dst):
     """(offsets[dst], weights[dst, 8]) of one axis of cv::resize(INTER_LANCZOS4) as the library evaluates it (host only)."""
     ofs = np.zeros(dst, dtype=np.int32)

@@ -1080,6 +1080,63 @@ int pb_canvas_compose_band_device(pb_canvas* c, void* d_out, int64_t plane_strid
   km_compose(ctx, n, compose_args(c->pl, c->pl, PR, o, off, ctx->esize()));
   PB_API_END
 }
+// ---- assembled reflectance image of a band-sharded canvas ------------------------------------------------------------
+struct pb_band_image {
+  pb_planes pl;  // 3 planes (r, g, b) of rows x cols elements of the context's type, one cudaMalloc (IPC exportable)
+};
+int pb_band_image_create(pb_context* ctx, int rows, int cols, pb_band_image** out) {
+  PB_API_BEGIN
+  PB_REQUIRE(ctx != nullptr && out != nullptr, "pb_band_image_create: null argument");
+  PB_REQUIRE(rows > 0 && cols > 0 && static_cast<int64_t>(rows) * cols < (1ll << 31), "pb_band_image_create: bad size");
+  DeviceGuard g(ctx);
+  auto im = std::make_unique<pb_band_image>();
+  planes_alloc(ctx, im->pl, rows, cols, 3);
+  *out = im.release();
+  PB_API_END
+}
+int pb_band_image_destroy(pb_band_image* im) {
+  PB_API_BEGIN
+  if (im) {
+    DeviceGuard g(im->pl.ctx);
+    PB_CUDA(cudaStreamSynchronize(im->pl.ctx->stream));
+    planes_free(im->pl);
+    delete im;
+  }
+  PB_API_END
+}
+int pb_band_image_device(pb_band_image* im, void** base, int64_t* plane_stride_bytes) {
+  PB_CHECK_HANDLE(im, "pb_band_image_device");
+  if (base) *base = im->pl.base;
+  if (plane_stride_bytes) *plane_stride_bytes = static_cast<int64_t>(im->pl.stride);
+  return 0;
+}
+int pb_band_image_download(pb_band_image* im, double* out) {
+  PB_API_BEGIN
+  PB_REQUIRE(im != nullptr && out != nullptr, "pb_band_image_download: null argument");
+  DeviceGuard g(im->pl.ctx);
+  download_aos(im->pl.ctx, im->pl, 0, 3, out);
+  PB_API_END
+}
+int pb_canvas_compose_gather(pb_canvas* c, int n_dst, void* const* dst_base, int64_t plane_stride_bytes) {
+  PB_API_BEGIN
+  PB_REQUIRE(c != nullptr && dst_base != nullptr, "pb_canvas_compose_gather: null argument");
+  PB_REQUIRE(n_dst >= 1 && n_dst <= PB_MAX_BANDS, "pb_canvas_compose_gather: 1..8 destinations");
+  pb_context* ctx = c->pl.ctx;
+  DeviceGuard g(ctx);
+  const size_t es   = ctx->esize();
+  const int64_t off = static_cast<int64_t>(c->row_begin - c->store_first) * c->cols;  // first owned pixel in the stored planes
+  const int64_t at  = static_cast<int64_t>(c->row_begin) * c->cols;                   // ... and in the assembled image
+  const int64_t n   = static_cast<int64_t>(c->row_end - c->row_begin) * c->cols;
+  void* dst[PB_MAX_BANDS][3];
+  for (int d = 0; d < n_dst; ++d) {
+    PB_REQUIRE(dst_base[d] != nullptr, "pb_canvas_compose_gather: null destination");
+    for (int k = 0; k < 3; ++k)
+      dst[d][k] = static_cast<char*>(dst_base[d]) + static_cast<size_t>(k) * static_cast<size_t>(plane_stride_bytes) + static_cast<size_t>(at) * es;
+  }
+  void* none[3] = {nullptr, nullptr, nullptr};
+  km_compose_gather(ctx, n, compose_args(c->pl, c->pl, PR, none, off, es), n_dst, dst);
+  PB_API_END
+}
 int pb_canvas_compose(pb_canvas* c, double* out) {
   PB_API_BEGIN
   PB_REQUIRE(c != nullptr, "pb_canvas_compose: null handle");

@@ -107,6 +107,8 @@ struct ComposeArgs {
   void* R[3];
 };
 void km_compose(pb_context* ctx, int64_t n, const ComposeArgs& a);
+// compose with a gather epilogue: R is stored into n_dst (<= 8) destination images (own HBM or NVLink peer mappings)
+void km_compose_gather(pb_context* ctx, int64_t n, const ComposeArgs& a, int n_dst, void* const (*dst)[3]);
 constexpr int kMaxStack = 8;
 struct StackArgs {
   const void* K[kMaxStack][3];

@@ -141,6 +141,44 @@ __global__ void __launch_bounds__(256) km_compose_kernel(ComposePtrs<T> a, int64
   }
 }
 
+// Compose + band gather (multi GPU): the band's reflectance rows are stored straight into the assembled image of up to
+// kGatherMax ranks — the rank's own HBM and CUDA-IPC peer mappings reached over NVLink — instead of composing into a local
+// buffer and running a collective afterwards. dst[d][c] already points at this band's first row in destination d.
+constexpr int kGatherMax = 8;
+template <typename T>
+struct GatherPtrs {
+  T* dst[kGatherMax][3];
+  int n_dst;
+};
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) km_compose_gather_kernel(ComposePtrs<T> a, GatherPtrs<T> g, int64_t n4, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (VEC && i < n4) {
+    const int64_t o = i * 4;
+    T k[3][4], s[3][4], v[4], r[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ld4(a.K[c] + o, k[c]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ld4(a.S[c] + o, s[c]);
+    ld4(a.V + o, v);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ld4(a.R0[c] + o, r[c]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) km_pixel(k[0][j], k[1][j], k[2][j], s[0][j], s[1][j], s[2][j], v[j], r[0][j], r[1][j], r[2][j]);
+    for (int d = 0; d < g.n_dst; ++d) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) st4(g.dst[d][c] + o, r[c]);
+    }
+  } else if (VEC ? i == n4 : i < n) {  // scalar tail (n % 4 pixels), or everything when a destination is not 16 B aligned
+    const int64_t o0 = VEC ? n4 * 4 : i, o1 = VEC ? n : i + 1;
+    for (int64_t o = o0; o < o1; ++o) {
+      T r0 = a.R0[0][o], r1 = a.R0[1][o], r2 = a.R0[2][o];
+      km_pixel(a.K[0][o], a.K[1][o], a.K[2][o], a.S[0][o], a.S[1][o], a.S[2][o], a.V[o], r0, r1, r2);
+      for (int d = 0; d < g.n_dst; ++d) g.dst[d][0][o] = r0, g.dst[d][1][o] = r1, g.dst[d][2][o] = r2;
+    }
+  }
+}
+
 // fallback for caller-provided planes that are not 16 B aligned: one pixel per thread
 template <typename T>
 __global__ void __launch_bounds__(256) km_compose_scalar_kernel(ComposePtrs<T> a, int64_t n) {
@@ -548,6 +586,45 @@ void km_compose_display(pb_context* ctx, int64_t n, const ComposeArgs& a, int mo
   }
   PB_CUDA(cudaGetLastError());
   ctx->launches++;
+}
+
+template <typename T>
+static void compose_gather_t(pb_context* ctx, int64_t n, const ComposeArgs& a, int n_dst, void* const (*dst)[3]) {
+  ComposePtrs<T> p;
+  GatherPtrs<T> g;
+  bool aligned = true;
+  auto al      = [&](const void* q) { aligned = aligned && (reinterpret_cast<uintptr_t>(q) % 16 == 0); };
+  for (int c = 0; c < 3; ++c) {
+    p.K[c]  = static_cast<const T*>(a.K[c]);
+    p.S[c]  = static_cast<const T*>(a.S[c]);
+    p.R0[c] = static_cast<const T*>(a.R0[c]);
+    p.R[c]  = nullptr;
+    al(a.K[c]), al(a.S[c]), al(a.R0[c]);
+  }
+  p.V = static_cast<const T*>(a.V);
+  al(a.V);
+  g.n_dst = n_dst;
+  for (int d = 0; d < n_dst; ++d)
+    for (int c = 0; c < 3; ++c) {
+      g.dst[d][c] = static_cast<T*>(dst[d][c]);
+      al(dst[d][c]);
+    }
+  if (aligned) {
+    const int64_t n4 = n / 4;
+    km_compose_gather_kernel<T, true><<<static_cast<unsigned>((n4 + 1 + 255) / 256), 256, 0, ctx->stream>>>(p, g, n4, n);
+  } else {
+    km_compose_gather_kernel<T, false><<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(p, g, 0, n);
+  }
+  PB_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+void km_compose_gather(pb_context* ctx, int64_t n, const ComposeArgs& a, int n_dst, void* const (*dst)[3]) {
+  PB_REQUIRE(n_dst >= 1 && n_dst <= kGatherMax, "compose_gather: 1..8 destinations");
+  if (n <= 0) return;
+  if (ctx->precision == PB_F64)
+    compose_gather_t<double>(ctx, n, a, n_dst, dst);
+  else
+    compose_gather_t<float>(ctx, n, a, n_dst, dst);
 }
 
 template <typename T>

@@ -83,9 +83,62 @@ class DistCanvas:
         self.dist.barrier()  # all GPUs have finished writing into each other's bands
         api._chk(lib.pb_fbrush_dist_end(brush.h, self.canvas.h))  # records -> planes
 
+    # ---- final assembly of the reflectance image: compose with a peer-store epilogue (no separate collective) ----
+    def attach_image(self, root=None):
+        """Create the assembled-image buffers and exchange their peer mappings. root=None: every rank receives the image
+        (all-gather); root=r: only rank r does. Collective."""
+        lib = api.lib()
+        if getattr(self, "_image", None):  # re-attach: nobody may still be writing into the old image
+            self.ctx.synchronize()
+            self.dist.barrier()
+            lib.pb_band_image_destroy(self._image)
+        self._image_root = root
+        self._image = _VP()
+        mine = None
+        if root is None or root == self.rank:
+            api._chk(lib.pb_band_image_create(self.ctx.h, self.rows, self.cols, C.byref(self._image)))
+            base, stride = _VP(), C.c_int64(0)
+            api._chk(lib.pb_band_image_device(self._image, C.byref(base), C.byref(stride)))
+            self._image_base, self._image_stride = base.value, stride.value
+            mine = (self._export(base.value), stride.value)
+        everyone = [None] * self.world
+        self.dist.all_gather_object(everyone, mine)
+        self._image_dst = []
+        for r, e in enumerate(everyone):
+            if e is None:
+                continue
+            self._image_stride = e[1]
+            self._image_dst.append(self._image_base if r == self.rank else self._import(e[0]))
+        self.dist.barrier()
+
+    def compose_gather(self):
+        """Renderer::compose of this rank's band, stored straight into the destination images over NVLink. The images are
+        complete after every rank's context has synchronised and a process-group barrier (finish_gather)."""
+        if not hasattr(self, "_image_dst"):
+            self.attach_image()
+        arr = (_VP * len(self._image_dst))(*self._image_dst)
+        api._chk(api.lib().pb_canvas_compose_gather(self.canvas.h, len(self._image_dst), arr, C.c_int64(self._image_stride)))
+
+    def finish_gather(self):
+        self.ctx.synchronize()
+        self.dist.barrier()
+
+    def image_device(self):
+        """(device base pointer, plane stride in bytes) of this rank's assembled image, or None on a non-root rank."""
+        return (self._image_base, self._image_stride) if self._image else None
+
+    def download_image(self, out=None):
+        """Assembled reflectance as host AoS f64 [rows, cols, 3] (ranks that hold an image)."""
+        out = np.empty((self.rows, self.cols, 3)) if out is None else out
+        api._chk(api.lib().pb_band_image_download(self._image, api._p(out)))
+        return out
+
     def close(self):
         self.ctx.synchronize()
         self.dist.barrier()
+        if getattr(self, "_image", None):
+            api.lib().pb_band_image_destroy(self._image)
+            self._image = None
         for p in self._imported:
             api.lib().pb_ipc_close(self.ctx.h, _VP(p))
         self._imported = []

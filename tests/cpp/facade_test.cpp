@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
 #include <map>
 #include <string>
 #include <vector>
@@ -18,6 +19,7 @@
 #include "painty/renderer/FootprintBrush.hxx"
 #include "painty/renderer/PaintLayer.hxx"
 #include "painty/renderer/Renderer.hxx"
+#include "painty/renderer/SbrRenderThread.hxx"
 #include "painty/renderer/SbrRenderThreadCuda.hxx"
 #include "painty/renderer/TextureBrush.hxx"
 // reference host code the façade keeps using
@@ -67,6 +69,8 @@ void painty::io::imRead(const std::string& filename, Mat<double>& gray, bool) {
   gray = Mat<double>(it->second.rows, it->second.cols);
   std::memcpy(gray.data, it->second.data.data(), sizeof(double) * it->second.data.size());
 }
+
+void painty::io::imRead(const std::string& filename, Mat<vec3>&, bool) { throw std::ios_base::failure(filename); }
 
 int main(int argc, char** argv) {
   if (argc < 6) {
@@ -182,6 +186,51 @@ int main(int argc, char** argv) {
     double sum2               = 0.0;
     for (const auto& p : dried) sum2 += p[0] + p[1] + p[2];
     EXPECT(std::fabs(sum2 - sum) < 1.0);  // drying moves the paint into the substrate, the picture stays
+  }
+  {  // the drop-in under the reference's own name and constructor (SbrRenderThread.hxx:19-74): a GpuTaskQueue pointer is
+     // accepted and ignored; brush textures come from a dictionary folder (file names <size>_<lengthClass>_<nn>.png,
+     // TextureBrushDictionary.cxx:81-118), one texture per stroke picked by (stroke length, 2 * radius)
+    namespace fs = std::filesystem;
+    const fs::path dir = fs::temp_directory_path() / "painty_b200_facade_textures";
+    fs::remove_all(dir);
+    fs::create_directories(dir / "textures");
+    const Image thick = g_images["data/sample_0/thickness_map.png"];
+    const char* names[] = {"1_0_01.png", "1_1_01.png", "4_0_01.png", "4_1_01.png", "4_1_02.png"};
+    const int crop_cols[] = {100, 400, 150, 500, 600}, crop_rows[] = {40, 60, 120, 150, 171};
+    for (int k = 0; k < 5; ++k) {
+      const std::string file = (dir / "textures" / names[k]).string();
+      std::fclose(std::fopen(file.c_str(), "wb"));
+      Image im{crop_rows[k], crop_cols[k], {}};
+      for (int y = 0; y < im.rows; ++y)
+        for (int x = 0; x < im.cols; ++x) im.data.push_back(thick.data[static_cast<size_t>(y) * thick.cols + x] * (k + 1));
+      g_images[file] = im;
+    }
+    painty::SbrRenderOptions opt;
+    opt.useCanvasPattern = false;  // needs OpenCV's 4-channel float resize (the stand-in cv::resize only serves baked results)
+    opt.dataDir          = dir.string();
+    opt.seed             = 7;
+    auto run = [&]() {
+      painty::SbrRenderThread rt(std::shared_ptr<painty::GpuTaskQueue>(), painty::Size{640U, 480U}, opt);
+      EXPECT(rt.getTextureCount() == 5U);
+      rt.setBrushThicknessScale(0.5);
+      rt.enableSmudge(false);
+      rt.render({{50, 250}, {300, 240}, {600, 260}}, 30.0, {painty::vec3(.2, .3, .4), painty::vec3(.1, .23, .14)});
+      rt.render({{100.5, 50.2}, {150.1, 100.7}}, 4.0, {painty::vec3(.5, .1, .2), painty::vec3(.3, .2, .5)});
+      rt.render({{300, 400}, {340, 300}, {420, 200}}, 12.0, {painty::vec3(.1, .5, .2), painty::vec3(.3, .3, .1)}).wait();
+      const painty::Mat3d rgb = rt.getLinearRgbImage().get();
+      const painty::Mat3d lab = rt.getLabImageScaled(240, 320).get();
+      EXPECT(lab.rows == 240 && lab.cols == 320);
+      double sum = 0.0, l_min = 1e9, l_max = -1e9;
+      for (const auto& p : rgb) sum += p[0] + p[1] + p[2];
+      for (const auto& p : lab) l_min = std::min(l_min, p[0]), l_max = std::max(l_max, p[0]);
+      EXPECT(l_max > 99.0 && l_max < 101.5 && l_min > 0.0 && l_min < 90.0);  // white canvas (L ~ 100) with painted strokes
+      return sum;
+    };
+    const double a = run(), b = run();
+    std::printf("sbr thread (dictionary) sumR %.6f\n", a);
+    EXPECT(a == b);                          // a seeded draw repeats
+    EXPECT(a < 640.0 * 480.0 * 3.0 - 100.0);  // the strokes left paint on the white canvas
+    fs::remove_all(dir);
   }
   {  // error translation: invalid_argument like KubelkaMunk.hxx:98
     double K[3], S[3];

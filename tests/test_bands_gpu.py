@@ -67,3 +67,33 @@ def test_texture_bands_equal_full_canvas(ctx32, ctx64, prec):
         parts.append(out)
     img = torch.cat([p.reshape(3, -1, cols) for p in parts], dim=1).permute(1, 2, 0).cpu().numpy().astype(np.float64)
     assert np.abs(img - want_R).max() <= (1e-12 if prec else 1e-6)
+
+
+@pytest.mark.parametrize("cols", [260, 261])
+@pytest.mark.parametrize("prec", [0, 1])
+def test_compose_gather_assembles_the_image(ctx32, ctx64, prec, cols):
+    """pb_canvas_compose_gather: band canvases compose straight into the assembled image(s) at their rows — equal to
+    Renderer::compose of the whole canvas bit for bit; cols = 261 takes the unaligned (scalar store) path."""
+    from painty_b200 import api
+    from tests.workloads import km_random_planes
+
+    ctx = [ctx32, ctx64][prec]
+    rows, world = 301, 3
+    K, S, V, R0 = km_random_planes(rows, cols, seed=21, edge_cases=False)
+    V[::5] = 0.0
+    full = api.Canvas(ctx, rows, cols)
+    full.setBackground(R0)
+    full.upload_layer(K, S, V)
+    want = full.compose()
+    img_a, img_b = api.BandImage(ctx, rows, cols), api.BandImage(ctx, rows, cols)
+    assert img_a.plane_stride_bytes == img_b.plane_stride_bytes
+    for b, e in bands.band_ranges(rows, world):
+        cv = api.Canvas(ctx, rows, cols, band=(b, e, 0))
+        cv.setBackground(R0[b:e])
+        cv.upload_layer(K[b:e], S[b:e], V[b:e])
+        api.compose_gather(cv, [img_a, img_b] if b else [img_a])  # band 0 only reaches image a
+        if b == 0:
+            api.compose_gather(cv, [img_b])
+    ctx.synchronize()
+    assert np.array_equal(img_a.download(), want)
+    assert np.array_equal(img_b.download(), want)

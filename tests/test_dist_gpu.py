@@ -56,6 +56,15 @@ def _worker(rank, world, port, prec, direct, q):
     dc.stroke_batch(br, rec[::-1].copy(), cx, cy, th)  # a second batch on the painted canvas (new epoch, stale snapshot)
     st = dc.canvas.download("KSV")
     ok = True
+    # final assembly: compose with the peer-store gather epilogue, once to every rank and once to rank 0 only
+    dc.attach_image(root=None)
+    dc.compose_gather()
+    dc.finish_gather()
+    image_all = dc.download_image()
+    dc.attach_image(root=0)
+    dc.compose_gather()
+    dc.finish_gather()
+    image_root = dc.download_image() if rank == 0 else None
     if rank == 0:  # reference: the same two batches on one GPU
         full = api.Canvas(ctx, rows, cols)
         b1 = api.FootprintBrush(ctx, radii[0])
@@ -70,8 +79,15 @@ def _worker(rank, world, port, prec, direct, q):
             for k in "KSV":
                 ok = ok and np.array_equal(part[k], want[k][b:e])
         ok = ok and float(want["V"].sum()) > 0
+        want_R = full.compose()
+        ok = ok and np.array_equal(image_root, want_R)
+        images = [None] * world
+        dist.gather_object(image_all, images, dst=0)
+        for im in images:
+            ok = ok and np.array_equal(im, want_R)
     else:
         dist.gather_object((dc.row_begin, dc.row_end, st), None, dst=0)
+        dist.gather_object(image_all, None, dst=0)
     dc.close()
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
