@@ -288,11 +288,26 @@ def main():
     if dc is not None:
         dc.attach_image(root=None)  # every rank receives the assembled image (all-gather semantics)
 
-    def strokes_all(r=rec, x=cx, y=cy, t=th):
-        if dc is not None:
+    # N > 1: the host half of a batch (dataflow planning of the global stroke list, 0.1-0.4 s) runs on a helper thread while
+    # the GPUs execute the previous batch — every step still plans its own batch, one step ahead (pb_fbrush_plan_stroke_batch)
+    from concurrent.futures import ThreadPoolExecutor
+
+    planner = ThreadPoolExecutor(1) if dc is not None else None
+    pending = [None]
+
+    def plan_next():
+        pending[0] = planner.submit(dc.plan, br, rec, cx, cy, th)
+
+    def strokes_all(r=None, x=None, y=None, t=None):
+        if dc is not None and r is None:
+            if pending[0] is None:
+                plan_next()
+            plan = pending[0].result()
+            dc.stroke_batch(br, plan=plan, after_launch=plan_next)
+        elif dc is not None:
             dc.stroke_batch(br, r, x, y, t)
         else:
-            br.stroke_batch(cv, r, x, y, t)
+            br.stroke_batch(cv, rec if r is None else r, cx if x is None else x, cy if y is None else y, th if t is None else t)
 
     # untimed: exact stroke-pixel count of the workload (reference's `counter`)
     br.enable_visited_count(True)
@@ -418,7 +433,8 @@ def main():
         "config": {"workload": "sbr-style 3840x%d, %d footprint strokes (%d imprints) + KM compose" % (rows_total, len(rec), len(cx)),
                    "parallelism": "single GPU" if world == 1 else
                    "one %dx%d canvas in %d row bands (one per GPU), strokes cross bands through NVLink peer memory, reflectance image "
-                   "assembled on every rank by the compose kernel's peer stores" % (rows_total, COLS, world),
+                   "assembled on every rank by the compose kernel's peer stores; host planning of a batch overlaps the previous batch's "
+                   "execution (plan thread)" % (rows_total, COLS, world),
                    "stroke_pixels_per_step": int(visited_all), "stroke_pixels_per_step_this_rank": int(visited),
                    "active_stroke_pixels_per_step_this_rank": int(active),
                    "l2": "canvas working set 8.3 Mpx x (2 x 32 B records + 1 B) = 539 MB > 126 MB L2; canvas cleared every step",
@@ -526,6 +542,10 @@ def main():
                           "what": "reflectance of the CPU sample's strokes rendered by the product in FP32 mode on a fresh 4K canvas"}
     if rank == 0:
         print(json.dumps(line))
+    if planner is not None:
+        if pending[0] is not None:
+            pending[0].result()
+        planner.shutdown()
     if world > 1:
         dist.destroy_process_group()
 

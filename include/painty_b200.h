@@ -234,12 +234,26 @@ typedef struct pb_stroke {
 int pb_fbrush_register_footprint(pb_fbrush* b, double radius, int side, const double* footprint);
 int pb_fbrush_stroke_batch(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_stroke* strokes, int64_t n_imprints,
                            const double* cx, const double* cy, const double* theta);
+/* The same in two steps. pb_fbrush_plan_stroke_batch does all the host work of a batch — dataflow graph, claim order, stroke
+ * records, per-imprint constants — and touches no stream, so the plan of the next batch can be made (also from another host
+ * thread) while the device executes the current one; pb_fbrush_run_batch_plan uploads the plan and launches. dist = NULL
+ * for a single GPU, or the descriptor pb_fbrush_stroke_batch_dist takes (run inside the same dist_begin / barrier bracket).
+ * A plan is made from the brush's state (radius, registered footprints, snapshot switch) at plan time and fails as stale
+ * if the radius differs when it is run; it can be run more than once. */
+typedef struct pb_batch_plan pb_batch_plan;
+struct pb_dist_desc;
+int pb_fbrush_plan_stroke_batch(pb_fbrush* b, pb_canvas* c, const struct pb_dist_desc* dist, int64_t n_strokes,
+                                const pb_stroke* strokes, int64_t n_imprints, const double* cx, const double* cy,
+                                const double* theta, pb_batch_plan** out);
+int pb_fbrush_run_batch_plan(pb_fbrush* b, pb_canvas* c, const struct pb_dist_desc* dist, const pb_batch_plan* plan);
+int pb_batch_plan_destroy(pb_batch_plan* plan);
 /* Host-side figures of the brush's last stroke or imprint batch (no device access):
  * [0] dataflow planning ms (segments + claim order), [1] per-imprint constants ms, [2] strokes planned (all ranks),
  * [3] dataflow segments, [4] wait entries, [5] the planner's model of the batch duration in ms (0 if the queue order
  * was not planned), [6] strokes executed by this rank, [7] kernel launches of this rank. */
 #define PB_BATCH_STATS 8
 int pb_fbrush_batch_stats(const pb_fbrush* b, double out[PB_BATCH_STATS]);
+int pb_batch_plan_stats(const pb_batch_plan* plan, double out[PB_BATCH_STATS]);
 
 /* Stroke-pixel counters since creation: visited = the reference's `counter` (:119), cells passing both bounds
  * checks; active = those with footprint height > 0. `visited` is only maintained while counting is enabled

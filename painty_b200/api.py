@@ -466,6 +466,20 @@ class FootprintBrush:
         _chk(lib().pb_fbrush_stroke_batch(self.h, canvas.h, C.c_int64(len(strokes)), strokes.ctypes.data_as(_VP),
                                           C.c_int64(len(cx)), _p(cx), _p(cy), _p(theta)))
 
+    def plan_stroke_batch(self, canvas, strokes, cx, cy, theta, dist_desc=None):
+        """Host half of stroke_batch (pb_fbrush_plan_stroke_batch): no stream is touched, so it may run on another host
+        thread while the device executes an earlier batch. Returns a BatchPlan for run_batch_plan."""
+        strokes = np.ascontiguousarray(strokes, dtype=STROKE_DTYPE)
+        cx, cy, theta = _f64(cx), _f64(cy), _f64(theta)
+        h = _VP()
+        _chk(lib().pb_fbrush_plan_stroke_batch(self.h, canvas.h, C.byref(dist_desc) if dist_desc is not None else None,
+                                               C.c_int64(len(strokes)), strokes.ctypes.data_as(_VP), C.c_int64(len(cx)), _p(cx), _p(cy),
+                                               _p(theta), C.byref(h)))
+        return BatchPlan(h)
+
+    def run_batch_plan(self, canvas, plan, dist_desc=None):
+        _chk(lib().pb_fbrush_run_batch_plan(self.h, canvas.h, C.byref(dist_desc) if dist_desc is not None else None, plan.h))
+
     def enable_visited_count(self, enable=True):
         lib().pb_fbrush_enable_visited_count(self.h, int(enable))
 
@@ -520,6 +534,25 @@ def lanczos4_taps(src, dst):
     w = np.zeros((dst, 8), dtype=np.float32)
     _chk(lib().pb_lanczos4_taps(int(src), int(dst), ofs.ctypes.data_as(_VP), w.ctypes.data_as(_VP)))
     return ofs, w
+
+
+class BatchPlan:
+    """Host-side plan of a footprint stroke batch (pb_batch_plan)."""
+
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib().pb_batch_plan_destroy(self.h)
+            self.h = None
+
+    def stats(self):
+        out = (C.c_double * 8)()
+        _chk(lib().pb_batch_plan_stats(self.h, out))
+        keys = ("plan_ms", "imprint_constants_ms", "strokes_planned", "segments", "wait_entries", "model_ms",
+                "strokes_this_rank", "launches_this_rank")
+        return {k: float(v) for k, v in zip(keys, out)}
 
 
 class TextureBrushDictionary:

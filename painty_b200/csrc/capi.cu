@@ -306,19 +306,56 @@ struct DistInfo {
 };
 constexpr int64_t kDistFlagCapacity = int64_t(1) << 22;
 
-// Plans and launches the persistent imprint kernel for a submission-ordered stroke list: one launch per run of
+// Host-side plan of a stroke batch: everything run_plan needs that does not depend on device state — the dataflow graph,
+// the claim order, per-run stroke records / wait lists / staging windows and the per-imprint constants of the strokes this
+// rank executes. Planning touches no stream, so the plan of the next batch can be made (on another host thread) while the
+// device still executes the current one.
+struct RunPlan {
+  size_t begin = 0, end = 0;  // range in `mine`
+  std::vector<DevStroke> ds;
+  std::vector<int2> preds;
+  std::vector<int32_t> seg_off;
+  std::vector<DevWindow> windows;  // one entry per segment of the run, parallel to seg_off
+  std::vector<int32_t> order;      // queue ticket -> stroke of this run (empty = submission order)
+  int max_active    = 1;
+  size_t max_window = 0;
+};
+}  // namespace
+struct pb_batch_plan {
+  bool multi = false;
+  int world = 1, rank = 0, rows_per_band = 0;
+  int rows = 0, cols = 0, store_first = 0, store_rows = 0;  // the canvas the plan was made for
+  bool use_snapshot = true;
+  size_t n_mine = 0;
+  std::vector<RunPlan> runs;
+  std::vector<DevImprint> im;
+  Region batch{0, 0, -1, -1};
+  double stats[PB_BATCH_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // brush state the plan assumes before / leaves after the batch (stroke batches; imprint batches keep the state)
+  bool sets_state = false;
+  double radius_before = 0.0, radius_after = 0.0;
+  const FootprintGeom* geom_after = nullptr;
+  double K_after[3] = {0, 0, 0}, S_after[3] = {0, 0, 0};
+};
+namespace {
+
+// Plans the persistent imprint kernel launches for a submission-ordered stroke list: one launch per run of
 // consecutive (local) strokes that share a launch class; dependencies are tracked across runs and — with `dist` —
 // across GPUs (every rank plans the same global list and executes the strokes whose first imprint lies in its band).
-void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs, int64_t n_imprints, const double* cx,
-                  const double* cy, const double* theta, const DistInfo* dist = nullptr) {
+void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs, int64_t n_imprints, const double* cx,
+                   const double* cy, const double* theta, const DistInfo* dist, pb_batch_plan& P) {
   pb_context* ctx = b->ctx;
   PB_REQUIRE(c->pl.ctx == ctx, "canvas and brush belong to different contexts");
-  if (hs.empty()) return;
   const bool multi = dist != nullptr && dist->world > 1;
-  if (b->use_snapshot || snapshot_matches(b, c)) ensure_snapshot(b, c);
-  ensure_work(b, c);
-  const bool have_dirty = b->dirty != nullptr && snapshot_matches(b, c);
-  PB_REQUIRE(!multi || (have_dirty && b->use_snapshot), "distributed strokes need the snapshot buffer enabled");
+  P.multi          = multi;
+  P.world          = multi ? dist->world : 1;
+  P.rank           = multi ? dist->rank : 0;
+  P.rows_per_band  = multi ? dist->rows_per_band : std::max(c->pl.rows, 1);
+  P.rows = c->rows, P.cols = c->cols, P.store_first = c->store_first, P.store_rows = c->pl.rows;
+  P.use_snapshot = b->use_snapshot;
+  if (hs.empty()) return;
+  PB_REQUIRE(!multi || b->use_snapshot, "distributed strokes need the snapshot buffer enabled");
+  (void)n_imprints;
 
   // Global plan: executor rank, local numbering, and the dataflow graph at segment granularity (schedule.hpp).
   const size_t n = hs.size();
@@ -450,49 +487,33 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
   const auto t_prep1 = std::chrono::steady_clock::now();
   {
     auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
-    b->stats[0] = ms(t_plan0, t_plan1);                                   // dataflow planning (segments + claim order)
-    b->stats[1] = ms(t_plan1, t_prep1);                                   // per-imprint constants (cos / sin)
-    b->stats[2] = static_cast<double>(n);                                 // strokes planned (all ranks)
-    b->stats[3] = static_cast<double>(plan.seg_first[n]);                 // dataflow segments
-    b->stats[4] = static_cast<double>(plan.pred_stroke.size());           // wait entries
-    b->stats[5] = model_makespan * 1e-3;                                  // the planner's model of the batch, ms
-    b->stats[6] = static_cast<double>(mine.size());                       // strokes this rank executes
-    b->stats[7] = static_cast<double>(my_runs.size());                    // kernel launches of this rank
+    P.stats[0] = ms(t_plan0, t_plan1);                                   // dataflow planning (segments + claim order)
+    P.stats[1] = ms(t_plan1, t_prep1);                                   // per-imprint constants (cos / sin)
+    P.stats[2] = static_cast<double>(n);                                 // strokes planned (all ranks)
+    P.stats[3] = static_cast<double>(plan.seg_first[n]);                 // dataflow segments
+    P.stats[4] = static_cast<double>(plan.pred_stroke.size());           // wait entries
+    P.stats[5] = model_makespan * 1e-3;                                  // the planner's model of the batch, ms
+    P.stats[6] = static_cast<double>(mine.size());                       // strokes this rank executes
+    P.stats[7] = static_cast<double>(my_runs.size());                    // kernel launches of this rank
   }
-  DevBuf<DevImprint> d_im(ctx, im.size());
-  d_im.upload(im.data(), im.size());
-
-  // completion flags: a per-batch buffer on one GPU, the brush's exported buffer + a fresh epoch across GPUs
-  DevBuf<long long> d_flags(ctx, multi ? 0 : mine.size() + 1);
-  int epoch = 1;
-  if (multi) {
-    epoch = ++b->dist_epoch;
-  } else {
-    d_flags.zero(mine.size() + 1);
-  }
-
-  // Single GPU: the kernels run on the record copy of the wet layer — convert the batch's region (stored rows, columns
-  // rounded to 4) on the way in and back on the way out. Multi GPU: the whole band is converted by pb_fbrush_dist_begin /
-  // _end around the batch (peers read each other's records, so every rank must be converted before any kernel starts).
-  Region conv{0, 0, -1, -1};
-  if (!multi && batch.x1 >= batch.x0 && batch.y1 >= batch.y0) {
-    conv.x0 = batch.x0 & ~3;
-    conv.x1 = std::min(c->cols - 1, batch.x1 | 3);
-    conv.y0 = std::max(batch.y0, c->store_first) - c->store_first;
-    conv.y1 = std::min(batch.y1, c->store_first + c->pl.rows - 1) - c->store_first;
-    planes_to_records(ctx, c->pl, b->work_rec, conv.x0, conv.y0, conv.x1, conv.y1);
-  }
+  P.im.swap(im);
+  P.batch  = batch;
+  P.n_mine = mine.size();
 
   for (const auto& my_run : my_runs) {
     const size_t run_begin = my_run.first, run_end = my_run.second;
     const size_t n_run = run_end - run_begin;
-
-    std::vector<DevStroke> ds(n_run);
-    std::vector<int2> run_preds;
-    std::vector<int32_t> run_seg_off(1, 0);
-    std::vector<DevWindow> run_windows;  // one entry per segment of the run, parallel to run_seg_off
-    int max_active = 1;
-    size_t max_window = 0;
+    P.runs.emplace_back();
+    RunPlan& RP = P.runs.back();
+    RP.begin = run_begin, RP.end = run_end;
+    std::vector<DevStroke>& ds = RP.ds;
+    ds.resize(n_run);
+    std::vector<int2>& run_preds = RP.preds;
+    std::vector<int32_t>& run_seg_off = RP.seg_off;
+    run_seg_off.assign(1, 0);
+    std::vector<DevWindow>& run_windows = RP.windows;
+    int& max_active = RP.max_active;
+    size_t& max_window = RP.max_window;
     for (size_t k = 0; k < n_run; ++k) {
       const size_t s      = mine[run_begin + k];
       const HostStroke& h = hs[s];
@@ -570,6 +591,65 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
       }
     }
 
+    if (!claim_pos.empty()) {
+      RP.order.resize(n_run);
+      for (size_t k = 0; k < n_run; ++k) RP.order[k] = static_cast<int32_t>(k);
+      std::sort(RP.order.begin(), RP.order.end(),
+                [&](int32_t a, int32_t b2) { return claim_pos[mine[run_begin + a]] < claim_pos[mine[run_begin + b2]]; });
+    }
+  }
+}
+
+// Uploads a plan and launches its kernels on the context's stream.
+void run_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo* dist) {
+  pb_context* ctx = b->ctx;
+  PB_REQUIRE(c->pl.ctx == ctx, "canvas and brush belong to different contexts");
+  const bool multi = dist != nullptr && dist->world > 1;
+  PB_REQUIRE(multi == P.multi && (!multi || (dist->world == P.world && dist->rank == P.rank && dist->rows_per_band == P.rows_per_band)),
+             "batch plan was made for another band layout");
+  PB_REQUIRE(P.rows == c->rows && P.cols == c->cols && P.store_first == c->store_first && P.store_rows == c->pl.rows,
+             "batch plan was made for another canvas shape");
+  PB_REQUIRE(P.use_snapshot == b->use_snapshot, "batch plan was made with another snapshot-buffer setting");
+  for (int i = 0; i < PB_BATCH_STATS; ++i) b->stats[i] = P.stats[i];
+  if (b->use_snapshot || snapshot_matches(b, c)) ensure_snapshot(b, c);
+  ensure_work(b, c);
+  const bool have_dirty = b->dirty != nullptr && snapshot_matches(b, c);
+  PB_REQUIRE(!multi || (have_dirty && b->use_snapshot), "distributed strokes need the snapshot buffer enabled");
+  const std::vector<DevImprint>& im = P.im;
+  const Region& batch               = P.batch;
+  DevBuf<DevImprint> d_im(ctx, im.size());
+  d_im.upload(im.data(), im.size());
+
+  // completion flags: a per-batch buffer on one GPU, the brush's exported buffer + a fresh epoch across GPUs
+  DevBuf<long long> d_flags(ctx, multi ? 0 : P.n_mine + 1);
+  int epoch = 1;
+  if (multi) {
+    epoch = ++b->dist_epoch;
+  } else {
+    d_flags.zero(P.n_mine + 1);
+  }
+
+  // Single GPU: the kernels run on the record copy of the wet layer — convert the batch's region (stored rows, columns
+  // rounded to 4) on the way in and back on the way out. Multi GPU: the whole band is converted by pb_fbrush_dist_begin /
+  // _end around the batch (peers read each other's records, so every rank must be converted before any kernel starts).
+  Region conv{0, 0, -1, -1};
+  if (!multi && batch.x1 >= batch.x0 && batch.y1 >= batch.y0) {
+    conv.x0 = batch.x0 & ~3;
+    conv.x1 = std::min(c->cols - 1, batch.x1 | 3);
+    conv.y0 = std::max(batch.y0, c->store_first) - c->store_first;
+    conv.y1 = std::min(batch.y1, c->store_first + c->pl.rows - 1) - c->store_first;
+    planes_to_records(ctx, c->pl, b->work_rec, conv.x0, conv.y0, conv.x1, conv.y1);
+  }
+
+  for (const RunPlan& RP : P.runs) {
+    const size_t run_begin = RP.begin, n_run = RP.end - RP.begin;
+    const std::vector<DevStroke>& ds = RP.ds;
+    const std::vector<int2>& run_preds = RP.preds;
+    const std::vector<int32_t>& run_seg_off = RP.seg_off;
+    const std::vector<DevWindow>& run_windows = RP.windows;
+    const std::vector<int32_t>& run_order = RP.order;
+    const int max_active = RP.max_active;
+    const size_t max_window = RP.max_window;
     ImprintLaunch L{};
     L.n_bands = multi ? dist->world : 1;
     size_t smem = 0;
@@ -593,7 +673,7 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
       L.done[0]       = d_flags.p;
       L.rows_per_band = std::max(c->pl.rows, 1);
       L.my_band       = 0;
-      L.queue         = reinterpret_cast<int*>(d_flags.p + mine.size());
+      L.queue         = reinterpret_cast<int*>(d_flags.p + P.n_mine);
       if (run_begin > 0) PB_CUDA(cudaMemsetAsync(L.queue, 0, sizeof(int), ctx->stream));
     }
     L.own_canvas   = L.canvas[L.my_band];
@@ -615,13 +695,6 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     DevBuf<DevStroke> d_strokes(ctx, ds.size());
     DevBuf<int2> d_preds(ctx, run_preds.size());
     DevBuf<int32_t> d_seg_off(ctx, run_seg_off.size());
-    std::vector<int32_t> run_order;  // queue ticket -> stroke of this run
-    if (!claim_pos.empty()) {
-      run_order.resize(n_run);
-      for (size_t k = 0; k < n_run; ++k) run_order[k] = static_cast<int32_t>(k);
-      std::sort(run_order.begin(), run_order.end(),
-                [&](int32_t a, int32_t b2) { return claim_pos[mine[run_begin + a]] < claim_pos[mine[run_begin + b2]]; });
-    }
     DevBuf<int32_t> d_order(ctx, run_order.size());
     d_order.upload(run_order.data(), run_order.size());
     L.order = run_order.empty() ? nullptr : d_order.p;
@@ -651,6 +724,14 @@ void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs,
     b->snap_canvas_id      = c->id;
     b->snap_canvas_version = c->version;
   }
+}
+
+void run_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs, int64_t n_imprints, const double* cx,
+                  const double* cy, const double* theta, const DistInfo* dist = nullptr) {
+  if (hs.empty()) return;
+  pb_batch_plan P;
+  plan_imprints(b, c, hs, n_imprints, cx, cy, theta, dist, P);
+  run_plan(b, c, P, dist);
 }
 
 }  // namespace
@@ -1522,21 +1603,42 @@ int pb_fbrush_imprint_batch(pb_fbrush* b, pb_canvas* c, int64_t n, const double*
   PB_API_END
 }
 namespace {
-void stroke_batch_impl(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_stroke* strokes, int64_t n_imprints,
-                       const double* cx, const double* cy, const double* theta, const DistInfo* dist) {
-  if (n_strokes <= 0) return;
-  PB_REQUIRE(n_strokes < (int64_t(1) << 27), "too many strokes in one batch");
-  PB_REQUIRE(strokes != nullptr && n_imprints >= 0 && (n_imprints == 0 || (cx != nullptr && cy != nullptr && theta != nullptr)),
+DistInfo dist_info(const pb_canvas* c, const pb_dist_desc* d) {
+  PB_REQUIRE(d != nullptr && d->world >= 1 && d->world <= kMaxBands && d->rank >= 0 && d->rank < d->world, "invalid pb_dist_desc");
+  PB_REQUIRE(d->rows_per_band > 0 && c->halo == 0 && c->row_begin == d->rank * d->rows_per_band &&
+               c->row_end == std::min(c->rows, (d->rank + 1) * d->rows_per_band),
+             "canvas is not this rank's band of a rows_per_band partition");
+  DistInfo di;
+  di.world         = d->world;
+  di.rank          = d->rank;
+  di.rows_per_band = d->rows_per_band;
+  for (int r = 0; r < d->world; ++r) {
+    di.canvas_base[r]     = d->canvas_base[r];
+    di.canvas_stride[r]   = d->canvas_stride[r];
+    di.snapshot_base[r]   = d->snapshot_base[r];
+    di.snapshot_stride[r] = d->snapshot_stride[r];
+    di.dirty_base[r]      = static_cast<unsigned char*>(d->dirty_base[r]);
+    di.flags_base[r]      = static_cast<long long*>(d->flags_base[r]);
+  }
+  return di;
+}
+
+// dip -> setRadius -> paintStroke per stroke (SbrRenderThread.cxx:68-72), planned from the brush's current state
+void plan_stroke_batch(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_stroke* strokes, int64_t n_imprints, const double* cx,
+                       const double* cy, const double* theta, const DistInfo* dist, pb_batch_plan& P) {
+  PB_REQUIRE(n_strokes >= 0 && n_strokes < (int64_t(1) << 27), "too many strokes in one batch");
+  PB_REQUIRE(n_strokes == 0 || (strokes != nullptr && n_imprints >= 0 && (n_imprints == 0 || (cx != nullptr && cy != nullptr && theta != nullptr))),
              "stroke_batch: null stroke or imprint arrays");
   std::vector<HostStroke> hs(static_cast<size_t>(n_strokes));
   double radius            = b->radius;
   const FootprintGeom* cur = b->cur;
+  P.radius_before          = b->radius;
   for (int64_t s = 0; s < n_strokes; ++s) {
     const pb_stroke& in = strokes[s];
     PB_REQUIRE(in.first_imprint >= 0 && in.n_imprints >= 0 && in.first_imprint + in.n_imprints <= n_imprints,
                "stroke imprint range out of bounds");
     PB_REQUIRE(in.n_imprints < (int64_t(1) << 31), "too many imprints in one stroke");
-    // dip -> setRadius -> paintStroke (SbrRenderThread.cxx:68-72); setRadius only acts on a change >= 0.5
+    // setRadius only acts on a change >= 0.5
     if (!(std::fabs(radius - in.radius) < 0.5)) {
       radius          = in.radius;
       const int width = static_cast<int32_t>(2.0 * std::ceil(radius) + 1.0);
@@ -1556,14 +1658,30 @@ void stroke_batch_impl(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const pb_s
     h.n     = in.n_imprints;
     h.flags = 0;  // dip(): clean pickup map
   }
-  // brush state after the batch = state after the last stroke
-  brush_set_geometry(b, radius, cur);
-  for (int i = 0; i < 3; ++i) {
-    b->paintK[i] = strokes[n_strokes - 1].K[i];
-    b->paintS[i] = strokes[n_strokes - 1].S[i];
+  if (n_strokes > 0) {
+    hs.back().flags = 2;
+    // brush state after the batch = state after the last stroke
+    P.sets_state   = true;
+    P.radius_after = radius;
+    P.geom_after   = cur;
+    for (int i = 0; i < 3; ++i) {
+      P.K_after[i] = strokes[n_strokes - 1].K[i];
+      P.S_after[i] = strokes[n_strokes - 1].S[i];
+    }
   }
-  hs.back().flags = 2;
-  run_imprints(b, c, hs, n_imprints, cx, cy, theta, dist);
+  plan_imprints(b, c, hs, n_imprints, cx, cy, theta, dist, P);
+}
+
+void run_stroke_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo* dist) {
+  if (!P.sets_state) return;  // empty batch
+  // the stroke records depend on the radius the brush had when the plan was made (the 0.5 rule of setRadius)
+  PB_REQUIRE(b->radius == P.radius_before, "batch plan is stale: the brush radius changed since it was planned");
+  brush_set_geometry(b, P.radius_after, P.geom_after);
+  for (int i = 0; i < 3; ++i) {
+    b->paintK[i] = P.K_after[i];
+    b->paintS[i] = P.S_after[i];
+  }
+  run_plan(b, c, P, dist);
 }
 }  // namespace
 
@@ -1573,8 +1691,49 @@ int pb_fbrush_stroke_batch(pb_fbrush* b, pb_canvas* c, int64_t n_strokes, const 
   PB_REQUIRE(b != nullptr, "pb_fbrush_stroke_batch: null handle");
   PB_REQUIRE(c != nullptr, "pb_fbrush_stroke_batch: null handle");
   DeviceGuard g(b->ctx);
-  stroke_batch_impl(b, c, n_strokes, strokes, n_imprints, cx, cy, theta, nullptr);
+  if (n_strokes <= 0) return 0;
+  pb_batch_plan P;
+  plan_stroke_batch(b, c, n_strokes, strokes, n_imprints, cx, cy, theta, nullptr, P);
+  run_stroke_plan(b, c, P, nullptr);
   PB_API_END
+}
+int pb_fbrush_plan_stroke_batch(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* dist, int64_t n_strokes, const pb_stroke* strokes,
+                                int64_t n_imprints, const double* cx, const double* cy, const double* theta, pb_batch_plan** out) {
+  PB_API_BEGIN
+  PB_REQUIRE(b != nullptr && c != nullptr && out != nullptr, "pb_fbrush_plan_stroke_batch: null argument");
+  DeviceGuard g(b->ctx);
+  auto P = std::make_unique<pb_batch_plan>();
+  if (dist != nullptr) {
+    const DistInfo di = dist_info(c, dist);
+    plan_stroke_batch(b, c, n_strokes, strokes, n_imprints, cx, cy, theta, &di, *P);
+  } else {
+    plan_stroke_batch(b, c, n_strokes, strokes, n_imprints, cx, cy, theta, nullptr, *P);
+  }
+  *out = P.release();
+  PB_API_END
+}
+int pb_fbrush_run_batch_plan(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* dist, const pb_batch_plan* plan) {
+  PB_API_BEGIN
+  PB_REQUIRE(b != nullptr && c != nullptr && plan != nullptr, "pb_fbrush_run_batch_plan: null argument");
+  DeviceGuard g(b->ctx);
+  if (dist != nullptr) {
+    PB_REQUIRE(b->dist_flags != nullptr, "call pb_fbrush_dist_storage first");
+    const DistInfo di = dist_info(c, dist);
+    run_stroke_plan(b, c, *plan, &di);
+  } else {
+    run_stroke_plan(b, c, *plan, nullptr);
+  }
+  PB_API_END
+}
+int pb_batch_plan_destroy(pb_batch_plan* plan) {
+  delete plan;
+  return 0;
+}
+int pb_batch_plan_stats(const pb_batch_plan* plan, double out[PB_BATCH_STATS]) {
+  PB_CHECK_HANDLE(plan, "pb_batch_plan_stats");
+  PB_CHECK_HANDLE(out, "pb_batch_plan_stats");
+  for (int i = 0; i < PB_BATCH_STATS; ++i) out[i] = plan->stats[i];
+  return 0;
 }
 
 // ---- multi-GPU ---------------------------------------------------------------------------------------------
@@ -1658,24 +1817,12 @@ int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* 
   PB_REQUIRE(b != nullptr, "pb_fbrush_stroke_batch_dist: null handle");
   PB_REQUIRE(c != nullptr, "pb_fbrush_stroke_batch_dist: null handle");
   DeviceGuard g(b->ctx);
-  PB_REQUIRE(d != nullptr && d->world >= 1 && d->world <= kMaxBands && d->rank >= 0 && d->rank < d->world, "invalid pb_dist_desc");
-  PB_REQUIRE(d->rows_per_band > 0 && c->halo == 0 && c->row_begin == d->rank * d->rows_per_band &&
-               c->row_end == std::min(c->rows, (d->rank + 1) * d->rows_per_band),
-             "canvas is not this rank's band of a rows_per_band partition");
   PB_REQUIRE(b->dist_flags != nullptr, "call pb_fbrush_dist_storage first");
-  DistInfo di;
-  di.world         = d->world;
-  di.rank          = d->rank;
-  di.rows_per_band = d->rows_per_band;
-  for (int r = 0; r < d->world; ++r) {
-    di.canvas_base[r]     = d->canvas_base[r];
-    di.canvas_stride[r]   = d->canvas_stride[r];
-    di.snapshot_base[r]   = d->snapshot_base[r];
-    di.snapshot_stride[r] = d->snapshot_stride[r];
-    di.dirty_base[r]      = static_cast<unsigned char*>(d->dirty_base[r]);
-    di.flags_base[r]      = static_cast<long long*>(d->flags_base[r]);
-  }
-  stroke_batch_impl(b, c, n_strokes, strokes, n_imprints, cx, cy, theta, &di);
+  const DistInfo di = dist_info(c, d);
+  if (n_strokes <= 0) return 0;
+  pb_batch_plan P;
+  plan_stroke_batch(b, c, n_strokes, strokes, n_imprints, cx, cy, theta, &di, P);
+  run_stroke_plan(b, c, P, &di);
   PB_API_END
 }
 int pb_fbrush_enable_visited_count(pb_fbrush* b, int enable) {

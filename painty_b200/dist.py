@@ -69,16 +69,24 @@ class DistCanvas:
         self.dist.barrier()
         return d
 
-    def stroke_batch(self, brush, strokes, cx, cy, theta):
-        """Every rank passes the same global stroke list (submission order)."""
+    def plan(self, brush, strokes, cx, cy, theta):
+        """Host half of stroke_batch: every rank plans the same global stroke list (submission order). Touches no stream —
+        call it on a helper thread to overlap the planning of the next batch with the execution of the current one."""
         d = self._desc.get(id(brush)) or self.attach(brush)
-        strokes = np.ascontiguousarray(strokes, dtype=api.STROKE_DTYPE)
-        cx, cy, theta = api._f64(cx), api._f64(cy), api._f64(theta)
+        return brush.plan_stroke_batch(self.canvas, strokes, cx, cy, theta, dist_desc=d)
+
+    def stroke_batch(self, brush, strokes=None, cx=None, cy=None, theta=None, plan=None, after_launch=None):
+        """Every rank passes the same global stroke list (submission order), or a plan made from it by plan().
+        after_launch() runs once this rank's kernels are queued (e.g. to start planning the next batch)."""
+        d = self._desc.get(id(brush)) or self.attach(brush)
         lib = api.lib()
         api._chk(lib.pb_fbrush_dist_begin(brush.h, self.canvas.h))  # planes -> records of this band (synchronises the stream)
+        if plan is None:
+            plan = self.plan(brush, strokes, cx, cy, theta)
         self.dist.barrier()  # every band is ready (cleared / snapshot taken / converted) before any kernel touches peer rows
-        api._chk(lib.pb_fbrush_stroke_batch_dist(brush.h, self.canvas.h, C.byref(d), C.c_int64(len(strokes)),
-                                                 strokes.ctypes.data_as(_VP), C.c_int64(len(cx)), api._p(cx), api._p(cy), api._p(theta)))
+        brush.run_batch_plan(self.canvas, plan, dist_desc=d)
+        if after_launch is not None:
+            after_launch()
         self.ctx.synchronize()
         self.dist.barrier()  # all GPUs have finished writing into each other's bands
         api._chk(lib.pb_fbrush_dist_end(brush.h, self.canvas.h))  # records -> planes

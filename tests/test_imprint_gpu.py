@@ -225,6 +225,63 @@ def test_stroke_batch_matches_sequential_oracle(ctx32, ctx64, port, prec):
     assert br.counters() == bro.counters()
 
 
+def test_planned_batches_equal_direct_batches(ctx64):
+    """pb_fbrush_plan_stroke_batch + pb_fbrush_run_batch_plan == pb_fbrush_stroke_batch, also when the plan of the second
+    batch is made on another host thread while the first batch runs, and when one plan is run twice; a plan whose
+    radius assumption no longer holds is refused."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from painty_b200 import api
+
+    rows, cols = 300, 400
+    strokes = sbr_strokes(rows, cols, 60, seed=78, sizes=(60, 40, 30, 20), safe_radius=assets.snap_to_safe_radius)
+    rec = np.zeros(len(strokes), dtype=api.STROKE_DTYPE)
+    allx, ally, allt, first = [], [], [], 0
+    for i, s in enumerate(strokes):
+        cx, cy, th = api.expand_stroke(s["path"], mode=0)
+        rec[i] = (s["radius"], s["K"], s["S"], first, len(cx))
+        first += len(cx)
+        allx.append(cx), ally.append(cy), allt.append(th)
+    cx, cy, th = np.concatenate(allx), np.concatenate(ally), np.concatenate(allt)
+    radii = sorted(set(float(s["radius"]) for s in strokes))
+
+    def brush():
+        br = api.FootprintBrush(ctx64, radii[0])
+        for r in radii:
+            br.register_radius(r)
+        return br
+
+    cv1, br1 = api.Canvas(ctx64, rows, cols), brush()
+    br1.stroke_batch(cv1, rec, cx, cy, th)
+    br1.stroke_batch(cv1, rec, cx, cy, th)
+    want = cv1.download("KSV")
+    cv2, br2 = api.Canvas(ctx64, rows, cols), brush()
+    with ThreadPoolExecutor(1) as pool:
+        p1 = br2.plan_stroke_batch(cv2, rec, cx, cy, th)
+        assert p1.stats()["strokes_planned"] == len(rec)
+        br2.run_batch_plan(cv2, p1)
+        p2 = pool.submit(br2.plan_stroke_batch, cv2, rec, cx, cy, th).result()  # planned while batch 1 executes
+        br2.run_batch_plan(cv2, p2)
+    got = cv2.download("KSV")
+    for k in "KSV":
+        assert np.array_equal(got[k], want[k]), k
+    for x, y in zip(br2.getPickupMap(), br1.getPickupMap()):
+        assert np.array_equal(x, y)
+    cv3, br3 = api.Canvas(ctx64, rows, cols), brush()
+    br3.stroke_batch(cv3, rec[-1:], cx, cy, th)  # brings the brush to the radius batch 2 starts from
+    cv3.clear()
+    br3.updateSnapshot(cv3)  # like a fresh brush: snapshot == the blank canvas
+    p = br3.plan_stroke_batch(cv3, rec, cx, cy, th)
+    br3.run_batch_plan(cv3, p)
+    br3.run_batch_plan(cv3, p)  # same start radius (the batch ends on its last stroke's radius): the plan is reusable
+    got = cv3.download("KSV")
+    for k in "KSV":
+        assert np.array_equal(got[k], want[k]), k
+    br3.setRadius(radii[0] + 7.0)
+    with pytest.raises(api.PaintyError):
+        br3.run_batch_plan(cv3, p)
+
+
 def test_unsafe_radius_policy(ctx64, port):
     """Radii whose padded footprint is narrower than the pickup map (B#2): out-of-range footprint reads are
     height 0 — same policy in the oracle port and on the device."""
