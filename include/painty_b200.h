@@ -255,6 +255,11 @@ int pb_batch_plan_destroy(pb_batch_plan* plan);
 int pb_fbrush_batch_stats(const pb_fbrush* b, double out[PB_BATCH_STATS]);
 int pb_batch_plan_stats(const pb_batch_plan* plan, double out[PB_BATCH_STATS]);
 
+/* Diagnostics: SM cycle stamps (clock64) inside the imprint kernel for the first 256 imprints of the first stroke of each
+ * launch, taken by the first and the last thread of the stroke's first CTA: out[imprint][thread 0|1][8] =
+ * {imprint start, snapshot ring done, pickup/deposit done, next interaction list built, barrier passed, 0, 0, 0}. */
+int pb_fbrush_enable_trace(pb_fbrush* b, int enable);
+int pb_fbrush_read_trace(pb_fbrush* b, uint64_t* out /* 256*2*8 */);
 /* Stroke-pixel counters since creation: visited = the reference's `counter` (:119), cells passing both bounds
  * checks; active = those with footprint height > 0. `visited` is only maintained while counting is enabled
  * (it costs a pass over all footprint cells). */

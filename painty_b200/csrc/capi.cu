@@ -126,6 +126,7 @@ struct pb_fbrush {
   double pickup_rate = 0.9, deposition_rate = 0.05, capacity = 1.0;  // :477-495
   double paintK[3] = {0, 0, 0}, paintS[3] = {0, 0, 0};                // zero-initialised
   unsigned long long* d_counters = nullptr;                          // [0] active [1] visited
+  unsigned long long* d_trace    = nullptr;                          // diagnostics, pb_fbrush_enable_trace
   bool count_visited             = false;
   // host-side figures of the last stroke / imprint batch (pb_fbrush_batch_stats)
   double stats[PB_BATCH_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -715,6 +716,7 @@ void run_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo
     L.preds    = d_preds.p;
     L.seg_off  = d_seg_off.p;
     L.counters = b->d_counters;
+    L.trace    = b->d_trace;
     imprint_launch(ctx, L, smem);
     if (b->count_visited) imprint_count_visited(ctx, d_strokes.p, L.n_strokes, d_im.p, c->rows, c->cols, b->d_counters + 1);
   }
@@ -1467,6 +1469,7 @@ int pb_fbrush_destroy(pb_fbrush* b) {
     if (b->dirty) cudaFree(b->dirty);
     if (b->dist_flags) cudaFree(b->dist_flags);
     cudaFree(b->d_counters);
+    if (b->d_trace) cudaFree(b->d_trace);
     delete b;
   }
   PB_API_END
@@ -1823,6 +1826,28 @@ int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* 
   pb_batch_plan P;
   plan_stroke_batch(b, c, n_strokes, strokes, n_imprints, cx, cy, theta, &di, P);
   run_stroke_plan(b, c, P, &di);
+  PB_API_END
+}
+int pb_fbrush_enable_trace(pb_fbrush* b, int enable) {
+  PB_API_BEGIN
+  PB_REQUIRE(b != nullptr, "pb_fbrush_enable_trace: null handle");
+  DeviceGuard g(b->ctx);
+  const size_t bytes = sizeof(unsigned long long) * kTraceImprints * 2 * kTraceStamps;
+  PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  if (enable && b->d_trace == nullptr) PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->d_trace), bytes));
+  if (!enable && b->d_trace != nullptr) {
+    cudaFree(b->d_trace);
+    b->d_trace = nullptr;
+  }
+  if (b->d_trace) PB_CUDA(cudaMemset(b->d_trace, 0, bytes));
+  PB_API_END
+}
+int pb_fbrush_read_trace(pb_fbrush* b, uint64_t* out) {
+  PB_API_BEGIN
+  PB_REQUIRE(b != nullptr && out != nullptr && b->d_trace != nullptr, "pb_fbrush_read_trace: tracing is not enabled");
+  DeviceGuard g(b->ctx);
+  PB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  PB_CUDA(cudaMemcpy(out, b->d_trace, sizeof(unsigned long long) * kTraceImprints * 2 * kTraceStamps, cudaMemcpyDeviceToHost));
   PB_API_END
 }
 int pb_fbrush_enable_visited_count(pb_fbrush* b, int enable) {

@@ -667,12 +667,17 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
       // the list of the next unit (geometry only, so the one that starts the next imprint is built before the barrier),
       // and synchronise whenever the next unit starts a new phase or imprint. One build site, one process site.
       const int chunks = max((my_cells + L.chunk_cells - 1) / L.chunk_cells, 1);
+      const bool tracing = L.trace != nullptr && si == 0 && crank == 0 && (tid == 0 || tid == bd - 1);
+      auto stamp = [&](int i, int slot) {
+        if (tracing && i < kTraceImprints) L.trace[(i * 2 + (tid != 0 ? 1 : 0)) * kTraceStamps + slot] = clock64();
+      };
       int ii = 0, ph = first_phase(0), chunk = 0;
       int n_list = build_list(0, 0, ph);
       bool need_full = true, imprint_start = true;
       int seg_k = 0, seg_next = st.seg_len;  // next segment boundary (imprint index)
       for (;;) {
         if (imprint_start) {
+          stamp(ii, 0);
           if (ii == seg_next) {
             ++seg_k;
             seg_next += st.seg_len;
@@ -707,8 +712,11 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
             if (two_phase) sync_all();
           }
           imprint_start = false;
+          stamp(ii, 1);
         }
+        const int ii_now = ii;
         process(n_list, chunk);
+        stamp(ii_now, 2);
         // next unit; left/top overhang: canvas pixels of column/row 0 can be hit twice (B#11) -> 4 ordered phases
         bool barrier = false, done = false;
         if (chunk + 1 < chunks) {
@@ -727,10 +735,12 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
           }
         }
         if (!done) n_list = build_list(ii, chunk, ph);
+        stamp(ii_now, 3);
         if (barrier) {
           if (tid < 4) cp_async_wait_all();
           sync_all();
         }
+        stamp(ii_now, 4);
         if (done) break;
       }
       if (wins) {

@@ -22,6 +22,7 @@ struct FootprintGeom {
 };
 
 constexpr int kMaxBands = 8;  // GPUs of one NVSwitch node
+constexpr int kTraceImprints = 256, kTraceStamps = 8;
 constexpr int kStrokeDone = 0x7fffffff;  // progress value of a finished stroke
 
 // DevStroke::flags
@@ -95,6 +96,9 @@ struct ImprintLaunch {
   int* queue;                    // single counter (zeroed): tickets
   const int32_t* order;          // ticket -> stroke of this launch (host-planned claim order); nullptr = identity
   unsigned long long* counters;  // [0] active stroke-pixels
+  // diagnostics (pb_fbrush_enable_trace): SM cycle stamps of the first kTraceImprints imprints of stroke 0 of the launch,
+  // taken by the first and the last thread of the cluster's rank-0 CTA: [imprint][thread][kTraceStamps]; nullptr = off
+  unsigned long long* trace;
   unsigned char* win_scratch;    // staging windows, win_stride bytes per stroke slot (two halves, one per window)
   int64_t win_stride;
   // per-CTA cell state in global memory for footprints that do not fit shared memory
