@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstring>
 #include <memory>
 #include <type_traits>
 #include <vector>
@@ -31,6 +32,8 @@ class Canvas final {
     Mat<vector_type> R0;
     Mat<T> h;
     bool host_valid = false, device_valid = true;
+    bool host_access = false;    // a mutable reference to R0 / h has been handed out (see PaintLayer.hxx, "Held references")
+    std::vector<double> shadow;  // R0 | h as of the last synchronisation
     ~State() {
       if (handle) pb_canvas_destroy(handle);
     }
@@ -55,23 +58,27 @@ class Canvas final {
 
   void clear() {  // reference :37-58
     b200::check(pb_canvas_clear(_s->handle));
-    _paintLayer.deviceWritten();
-    _s->host_valid   = false;
-    _s->device_valid = true;
+    deviceWritten();
     std::fill(_timeMap.begin(), _timeMap.end(), std::chrono::system_clock::now());
   }
 
   const Mat<vector_type>& getR0() const { return toHost(), _s->R0; }
   const Mat<T>& get_h() const { return toHost(), _s->h; }
-  Mat<vector_type>& getR0() { return toHost(), _s->device_valid = false, _s->R0; }
-  Mat<T>& get_h() { return toHost(), _s->device_valid = false, _s->h; }
+  Mat<vector_type>& getR0() { return hostAccess(), _s->R0; }
+  Mat<T>& get_h() { return hostAccess(), _s->h; }
+  /** Leave host-access mode of the canvas and its wet layer (see PaintLayer.hxx, "Held references"). */
+  void endHostAccess() {
+    device();
+    _paintLayer.endHostAccess();
+    _s->host_access = false;
+    _s->shadow.clear();
+    _s->shadow.shrink_to_fit();
+  }
   Mat<vector_type> getReflectanceLayerDry() const { return getR0().clone(); }
 
   void setBackground(const Mat<vector_type>& background) {  // reference :80-87
     b200::check(pb_canvas_set_background(_s->handle, reinterpret_cast<const double*>(background.data)));
-    _paintLayer.deviceWritten();
-    _s->host_valid   = false;
-    _s->device_valid = true;
+    deviceWritten();
   }
 
   const PaintLayer<vector_type>& getPaintLayer() const { return _paintLayer; }
@@ -120,10 +127,12 @@ class Canvas final {
   /** Device handle with pending host edits (wet layer, R0, h) uploaded. */
   pb_canvas* device() const {
     _paintLayer.device();
+    if (_s->host_access && _s->host_valid && differsFromShadow()) _s->device_valid = false;  // written through a held reference
     if (!_s->device_valid) {
       b200::check(pb_canvas_upload_substrate(_s->handle, reinterpret_cast<const double*>(_s->R0.data),
                                              reinterpret_cast<const double*>(_s->h.data)));
       _s->device_valid = true;
+      if (_s->host_access) snapshotShadow();
     }
     return _s->handle;
   }
@@ -131,9 +140,33 @@ class Canvas final {
     _paintLayer.deviceWritten();
     _s->host_valid   = false;
     _s->device_valid = true;
+    if (_s->host_access) {
+      toHost();
+      snapshotShadow();
+    }
   }
 
  private:
+  void hostAccess() {
+    toHost();
+    if (!_s->host_access) {
+      _s->host_access = true;
+      snapshotShadow();
+    }
+  }
+  size_t pixels() const { return static_cast<size_t>(pb_canvas_rows(_s->handle)) * static_cast<size_t>(pb_canvas_cols(_s->handle)); }
+  void snapshotShadow() const {
+    const size_t n = pixels();
+    _s->shadow.resize(4 * n);
+    std::memcpy(_s->shadow.data(), _s->R0.data, 3 * n * sizeof(double));
+    std::memcpy(_s->shadow.data() + 3 * n, _s->h.data, n * sizeof(double));
+  }
+  bool differsFromShadow() const {
+    const size_t n = pixels();
+    if (_s->shadow.size() != 4 * n) return true;
+    return std::memcmp(_s->shadow.data(), _s->R0.data, 3 * n * sizeof(double)) != 0 ||
+           std::memcmp(_s->shadow.data() + 3 * n, _s->h.data, n * sizeof(double)) != 0;
+  }
   void toHost() const {
     if (_s->host_valid) return;
     const int32_t r = pb_canvas_rows(_s->handle), c = pb_canvas_cols(_s->handle);

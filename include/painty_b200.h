@@ -176,8 +176,12 @@ int pb_lanczos4_taps(int src, int dst, int32_t* offsets, float* weights);
  * Cook-Torrance, the wet layer's thickness as height field, 5-tap BORDER_REFLECT normal) fused in one kernel; host
  * AoS f64 out, clamped to [0,1] like the reference. Full canvases only (the stencil needs the neighbouring rows). */
 int pb_canvas_render(pb_canvas* c, double* out);
-/* Device plane pointers (element type of the context): 0-2 K, 3-5 S, 6 V, 7-9 R0, 10 h. */
+/* Device plane pointers (element type of the context): 0-2 K, 3-5 S, 6 V, 7-9 R0, 10 h. The pointers are writable, so
+ * handing them out counts as a modification of the wet layer (a footprint brush then treats its snapshot bookkeeping as
+ * out of date, exactly as after clear / dry / upload). A host that keeps the pointers and writes through them LATER must
+ * call pb_canvas_mark_modified before the next brush operation. */
 int pb_canvas_device_planes(pb_canvas* c, void* planes[11], int64_t* elems_per_plane);
+int pb_canvas_mark_modified(pb_canvas* c);
 int pb_canvas_stored_rows(const pb_canvas* c, int* first_row, int* n_rows);
 /* Canvas::getPaintLayer(): a non-owning pb_layer aliasing the canvas' wet planes (destroy with pb_layer_destroy;
  * it must not outlive the canvas). */

@@ -1393,6 +1393,12 @@ int pb_canvas_device_planes(pb_canvas* c, void* planes[11], int64_t* elems_per_p
   PB_CHECK_HANDLE(c, "pb_canvas_device_planes");
   for (int p = 0; p < kCanvasPlanes; ++p) planes[p] = c->pl.plane(p);
   if (elems_per_plane) *elems_per_plane = c->pl.n();
+  c->version++;  // the pointers are writable: brushes must assume the wet layer changed
+  return 0;
+}
+int pb_canvas_mark_modified(pb_canvas* c) {
+  PB_CHECK_HANDLE(c, "pb_canvas_mark_modified");
+  c->version++;
   return 0;
 }
 
@@ -1770,6 +1776,7 @@ int pb_canvas_storage(pb_canvas* c, void** base, int64_t* plane_stride_bytes) {
   PB_CHECK_HANDLE(c, "pb_canvas_storage");
   if (base) *base = c->pl.base;
   if (plane_stride_bytes) *plane_stride_bytes = static_cast<int64_t>(c->pl.stride);
+  c->version++;  // writable pointer handed out
   return 0;
 }
 int pb_fbrush_dist_storage(pb_fbrush* b, pb_canvas* c, void** canvas_records, void** snapshot_records, void** dirty_base,

@@ -187,6 +187,34 @@ int main(int argc, char** argv) {
     for (const auto& p : dried) sum2 += p[0] + p[1] + p[2];
     EXPECT(std::fabs(sum2 - sum) < 1.0);  // drying moves the paint into the substrate, the picture stays
   }
+  {  // held references (the reference's callers keep `auto& v = layer.getV_buffer()` across operations): reads through a
+     // held mutable reference stay current after device work, writes through it reach the device
+    painty::Canvas<painty::vec3> canvas(120, 160);
+    auto& V = canvas.getPaintLayer().getV_buffer();
+    auto& K = canvas.getPaintLayer().getK_buffer();
+    auto& S = canvas.getPaintLayer().getS_buffer();
+    auto& R0 = canvas.getR0();
+    EXPECT(V(60, 80) == 0.0);
+    painty::TextureBrush<painty::vec3> brush("data/sample_0");
+    brush.enableSmudge(false);
+    brush.setRadius(20.0);
+    brush.dip({painty::vec3(.2, .3, .4), painty::vec3(.1, .23, .14)});
+    brush.paintStroke({{20, 60}, {80, 62}, {140, 58}}, canvas);
+    double wet = 0.0;
+    for (int x = 0; x < 160; ++x) wet += V(60, x);
+    EXPECT(wet > 0.0);  // the held reference sees what the kernel wrote
+    V(5, 5)  = 0.5;     // a write through the held reference, after a device operation
+    K(5, 5)  = painty::vec3(1.0, 2.0, 3.0);
+    S(5, 5)  = painty::vec3(0.5, 0.5, 0.5);
+    R0(6, 6) = painty::vec3(0.25, 0.5, 0.75);
+    const auto rgb = painty::Renderer<painty::vec3>().compose(canvas);
+    const auto want = painty::ComputeReflectance(painty::vec3(1.0, 2.0, 3.0), painty::vec3(0.5, 0.5, 0.5), painty::vec3(1.0, 1.0, 1.0), 0.5);
+    EXPECT(std::fabs(rgb(5, 5)[0] - want[0]) < 1e-4 && std::fabs(rgb(5, 5)[2] - want[2]) < 1e-4);
+    EXPECT(std::fabs(rgb(6, 6)[1] - 0.5) < 1e-6);
+    canvas.dryCanvas();
+    EXPECT(V(5, 5) == 0.0 && std::fabs(R0(5, 5)[0] - want[0]) < 1e-4);  // mirrors refreshed behind the held references
+    canvas.endHostAccess();
+  }
   {  // the drop-in under the reference's own name and constructor (SbrRenderThread.hxx:19-74): a GpuTaskQueue pointer is
      // accepted and ignored; brush textures come from a dictionary folder (file names <size>_<lengthClass>_<nn>.png,
      // TextureBrushDictionary.cxx:81-118), one texture per stroke picked by (stroke length, 2 * radius)
