@@ -1,19 +1,21 @@
-"""Row-band sharding of a canvas over the GPUs of one node (one process per GPU, torch.distributed).
+"""Row-band sharding of a canvas over the GPUs of one node (one process per GPU): host-side routing helpers.
 
 What shards, and how exactly:
 
-* KM compose / dry: independent pixels -> every rank composes its own rows, no exchange. The final image is
-  assembled with one all_gather of the 3 reflectance planes of each band (NCCL over NVLink; gloo on CPU in tests).
+* KM compose / dry: independent pixels -> every rank composes its own rows, no exchange. The final image is assembled by
+  the compose kernel itself: `pb_canvas_compose_gather` stores the band's reflectance rows straight into the destination
+  ranks' images over NVLink peer mappings (`painty_b200/dist.py: DistCanvas.compose_gather`); `gather_bands` below is the
+  torch.distributed collective used by the CPU (gloo) tests of the host logic.
 * Texture-brush strokes (no smudge): a pixel's result depends only on the earlier strokes that cover that pixel, so a
   rank applies — in submission order — every stroke whose bounding box meets its band; the kernel clips to the
   stored rows. No halo, no exchange, bit-identical to the single-canvas result (`route_texture_strokes`).
-* Footprint-brush strokes carry state along the whole stroke (pickup map, snapshot buffer), so a stroke must be
-  executed entirely by one rank on exact data. `route_footprint_strokes` assigns every stroke to the rank that owns
-  its first imprint and reports which strokes cross a band boundary ("straddlers"). Strokes confined to their band
-  (region = imprint centres +- (wr + radius + 2)) need no exchange and are exact; the round-1 multi-GPU bench uses
-  such band-confined workloads (weak scaling). Straddlers need the owner's rows pulled before / pushed after the
-  stroke (wave-synchronous halo exchange) — planned for the next round; `stroke_levels` already computes the
-  wave index (dataflow level) that scheme needs.
+* Footprint-brush strokes carry state along the whole stroke (pickup map, snapshot buffer), so a stroke is executed
+  entirely by the rank that owns its first imprint. The routing and the cross-GPU dataflow live in the library
+  (`pb_fbrush_stroke_batch_dist`, csrc/capi.cu + csrc/imprint.cu): strokes that leave their band ("straddlers") stage the
+  neighbour rows of each 64-imprint dataflow segment in local windows (pulled and pushed over NVLink per segment) or access
+  them directly through peer mappings; stroke order across GPUs is kept by progress words polled through peer memory.
+  `route_footprint_strokes` / `stroke_levels` restate that routing rule on the host for the CPU tests
+  (tests/test_bands_cpu.py); the product path does not call them.
 
 Nothing here touches a GPU: it is host-side planning, testable with the gloo backend.
 """

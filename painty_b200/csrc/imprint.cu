@@ -256,54 +256,121 @@ __device__ __noinline__ int3 hits_exact_cold(const DevImprint* imprints, int64_t
 // pixels) and copies just those. The rectangles to scan come from ring_rects (imprint_geom.hpp): the whole ring, or
 // only what entered it since the previous imprint. Items (words) are numbered across the rectangles; a thread takes
 // items t0, t0 + stride, ...
-template <typename T, bool VIEWS>
-__device__ __forceinline__ void ring_word(const ImprintLaunch& L, const Band<T>* views, const RingGeom& g, int row, int w,
-                                          unsigned word) {
-  const int band = VIEWS ? band_of(L, row) : 0;
-  const int lrow = VIEWS ? row - band * L.rows_per_band : row - L.store_first;
-  const Band<T> C = band_view<T, VIEWS>(L, views, band);
-  const int rbase = lrow * C.pitch;
-#pragma unroll 1
-  for (int b = 0; b < 4; ++b) {
-    const int f = 4 * w + b;  // flat pixel index == dirty byte index
-    if (((word >> (8 * b)) & 0xffu) == 0u || !in_ring(g, row, f - rbase)) continue;
-    st_rec(C.src + static_cast<int64_t>(f) * kRecord, ld_rec(C.can + static_cast<int64_t>(f) * kRecord));
-    __stcg(C.dirty + f, static_cast<unsigned char>(0));
-    if (VIEWS && C.touched) __stcg(C.touched + f, static_cast<unsigned char>(1));
-  }
+// Items (words) are numbered across the rectangles; a thread takes items t0, t0 + stride, ... in BATCHES of kRingBatch: the
+// dirty words of a batch are loaded together, then the dirty ring pixels among them are copied four records at a time
+// (kRingCopy loads in flight, then the stores) — the pass costs a thread a few L2 round trips per batch instead of one
+// per word plus one per copied pixel.
+constexpr int kRingBatch = 4;
+constexpr int kRingCopy  = 2;  // records in flight while copying (register budget of the 512-thread CTAs)
+struct RingCtx {
+  int rows_per_band, my_band, store_first, pitch;
+};
+__device__ __forceinline__ int ring_band_of(const RingCtx& X, int row) {
+  const int b0 = X.my_band * X.rows_per_band;
+  return (row >= b0 && row < b0 + X.rows_per_band) ? X.my_band : row / X.rows_per_band;
 }
-
 template <typename T, bool VIEWS>
-__device__ __forceinline__ void ring_scan(const ImprintLaunch& L, const Band<T>* views, const RingGeom& g, const RingGeom* prev,
-                                          int t0, int stride) {
-  // the rectangle list is small and indexed dynamically below: it lives in local memory (L1), which keeps the scan
-  // loop — instantiated once — out of the emit sites of ring_rects
+__device__ __forceinline__ void ring_scan(T* own_can, T* own_src, unsigned char* own_dirty, const Band<T>* views, const RingCtx X,
+                                       const RingGeom g, const RingGeom prev, const bool has_prev, int t0, int stride) {
+  // the rectangle list is small and indexed dynamically below: it lives in local memory (L1)
   Rect rl[8];
-  int n_rects = 0;
-  ring_rects(g, prev, [&](const Rect& r) {
-    if (n_rects < 8) rl[n_rects++] = r;
+  int n_rects = 0, total = 0;
+  ring_rects(g, has_prev ? &prev : nullptr, [&](const Rect& r) {
+    if (n_rects < 8) {
+      rl[n_rects++] = r;
+      total += (r.y1 - r.y0 + 1) * rect_words(r);
+    }
   });
-  int t = t0;  // next item of this thread, relative to the current rectangle
 #pragma unroll 1
-  for (int ri = 0; ri < n_rects; ++ri) {
-    const Rect r = rl[ri];
-    const int nw = rect_words(r), cnt = (r.y1 - r.y0 + 1) * nw;
-    if (t < cnt) {
-      const float inv = __frcp_rn(static_cast<float>(nw));
+  for (int base = t0; base < total; base += kRingBatch * stride) {
+    int row[kRingBatch], w[kRingBatch];
+    unsigned word[kRingBatch];
+#pragma unroll
+    for (int q = 0; q < kRingBatch; ++q) {
+      int t   = base + q * stride;
+      word[q] = 0u, row[q] = 0, w[q] = 0;
+      if (t < total) {
+        int ri = 0, nw = rect_words(rl[0]), cnt = (rl[0].y1 - rl[0].y0 + 1) * nw;
 #pragma unroll 1
-      for (; t < cnt; t += stride) {
-        int row, j;
-        rect_item(r, nw, inv, t, row, j);
-        const int band = VIEWS ? band_of(L, row) : 0;
-        const int lrow = VIEWS ? row - band * L.rows_per_band : row - L.store_first;
-        const unsigned char* dbase = VIEWS ? views[band].dirty : L.own_dirty;
-        const int pitch            = VIEWS ? views[band].pitch : L.cols;
-        const int w                = ((lrow * pitch + r.x0) >> 2) + j;
-        const unsigned word        = __ldcg(reinterpret_cast<const unsigned*>(dbase) + w);
-        if (word != 0u) ring_word<T, VIEWS>(L, views, g, row, w, word);
+        while (t >= cnt) {  // t < total: ends inside the list
+          t -= cnt;
+          ++ri;
+          nw  = rect_words(rl[ri]);
+          cnt = (rl[ri].y1 - rl[ri].y0 + 1) * nw;
+        }
+        const Rect r = rl[ri];
+        int j;
+        rect_item(r, nw, __frcp_rn(static_cast<float>(nw)), t, row[q], j);
+        int lrow = row[q] - X.store_first, pitch = X.pitch;
+        const unsigned char* dbase = own_dirty;
+        if (VIEWS) {
+          const int band = ring_band_of(X, row[q]);
+          lrow           = row[q] - band * X.rows_per_band;
+          pitch          = views[band].pitch;
+          dbase          = views[band].dirty;
+        }
+        w[q]    = ((lrow * pitch + r.x0) >> 2) + j;
+        word[q] = __ldcg(reinterpret_cast<const unsigned*>(dbase) + w[q]);
       }
     }
-    t -= cnt;
+    // dirty ring pixels of the batch: bit 4 * q + b = byte b of word q
+    unsigned todo = 0u;
+#pragma unroll
+    for (int q = 0; q < kRingBatch; ++q) {
+      if (word[q] == 0u) continue;
+      int lrow = row[q] - X.store_first, pitch = X.pitch;
+      if (VIEWS) {
+        const int band = ring_band_of(X, row[q]);
+        lrow           = row[q] - band * X.rows_per_band;
+        pitch          = views[band].pitch;
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (((word[q] >> (8 * b)) & 0xffu) != 0u && in_ring(g, row[q], 4 * w[q] + b - lrow * pitch)) todo |= 1u << (4 * q + b);
+      }
+    }
+#pragma unroll 1
+    while (todo) {
+      Rec<T> rec[kRingCopy];
+      int f[kRingCopy], bnd[kRingCopy];
+#pragma unroll
+      for (int k = 0; k < kRingCopy; ++k) {
+        f[k] = -1, bnd[k] = 0;
+        if (todo) {
+          const int bit = __ffs(static_cast<int>(todo)) - 1;
+          todo &= todo - 1u;
+          const int q = bit >> 2;
+          int wq = w[0], rq = row[0];  // select w[q], row[q] without dynamic register indexing
+#pragma unroll
+          for (int z = 1; z < kRingBatch; ++z) {
+            if (q == z) wq = w[z], rq = row[z];
+          }
+          f[k]         = 4 * wq + (bit & 3);
+          const T* can = own_can;
+          if (VIEWS) {
+            bnd[k] = ring_band_of(X, rq);
+            can    = views[bnd[k]].can;
+          }
+          rec[k] = ld_rec(can + static_cast<int64_t>(f[k]) * kRecord);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kRingCopy; ++k) {
+        if (f[k] >= 0) {
+          T* src                 = own_src;
+          unsigned char* dirty   = own_dirty;
+          unsigned char* touched = nullptr;
+          if (VIEWS) {
+            src     = views[bnd[k]].src;
+            dirty   = views[bnd[k]].dirty;
+            touched = views[bnd[k]].touched;
+          }
+          st_rec(src + static_cast<int64_t>(f[k]) * kRecord, rec[k]);
+          __stcg(dirty + f[k], static_cast<unsigned char>(0));
+          if (VIEWS && touched) __stcg(touched + f[k], static_cast<unsigned char>(1));
+        }
+      }
+    }
   }
 }
 
@@ -437,6 +504,18 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
     if (MULTI && remote) __threadfence_system();
     if (CL) {
       cluster.sync();
+    } else {
+      __syncthreads();
+    }
+  };
+  // the same barrier in two halves: arrive (release: this thread's stores) ... independent work ... wait (acquire)
+  auto sync_arrive = [&]() {
+    if (MULTI && remote) __threadfence_system();
+    if (CL) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  };
+  auto sync_wait = [&]() {
+    if (CL) {
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     } else {
       __syncthreads();
     }
@@ -702,11 +781,14 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
                        reinterpret_cast<const char*>(L.imprints + st.first_imprint + ii + 2) + 16 * tid);
           if (L.use_snapshot) {
             const int rt_local = tid - (bd - L.ring_threads);
+            const RingCtx X{L.rows_per_band, L.my_band, L.store_first, L.cols};
+            T* const oc = static_cast<T*>(L.own_canvas);
+            T* const os = static_cast<T*>(L.own_snapshot);
             if (two_phase || need_full) {
-              ring_scan<T, VIEWS>(L, views, geom_of(ii), nullptr, scan_id(), scan_stride());
+              ring_scan<T, VIEWS>(oc, os, L.own_dirty, views, X, geom_of(ii), RingGeom{}, false, scan_id(), scan_stride());
             } else if (rt_local >= 0) {
-              const RingGeom prev = geom_of(ii - 1);
-              ring_scan<T, VIEWS>(L, views, geom_of(ii), &prev, crank * L.ring_threads + rt_local, csize * L.ring_threads);
+              ring_scan<T, VIEWS>(oc, os, L.own_dirty, views, X, geom_of(ii), geom_of(ii - 1), true,
+                                  crank * L.ring_threads + rt_local, csize * L.ring_threads);
             }
             need_full = false;
             if (two_phase) sync_all();
@@ -734,12 +816,15 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
             done = true;
           }
         }
-        if (!done) n_list = build_list(ii, chunk, ph);
-        stamp(ii_now, 3);
+        // the barrier's latency (store acknowledgements, arrival of the other CTAs) overlaps building the next list,
+        // which depends on no pixel data
         if (barrier) {
           if (tid < 4) cp_async_wait_all();
-          sync_all();
+          sync_arrive();
         }
+        if (!done) n_list = build_list(ii, chunk, ph);
+        stamp(ii_now, 3);
+        if (barrier) sync_wait();
         stamp(ii_now, 4);
         if (done) break;
       }
