@@ -66,6 +66,13 @@ int pb_paint_mix_single(int n, const double* baseK, const double* baseS, int n_w
 int pb_expand_stroke(int mode, int n, const double* path_xy, int64_t capacity, double* cx, double* cy, double* theta,
                      int64_t* n_imprints);
 
+/* The same for a list of strokes (stroke s = vertices [first_vertex[s], first_vertex[s] + n_vertices[s]) of path_xy): imprints are
+ * written back to back, first_imprint[s] / n_imprints[s] (either may be NULL) receive every stroke's range and *total the
+ * overall count. Call with capacity 0 to size. */
+int pb_expand_stroke_batch(int mode, int64_t n_strokes, const int64_t* first_vertex, const int32_t* n_vertices, const double* path_xy,
+                           int64_t capacity, double* cx, double* cy, double* theta, int64_t* first_imprint, int64_t* n_imprints,
+                           int64_t* total);
+
 /* Host-side dataflow planner used by the stroke batches (no device needed; exposed for testing and for hosts that
  * want to inspect the schedule). Strokes are given in submission order by two inclusive pixel rectangles
  * (x0,y0,x1,y1): `box` = what the stroke modifies, `allowed` = what it may read or refresh (for a texture stroke pass

@@ -114,6 +114,21 @@ def expand_stroke(path, mode=0):
     return cx, cy, th
 
 
+def expand_strokes(first_vertex, n_vertices, path_xy, mode=0):
+    """Batch form of expand_stroke: -> (cx, cy, theta, first_imprint[n], n_imprints[n])."""
+    fv = np.ascontiguousarray(first_vertex, dtype=np.int64)
+    nv = np.ascontiguousarray(n_vertices, dtype=np.int32)
+    path_xy = _f64(path_xy).reshape(-1, 2)
+    n = len(fv)
+    fi, ni, total = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64), C.c_int64(0)
+    args = (mode, C.c_int64(n), fv.ctypes.data_as(_VP), nv.ctypes.data_as(_VP), _p(path_xy))
+    _chk(lib().pb_expand_stroke_batch(*args, C.c_int64(0), None, None, None, None, None, C.byref(total)))
+    cx, cy, th = np.empty(total.value), np.empty(total.value), np.empty(total.value)
+    _chk(lib().pb_expand_stroke_batch(*args, C.c_int64(total.value), _p(cx), _p(cy), _p(th), fi.ctypes.data_as(_VP),
+                                      ni.ctypes.data_as(_VP), C.byref(total)))
+    return cx, cy, th, fi, ni
+
+
 def plan_dependencies(rows, cols, box, allowed):
     """Host-side dataflow plan: (offsets[n+1], preds) CSR of the strokes each stroke has to wait for."""
     box = np.ascontiguousarray(box, dtype=np.int32).reshape(-1, 4)

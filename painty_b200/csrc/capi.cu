@@ -837,6 +837,31 @@ int pb_expand_stroke(int mode, int n, const double* path_xy, int64_t capacity, d
   PB_API_END
 }
 
+int pb_expand_stroke_batch(int mode, int64_t n_strokes, const int64_t* first_vertex, const int32_t* n_vertices, const double* path_xy,
+                           int64_t capacity, double* cx, double* cy, double* theta, int64_t* first_imprint, int64_t* n_imprints,
+                           int64_t* total) {
+  PB_API_BEGIN
+  PB_REQUIRE(mode == 0 || mode == 1, "pb_expand_stroke_batch: mode must be 0 (library) or 1 (GUI)");
+  PB_REQUIRE(n_strokes >= 0 && (n_strokes == 0 || (first_vertex && n_vertices && path_xy)), "pb_expand_stroke_batch: null arrays");
+  int64_t at = 0;
+  std::vector<host::Imprint> out;
+  for (int64_t s = 0; s < n_strokes; ++s) {
+    out.clear();
+    host::expand_stroke(mode, reinterpret_cast<const host::V2*>(path_xy) + first_vertex[s], n_vertices[s], out);
+    if (first_imprint) first_imprint[s] = at;
+    if (n_imprints) n_imprints[s] = static_cast<int64_t>(out.size());
+    for (size_t i = 0; i < out.size(); ++i, ++at) {
+      if (at < capacity) {
+        cx[at]    = out[i].cx;
+        cy[at]    = out[i].cy;
+        theta[at] = out[i].theta;
+      }
+    }
+  }
+  if (total) *total = at;
+  PB_API_END
+}
+
 int pb_plan_dependencies(int rows, int cols, int64_t n, const int32_t* box, const int32_t* allowed, int64_t* offsets,
                          int64_t capacity, int32_t* preds, int64_t* n_preds) {
   PB_API_BEGIN
