@@ -511,11 +511,11 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
   // the same barrier in two halves: arrive (release: this thread's stores) ... independent work ... wait (acquire)
   auto sync_arrive = [&]() {
     if (MULTI && remote) __threadfence_system();
-    if (CL) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (CL) asm volatile("barrier.cluster.arrive.release;" ::: "memory");
   };
   auto sync_wait = [&]() {
     if (CL) {
-      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
     } else {
       __syncthreads();
     }
