@@ -962,7 +962,7 @@ void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& sme
   }
   L.cta_cells    = cta_cells;
   L.chunk_cells  = chunk;
-  L.ring_threads = std::min(block, 64);
+  L.ring_threads = std::min(block, std::max(32, env_int("PB_RING_THREADS", 64) / 32 * 32));
   L.block        = block;
   L.cluster      = cluster;
   // occupancy queries and attribute changes cost milliseconds: do them once per launch shape
