@@ -261,8 +261,10 @@ int pb_batch_plan_destroy(pb_batch_plan* plan);
 /* Host-side figures of the brush's last stroke or imprint batch (no device access):
  * [0] dataflow planning ms (segments + claim order), [1] per-imprint constants ms, [2] strokes planned (all ranks),
  * [3] dataflow segments, [4] wait entries, [5] the planner's model of the batch duration in ms (0 if the queue order
- * was not planned), [6] strokes executed by this rank, [7] kernel launches of this rank. */
-#define PB_BATCH_STATS 8
+ * was not planned), [6] strokes executed by this rank, [7] kernel launches of this rank, [8] / [9] / [10] resident
+ * thread-block clusters (= concurrent strokes, cudaOccupancyMaxActiveClusters) of this rank's launch shapes for footprints
+ * of <= 256 / <= 4096 / more active cells (0 where the batch has none), [11] threads per cluster of the largest shape. */
+#define PB_BATCH_STATS 12
 int pb_fbrush_batch_stats(const pb_fbrush* b, double out[PB_BATCH_STATS]);
 int pb_batch_plan_stats(const pb_batch_plan* plan, double out[PB_BATCH_STATS]);
 

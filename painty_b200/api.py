@@ -505,10 +505,9 @@ class FootprintBrush:
 
     def batch_stats(self):
         """Host-side figures of the last stroke / imprint batch (pb_fbrush_batch_stats)."""
-        out = (C.c_double * 8)()
+        out = (C.c_double * 12)()
         _chk(lib().pb_fbrush_batch_stats(self.h, out))
-        keys = ("plan_ms", "imprint_constants_ms", "strokes_planned", "segments", "wait_entries", "model_ms",
-                "strokes_this_rank", "launches_this_rank")
+        keys = _STATS_KEYS
         return {k: float(v) for k, v in zip(keys, out)}
 
 
@@ -551,6 +550,11 @@ def lanczos4_taps(src, dst):
     return ofs, w
 
 
+_STATS_KEYS = ("plan_ms", "imprint_constants_ms", "strokes_planned", "segments", "wait_entries", "model_ms", "strokes_this_rank",
+               "launches_this_rank", "resident_clusters_small", "resident_clusters_mid", "resident_clusters_large",
+               "threads_per_cluster_max")
+
+
 class BatchPlan:
     """Host-side plan of a footprint stroke batch (pb_batch_plan)."""
 
@@ -563,10 +567,9 @@ class BatchPlan:
             self.h = None
 
     def stats(self):
-        out = (C.c_double * 8)()
+        out = (C.c_double * 12)()
         _chk(lib().pb_batch_plan_stats(self.h, out))
-        keys = ("plan_ms", "imprint_constants_ms", "strokes_planned", "segments", "wait_entries", "model_ms",
-                "strokes_this_rank", "launches_this_rank")
+        keys = _STATS_KEYS
         return {k: float(v) for k, v in zip(keys, out)}
 
 

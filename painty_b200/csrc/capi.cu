@@ -129,7 +129,7 @@ struct pb_fbrush {
   unsigned long long* d_trace    = nullptr;                          // diagnostics, pb_fbrush_enable_trace
   bool count_visited             = false;
   // host-side figures of the last stroke / imprint batch (pb_fbrush_batch_stats)
-  double stats[PB_BATCH_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double stats[PB_BATCH_STATS] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 struct pb_tbrush {
@@ -331,7 +331,7 @@ struct pb_batch_plan {
   std::vector<RunPlan> runs;
   std::vector<DevImprint> im;
   Region batch{0, 0, -1, -1};
-  double stats[PB_BATCH_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double stats[PB_BATCH_STATS] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   // brush state the plan assumes before / leaves after the batch (stroke batches; imprint batches keep the state)
   bool sets_state = false;
   double radius_before = 0.0, radius_after = 0.0;
@@ -592,6 +592,15 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
       }
     }
 
+    {  // resident clusters of this run's launch shape (diagnostics)
+      ImprintLaunch Lq{};
+      Lq.n_bands   = multi ? dist->world : 1;
+      size_t smemq = 0;
+      imprint_plan(ctx, max_active, Lq, smemq);
+      const int cls = imprint_cluster_class(max_active);
+      P.stats[cls == 1 ? 8 : (cls == 16 ? 9 : 10)] = static_cast<double>(imprint_slots(Lq));
+      P.stats[11] = std::max(P.stats[11], static_cast<double>(Lq.block) * Lq.cluster);
+    }
     if (!claim_pos.empty()) {
       RP.order.resize(n_run);
       for (size_t k = 0; k < n_run; ++k) RP.order[k] = static_cast<int32_t>(k);
