@@ -108,28 +108,95 @@ template <typename T>
 struct Rec {
   T v[kRecord];
 };
+// L1C = false: L2-only accesses (ld/st.global.cg) — the data is shared between the SMs of a cluster. L1C = true: default
+// caching (L1): used by strokes that run on ONE CTA (no cluster) and stay in the executor's own band. Everything such a
+// stroke reads was written by its own SM, or by another stroke whose completion it acquired (ld.acquire on the progress
+// word + bar.sync: the acquire drops stale L1 lines), so L1 hits are coherent — and consecutive imprints overlap by ~98 %,
+// which turns almost every record access into an L1 hit.
+template <bool L1C>
 __device__ __forceinline__ Rec<float> ld_rec(const float* p) {
   Rec<float> r;
-  asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
-               : "l"(p)
-               : "memory");
+  if (L1C) {
+    asm volatile("ld.global.ca.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p)
+                 : "memory");
+  } else {
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p)
+                 : "memory");
+  }
   return r;
 }
+template <bool L1C>
 __device__ __forceinline__ void st_rec(float* p, const Rec<float>& r) {
-  asm volatile("st.global.cg.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]),
-               "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
-               : "memory");
+  if (L1C) {
+    asm volatile("st.global.wb.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]),
+                 "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+                 : "memory");
+  } else {
+    asm volatile("st.global.cg.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]),
+                 "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+                 : "memory");
+  }
 }
+template <bool L1C>
 __device__ __forceinline__ Rec<double> ld_rec(const double* p) {
   Rec<double> r;
-  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p) : "memory");
-  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[4]), "=d"(r.v[5]), "=d"(r.v[6]), "=d"(r.v[7]) : "l"(p + 4) : "memory");
+  if (L1C) {
+    asm volatile("ld.global.ca.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p) : "memory");
+    asm volatile("ld.global.ca.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[4]), "=d"(r.v[5]), "=d"(r.v[6]), "=d"(r.v[7]) : "l"(p + 4) : "memory");
+  } else {
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p) : "memory");
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[4]), "=d"(r.v[5]), "=d"(r.v[6]), "=d"(r.v[7]) : "l"(p + 4) : "memory");
+  }
   return r;
 }
+template <bool L1C>
 __device__ __forceinline__ void st_rec(double* p, const Rec<double>& r) {
-  asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.v[0]), "d"(r.v[1]), "d"(r.v[2]), "d"(r.v[3]) : "memory");
-  asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + 4), "d"(r.v[4]), "d"(r.v[5]), "d"(r.v[6]), "d"(r.v[7]) : "memory");
+  if (L1C) {
+    asm volatile("st.global.wb.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.v[0]), "d"(r.v[1]), "d"(r.v[2]), "d"(r.v[3]) : "memory");
+    asm volatile("st.global.wb.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + 4), "d"(r.v[4]), "d"(r.v[5]), "d"(r.v[6]), "d"(r.v[7]) : "memory");
+  } else {
+    asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.v[0]), "d"(r.v[1]), "d"(r.v[2]), "d"(r.v[3]) : "memory");
+    asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + 4), "d"(r.v[4]), "d"(r.v[5]), "d"(r.v[6]), "d"(r.v[7]) : "memory");
+  }
+}
+// the non-templated forms = L2-only (staging windows, peer memory)
+template <typename T>
+__device__ __forceinline__ Rec<T> ld_rec(const T* p) {
+  return ld_rec<false>(p);
+}
+template <typename T>
+__device__ __forceinline__ void st_rec(T* p, const Rec<T>& r) {
+  st_rec<false>(p, r);
+}
+// scalar accesses with the same choice of cache operator
+template <bool L1C>
+__device__ __forceinline__ unsigned ld_word(const unsigned* p) {
+  unsigned v;
+  if (L1C)
+    asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  else
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+template <bool L1C>
+__device__ __forceinline__ void st_byte(unsigned char* p, unsigned char v) {
+  const unsigned w = v;
+  if (L1C)
+    asm volatile("st.global.wb.u8 [%0], %1;" ::"l"(p), "r"(w) : "memory");
+  else
+    asm volatile("st.global.cg.u8 [%0], %1;" ::"l"(p), "r"(w) : "memory");
+}
+template <bool L1C, typename T>
+__device__ __forceinline__ void st_scalar(T* p, T v) {
+  if (L1C) {
+    *reinterpret_cast<volatile T*>(p) = v;
+  } else {
+    __stcg(p, v);
+  }
 }
 
 // View of one row band: canvas records, snapshot records and dirty map, all indexed with (band-local row) * pitch +
@@ -180,14 +247,14 @@ struct OpData {
   Rec<T> can, src;
 };
 
-template <typename T>
+template <typename T, bool L1C>
 __device__ __forceinline__ void op_load(const Band<T>& C, int ci, OpData<T>& d) {
   const bool own_src = C.src == C.can;  // snapshot buffer disabled: pickup source is the canvas itself
-  d.can = ld_rec(C.can + static_cast<int64_t>(ci) * kRecord);
-  d.src = own_src ? d.can : ld_rec(C.src + static_cast<int64_t>(ci) * kRecord);
+  d.can = ld_rec<L1C>(C.can + static_cast<int64_t>(ci) * kRecord);
+  d.src = own_src ? d.can : ld_rec<L1C>(C.src + static_cast<int64_t>(ci) * kRecord);
 }
 
-template <typename T>
+template <typename T, bool L1C>
 __device__ __forceinline__ void op_finish(const OpCtx<T>& P, const Band<T>& C, int ci, T fh, const OpData<T>& d, T* pick, int ps,
                                           int slot) {
   using Blend = typename BlendSel<T>::type;
@@ -208,7 +275,7 @@ __device__ __forceinline__ void op_finish(const OpCtx<T>& P, const Band<T>& C, i
     if (own_src) {
       vCan = remain;
     } else {
-      __stcg(C.src + static_cast<int64_t>(ci) * kRecord + PV, remain);
+      st_scalar<L1C>(C.src + static_cast<int64_t>(ci) * kRecord + PV, remain);
     }
     const Blend bl(vP, leave);
 #pragma unroll
@@ -238,7 +305,7 @@ __device__ __forceinline__ void op_finish(const OpCtx<T>& P, const Band<T>& C, i
   }
   out.v[PV] = vB + vCan;
   out.v[7]  = static_cast<T>(0);
-  st_rec(C.can + static_cast<int64_t>(ci) * kRecord, out);
+  st_rec<L1C>(C.can + static_cast<int64_t>(ci) * kRecord, out);
 }
 
 // The rare path of the hit test (a candidate within the float error of a rounding boundary): the reference's f64
@@ -269,7 +336,7 @@ __device__ __forceinline__ int ring_band_of(const RingCtx& X, int row) {
   const int b0 = X.my_band * X.rows_per_band;
   return (row >= b0 && row < b0 + X.rows_per_band) ? X.my_band : row / X.rows_per_band;
 }
-template <typename T, bool VIEWS>
+template <typename T, bool VIEWS, bool L1C>
 __device__ __forceinline__ void ring_scan(T* own_can, T* own_src, unsigned char* own_dirty, const Band<T>* views, const RingCtx X,
                                        const RingGeom g, const RingGeom prev, const bool has_prev, int t0, int stride) {
   // the rectangle list is small and indexed dynamically below: it lives in local memory (L1)
@@ -310,7 +377,7 @@ __device__ __forceinline__ void ring_scan(T* own_can, T* own_src, unsigned char*
           dbase          = views[band].dirty;
         }
         w[q]    = ((lrow * pitch + r.x0) >> 2) + j;
-        word[q] = __ldcg(reinterpret_cast<const unsigned*>(dbase) + w[q]);
+        word[q] = ld_word<L1C>(reinterpret_cast<const unsigned*>(dbase) + w[q]);
       }
     }
     // dirty ring pixels of the batch: bit 4 * q + b = byte b of word q
@@ -351,7 +418,7 @@ __device__ __forceinline__ void ring_scan(T* own_can, T* own_src, unsigned char*
             bnd[k] = ring_band_of(X, rq);
             can    = views[bnd[k]].can;
           }
-          rec[k] = ld_rec(can + static_cast<int64_t>(f[k]) * kRecord);
+          rec[k] = ld_rec<L1C>(can + static_cast<int64_t>(f[k]) * kRecord);
         }
       }
 #pragma unroll
@@ -365,8 +432,8 @@ __device__ __forceinline__ void ring_scan(T* own_can, T* own_src, unsigned char*
             dirty   = views[bnd[k]].dirty;
             touched = views[bnd[k]].touched;
           }
-          st_rec(src + static_cast<int64_t>(f[k]) * kRecord, rec[k]);
-          __stcg(dirty + f[k], static_cast<unsigned char>(0));
+          st_rec<L1C>(src + static_cast<int64_t>(f[k]) * kRecord, rec[k]);
+          st_byte<L1C>(dirty + f[k], static_cast<unsigned char>(0));
           if (VIEWS && touched) __stcg(touched + f[k], static_cast<unsigned char>(1));
         }
       }
@@ -652,6 +719,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
     // per-band views.
     auto imprint_chain = [&](auto views_tag) {
       constexpr bool VIEWS = decltype(views_tag)::value;
+      constexpr bool L1C   = !CL && !VIEWS;  // one CTA, own band: L1-cached pixel accesses (see ld_rec)
       if (st.n_imprints <= 0) return;
       const DevWindow* wins = (VIEWS && (st.flags & kStrokeWindows)) ? L.windows + st.seg_begin : nullptr;
       const DevWindow no_window{{-1, -1}, {0, 0}, {0, 0}};
@@ -716,7 +784,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
             if (j + q < n) {
               ci[q] = lci[(j + q) * bd + tid];
               e[q]  = lk[(j + q) * bd + tid];
-              op_load(band_view<T, VIEWS>(L, views, static_cast<int>(e[q] >> 4)), ci[q], d[q]);
+              op_load<T, L1C>(band_view<T, VIEWS>(L, views, static_cast<int>(e[q] >> 4)), ci[q], d[q]);
             }
           }
 #pragma unroll
@@ -724,8 +792,8 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
             if (j + q < n) {
               const Band<T> B = band_view<T, VIEWS>(L, views, static_cast<int>(e[q] >> 4));
               const int slot  = tid + (k0 + static_cast<int>(e[q] & 15u)) * bd;
-              op_finish(s_ctx, B, ci[q], fhp[slot], d[q], pick, ps, slot);
-              if (B.dirty) __stcg(B.dirty + ci[q], static_cast<unsigned char>(1));
+              op_finish<T, L1C>(s_ctx, B, ci[q], fhp[slot], d[q], pick, ps, slot);
+              if (B.dirty) st_byte<L1C>(B.dirty + ci[q], static_cast<unsigned char>(1));
               if (VIEWS && B.touched) __stcg(B.touched + ci[q], static_cast<unsigned char>(1));
               ++my_active;
             }
@@ -785,9 +853,9 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
             T* const oc = static_cast<T*>(L.own_canvas);
             T* const os = static_cast<T*>(L.own_snapshot);
             if (two_phase || need_full) {
-              ring_scan<T, VIEWS>(oc, os, L.own_dirty, views, X, geom_of(ii), RingGeom{}, false, scan_id(), scan_stride());
+              ring_scan<T, VIEWS, L1C>(oc, os, L.own_dirty, views, X, geom_of(ii), RingGeom{}, false, scan_id(), scan_stride());
             } else if (rt_local >= 0) {
-              ring_scan<T, VIEWS>(oc, os, L.own_dirty, views, X, geom_of(ii), geom_of(ii - 1), true,
+              ring_scan<T, VIEWS, L1C>(oc, os, L.own_dirty, views, X, geom_of(ii), geom_of(ii - 1), true,
                                   crank * L.ring_threads + rt_local, csize * L.ring_threads);
             }
             need_full = false;

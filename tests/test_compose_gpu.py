@@ -94,7 +94,7 @@ def test_canvas_compose_dry_clear(ctx32, ctx64, port, prec):
     K2, S2, V2, _ = km_random_planes(rows, cols, seed=4)
     cv.upload_layer(K2, S2, V2)
     cc.set_layer(K2, S2, V2)
-    _cmp(cv.compose(), cc.compose(), 2 * TOL[prec])
+    _cmp(cv.compose(), cc.compose(), TOL[prec])  # the north-star budget holds across dryCanvas as well
     cv.clear()
     assert (cv.compose() == 1).all()
 
