@@ -953,19 +953,17 @@ int pb_ring_rects(const int32_t box[4], const int32_t allowed[4], const int32_t*
   RingGeom prev{};
   if (prev_box) prev = RingGeom{prev_box[0], prev_box[1], prev_box[2], prev_box[3], prev_allowed[0], prev_allowed[1], prev_allowed[2], prev_allowed[3]};
   int64_t n = 0;
-  // the device's enumeration (imprint.cu: ring_scan), item by item
-  ring_rects(g, prev_box ? &prev : nullptr, [&](const Rect& r) {
-    const int nw = rect_words(r), cnt = (r.y1 - r.y0 + 1) * nw;
-    const float inv = 1.0f / static_cast<float>(nw);
-    for (int t = 0; t < cnt; ++t, ++n) {
-      int row = 0, j = 0;
-      rect_item(r, nw, inv, t, row, j);
-      if (n < capacity) {
-        rows[n]  = row;
-        words[n] = ((row * pitch + r.x0) >> 2) + j;
-      }
+  // the device's enumeration (imprint.cu: ring_scan -> imprint_geom.hpp: ring_list / ring_list_item), item by item
+  RingList rl;
+  ring_list(g, prev_box ? &prev : nullptr, rl);
+  for (int t = 0; t < rl.total; ++t, ++n) {
+    int row = 0, x0 = 0, j = 0;
+    ring_list_item(rl, t, row, x0, j);
+    if (n < capacity) {
+      rows[n]  = row;
+      words[n] = ((row * pitch + x0) >> 2) + j;
     }
-  });
+  }
   *n_words = n;
   PB_API_END
 }

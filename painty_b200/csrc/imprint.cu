@@ -339,35 +339,21 @@ __device__ __forceinline__ int ring_band_of(const RingCtx& X, int row) {
 template <typename T, bool VIEWS, bool L1C>
 __device__ __forceinline__ void ring_scan(T* own_can, T* own_src, unsigned char* own_dirty, const Band<T>* views, const RingCtx X,
                                        const RingGeom g, const RingGeom prev, const bool has_prev, int t0, int stride) {
-  // the rectangle list is small and indexed dynamically below: it lives in local memory (L1)
-  Rect rl[8];
-  int n_rects = 0, total = 0;
-  ring_rects(g, has_prev ? &prev : nullptr, [&](const Rect& r) {
-    if (n_rects < 8) {
-      rl[n_rects++] = r;
-      total += (r.y1 - r.y0 + 1) * rect_words(r);
-    }
-  });
+  // the rectangle list is small and indexed dynamically: it lives in local memory (L1)
+  RingList rl;
+  ring_list(g, has_prev ? &prev : nullptr, rl);
+  const int total = rl.total;
 #pragma unroll 1
   for (int base = t0; base < total; base += kRingBatch * stride) {
     int row[kRingBatch], w[kRingBatch];
     unsigned word[kRingBatch];
 #pragma unroll
     for (int q = 0; q < kRingBatch; ++q) {
-      int t   = base + q * stride;
+      const int t = base + q * stride;
       word[q] = 0u, row[q] = 0, w[q] = 0;
       if (t < total) {
-        int ri = 0, nw = rect_words(rl[0]), cnt = (rl[0].y1 - rl[0].y0 + 1) * nw;
-#pragma unroll 1
-        while (t >= cnt) {  // t < total: ends inside the list
-          t -= cnt;
-          ++ri;
-          nw  = rect_words(rl[ri]);
-          cnt = (rl[ri].y1 - rl[ri].y0 + 1) * nw;
-        }
-        const Rect r = rl[ri];
-        int j;
-        rect_item(r, nw, __frcp_rn(static_cast<float>(nw)), t, row[q], j);
+        int x0, j;
+        ring_list_item(rl, t, row[q], x0, j);
         int lrow = row[q] - X.store_first, pitch = X.pitch;
         const unsigned char* dbase = own_dirty;
         if (VIEWS) {
@@ -376,7 +362,7 @@ __device__ __forceinline__ void ring_scan(T* own_can, T* own_src, unsigned char*
           pitch          = views[band].pitch;
           dbase          = views[band].dirty;
         }
-        w[q]    = ((lrow * pitch + r.x0) >> 2) + j;
+        w[q]    = ((lrow * pitch + x0) >> 2) + j;
         word[q] = ld_word<L1C>(reinterpret_cast<const unsigned*>(dbase) + w[q]);
       }
     }

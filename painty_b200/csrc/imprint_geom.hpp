@@ -247,4 +247,39 @@ PB_HD void rect_item(const Rect& r, int nw, float inv_nw, int q, int& row, int& 
   j   = q - rr * nw;
 }
 
+
+// The items (dirty-map words) of one ring pass, numbered 0 .. total-1 across the rectangles of ring_rects in their fixed
+// order. The device walks them with one thread per item and stride; the host test hook walks them all.
+struct RingList {
+  Rect r[8];
+  int n, total;
+};
+PB_HD void ring_list(const RingGeom& g, const RingGeom* prev, RingList& out) {
+  out.n = 0, out.total = 0;
+  ring_rects(g, prev, [&](const Rect& r) {
+    if (out.n < 8) {
+      out.r[out.n++] = r;
+      out.total += (r.y1 - r.y0 + 1) * rect_words(r);
+    }
+  });
+}
+// item t (0 <= t < total) -> canvas row, first column x0 of its rectangle and word index j within the row of the rectangle:
+// the word covers the flat dirty-map bytes [4 * (((row_local * pitch + x0) >> 2) + j), + 4)
+PB_HD void ring_list_item(const RingList& rl, int t, int& row, int& x0, int& j) {
+  int ri = 0, nw = rect_words(rl.r[0]), cnt = (rl.r[0].y1 - rl.r[0].y0 + 1) * nw;
+  while (t >= cnt && ri + 1 < rl.n) {
+    t -= cnt;
+    ++ri;
+    nw  = rect_words(rl.r[ri]);
+    cnt = (rl.r[ri].y1 - rl.r[ri].y0 + 1) * nw;
+  }
+#if defined(__CUDA_ARCH__)
+  const float inv = __frcp_rn(static_cast<float>(nw));
+#else
+  const float inv = 1.0f / static_cast<float>(nw);
+#endif
+  rect_item(rl.r[ri], nw, inv, t, row, j);
+  x0 = rl.r[ri].x0;
+}
+
 }  // namespace pb
