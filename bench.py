@@ -17,8 +17,9 @@ in an untimed pass.
   e2e      : same metric through the C ABI with HOST buffers: stroke list H2D + kernels + reflectance D2H
              (AoS f64 like Renderer::compose returns) inside the timed region.
   roofline : the KM compose kernel (the path's HBM-bound kernel): 52 B/px algorithmic / event time.
-N > 1: one process per GPU (torchrun), weak scaling of ONE canvas: the canvas grows to (N x 2160) x 3840 with N x S
-strokes of the same size distribution and is cut into N row bands, one per GPU. A stroke is executed by the GPU
+N > 1: one process per GPU (torchrun), weak scaling of ONE canvas: the canvas grows to (N x 2160) x 3840 and is cut into N
+row bands, one per GPU; the stroke list is the single-GPU list repeated per band (copy k shifted down by k x 2160 rows), so
+every GPU receives exactly the single-GPU work and the copies interact across the band boundaries. A stroke is executed by the GPU
 whose band holds its first imprint; where it leaves the band the kernel reads / writes the neighbour's HBM through
 NVLink peer mappings and strokes wait on completion flags of conflicting earlier strokes on any GPU
 (painty_b200/dist.py, bit-exact vs one GPU: tests/test_dist_gpu.py). The reflectance image is assembled inside the timed
@@ -70,11 +71,24 @@ def imprint_counts(strokes):
     return out
 
 
-def build_workload(n_strokes, rows=ROWS, cols=COLS, seed=1234):
-    """Stroke records + imprint arrays for the product arm (expansion = pb_expand_stroke, host f64)."""
+def build_workload(n_strokes, rows=ROWS, cols=COLS, seed=1234, tiles=1):
+    """Stroke records + imprint arrays for the product arm (expansion = pb_expand_stroke, host f64).
+    tiles > 1 (weak scaling over GPUs): the (rows x cols) stroke list is repeated `tiles` times, tile k shifted down by
+    k * rows — every band of the taller canvas receives exactly the single-GPU workload, and the copies meet at the band
+    boundaries (strokes that leave the single-GPU canvas at its top / bottom border reach into the neighbouring copy).
+    Submission order: original order, the tiles of one stroke next to each other."""
     from painty_b200 import api
 
-    strokes = build_strokes(n_strokes, rows, cols, seed)
+    base = build_strokes(n_strokes, rows, cols, seed)
+    if tiles > 1:
+        strokes = []
+        for s in base:
+            for k in range(tiles):
+                t = dict(s)
+                t["path"] = s["path"] + np.array([0.0, float(k * rows)])
+                strokes.append(t)
+    else:
+        strokes = base
     rec = np.zeros(len(strokes), dtype=api.STROKE_DTYPE)
     xs, ys, ts_ = [], [], []
     first = 0
@@ -262,7 +276,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     rows_total = ROWS * world
-    strokes, rec, cx, cy, th, radii = build_workload(args.strokes * world, rows=rows_total)  # same list on every rank
+    strokes, rec, cx, cy, th, radii = build_workload(args.strokes, rows=ROWS, tiles=world)  # same list on every rank
     ctx = api.Context(local, api.F32)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
     dc = None
@@ -430,7 +444,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "stroke-pixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "sbr-style 3840x%d, %d footprint strokes (%d imprints) + KM compose" % (rows_total, len(rec), len(cx)),
+        "config": {"workload": "sbr-style 3840x%d, %d footprint strokes (%d imprints) + KM compose%s" % (
+            rows_total, len(rec), len(cx), "" if world == 1 else "; the 3840x2160 / %d-stroke list repeated in each of the %d bands" % (args.strokes, world)),
                    "parallelism": "single GPU" if world == 1 else
                    "one %dx%d canvas in %d row bands (one per GPU), strokes cross bands through NVLink peer memory, reflectance image "
                    "assembled on every rank by the compose kernel's peer stores; host planning of a batch overlaps the previous batch's "

@@ -31,7 +31,7 @@ for s in range(n):
     p = ex[s]
     if last[p] != cls[s]: slots[p].append(9 if cls[s] != 1 else 148); last[p] = cls[s]
     run[s] = len(slots[p]) - 1
-cost = 5.2 + 0.81e-3 * NA
+cost = np.interp(NA, [146, 1107, 5081, 15200, 20319, 27507], [6.3, 4.7, 4.8, 5.8, 7.6, 13.0])  # measured r02, us per imprint
 for name, single, c in (("straddlers as one segment (today)", remote, cost),
                         ("straddlers segmented like the rest (ideal)", None, cost),
                         ("one segment + 30% slower straddlers", remote, cost * np.where(remote > 0, 1.3, 1.0)),
