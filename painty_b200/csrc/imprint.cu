@@ -473,21 +473,40 @@ __device__ __forceinline__ void stage_in(const ImprintLaunch& L, const DevStroke
     if (dw.band[w] < 0) continue;
     const Window<T> W(L, st, dw, slot, w);
     const int npx = W.rows * W.cols;
+    // two pixels per thread and iteration: the six NVLink loads of a pair are in flight together
 #pragma unroll 1
-    for (int i = sgt; i < npx; i += gstride) {
-      const int lr = i / W.cols, c = i - lr * W.cols, px = W.ox + c;
-      __stcg(W.touched + i, static_cast<unsigned char>(0));
-      if (px >= L.cols) {
-        __stcg(W.dirty + i, static_cast<unsigned char>(0));
-        continue;
+    for (int i0 = sgt; i0 < npx; i0 += 2 * gstride) {
+      Rec<T> a[2], b[2];
+      unsigned char dflag[2];
+      int idx[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = i0 + u * gstride;
+        idx[u]      = -1;
+        dflag[u]    = 0;
+        if (i >= npx) continue;
+        const int lr = i / W.cols, c = i - lr * W.cols, px = W.ox + c;
+        idx[u] = i;
+        if (px >= L.cols) {
+          idx[u] = -2 - i;  // outside the canvas: only the flags are initialised
+          continue;
+        }
+        const int64_t gi = static_cast<int64_t>(W.row0 + lr) * L.cols + px;
+        a[u]     = ld_rec(static_cast<const T*>(L.canvas[W.band]) + gi * kRecord);
+        b[u]     = ld_rec(static_cast<const T*>(L.snapshot[W.band]) + gi * kRecord);
+        dflag[u] = __ldcg(L.dirty[W.band] + gi);
       }
-      const int64_t gi = static_cast<int64_t>(W.row0 + lr) * L.cols + px;
-      const Rec<T> a = ld_rec(static_cast<const T*>(L.canvas[W.band]) + gi * kRecord);
-      const Rec<T> b = ld_rec(static_cast<const T*>(L.snapshot[W.band]) + gi * kRecord);
-      const unsigned char dflag = __ldcg(L.dirty[W.band] + gi);
-      st_rec(W.can + static_cast<int64_t>(i) * kRecord, a);
-      st_rec(W.src + static_cast<int64_t>(i) * kRecord, b);
-      __stcg(W.dirty + i, dflag);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (idx[u] == -1) continue;
+        const int i = idx[u] >= 0 ? idx[u] : -2 - idx[u];
+        __stcg(W.touched + i, static_cast<unsigned char>(0));
+        __stcg(W.dirty + i, dflag[u]);
+        if (idx[u] >= 0) {
+          st_rec(W.can + static_cast<int64_t>(i) * kRecord, a[u]);
+          st_rec(W.src + static_cast<int64_t>(i) * kRecord, b[u]);
+        }
+      }
     }
   }
 }
