@@ -98,11 +98,16 @@ def texture_config(ctx, cpu, n_strokes, n_cpu, rows=4320, cols=7680, seed=4321):
     cvo.set_background(R0)
     cpu_brushes = {}
     t_cpu = 0.0
+    state = 1.0e9  # the ONE brush's radius: setRadius only acts on a change >= 0.5 (TextureBrush.hxx:33-41)
+    tb.setRadius(state)
     for s, pick in zip(strokes[:n_cpu], picks[:n_cpu]):
         if pick not in cpu_brushes:
             cpu_brushes[pick] = cpu.texture_brush(tex[pick][3])
         tbo = cpu_brushes[pick]
-        tbo.set_radius(s["radius"])
+        if not abs(state - s["radius"]) < 0.5:
+            state = s["radius"]
+        tbo.set_radius(state + 1000.0)  # force the per-texture CPU brush to exactly the single brush's effective radius
+        tbo.set_radius(state)
         tbo.dip(s["K"], s["S"])
         tbo.set_thickness_scale(0.05)
         t_cpu += tbo.paint_stroke(cvo, s["path"])

@@ -155,6 +155,13 @@ def test_per_stroke_dictionary_textures_match_oracle(ctx32, ctx64, port, prec):
     cvo.set_background(R0)
     tb = api.TextureBrush(ctx)
     ids, cpu_brushes = {}, {}
+    state = 0.0  # the ONE brush's radius: setRadius only acts on a change >= 0.5 (TextureBrush.hxx:33-41)
+    tb.setRadius(state)
+
+    def cpu_set_radius(tbo, radius):  # force a CPU brush (one per texture) to exactly the single brush's effective radius
+        tbo.set_radius(radius + 1000.0)
+        tbo.set_radius(radius)
+
     n = 30
     rec = np.zeros(n, dtype=api.TSTROKE_DTYPE)
     verts, first, groups = [], 0, set()
@@ -171,7 +178,9 @@ def test_per_stroke_dictionary_textures_match_oracle(ctx32, ctx64, port, prec):
             ids[pick] = tb.addTexture(tex[pick][3])
             cpu_brushes[pick] = port.texture_brush(tex[pick][3])
         tbo = cpu_brushes[pick]
-        tbo.set_radius(rad)
+        if not abs(state - rad) < 0.5:
+            state = rad
+        cpu_set_radius(tbo, state)
         tbo.dip(K, S)
         tbo.set_thickness_scale(0.05)
         tbo.paint_stroke(cvo, path)
@@ -194,7 +203,7 @@ def test_per_stroke_dictionary_textures_match_oracle(ctx32, ctx64, port, prec):
     tb.setThicknessScale(0.3)
     tb.paintStroke([(20, 30), (150, 120), (300, 200)], cv2_)
     tbo = cpu_brushes[some]
-    tbo.set_radius(12.0)
+    cpu_set_radius(tbo, 12.0)
     tbo.dip([.2, .3, .4], [.1, .23, .14])
     tbo.set_thickness_scale(0.3)
     tbo.paint_stroke(cvo2, [(20, 30), (150, 120), (300, 200)])
