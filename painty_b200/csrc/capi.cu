@@ -324,6 +324,7 @@ struct RunPlan {
 }  // namespace
 struct pb_batch_plan {
   bool multi = false;
+  int policy = kShapeLatency;  // launch-shape policy the runs were cut for
   int world = 1, rank = 0, rows_per_band = 0;
   int rows = 0, cols = 0, store_first = 0, store_rows = 0;  // the canvas the plan was made for
   bool use_snapshot = true;
@@ -398,7 +399,8 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
   // a run = consecutive local strokes of one launch class = one kernel launch
   // (one launch per class: sharing a launch between the two cluster classes, sized for the larger footprints, was
   // measured slower — 7.43 vs 7.22 s on the 10k-stroke workload — although it removes a kernel boundary)
-  auto launch_class = [&](size_t s) { return imprint_cluster_class(hs[s].g->n_active); };
+  int policy = kShapeLatency;  // launch-shape policy of the batch (imprint.cuh), chosen below
+  auto launch_class = [&](size_t s) { return imprint_cluster_class(hs[s].g->n_active, policy); };
   auto split_runs = [&](const std::vector<size_t>& list) {
     std::vector<std::pair<size_t, size_t>> runs;
     for (size_t a = 0; a < list.size();) {
@@ -415,57 +417,80 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
     for (size_t k = run.first; k < run.second; ++k) m = std::max(m, hs[list[k]].g->n_active);
     return m;
   };
-  const std::vector<std::pair<size_t, size_t>> my_runs = split_runs(mine);
 
-  // Claim order of the device queues (schedule.hpp): list-schedule the whole batch, all ranks included, with a
-  // cost model of the imprint chain — measured 5.2 us + 0.81 us per 1000 active cells per imprint on a 16-CTA
-  // cluster — and pop the strokes of every launch in the order the model started them.
+  // Claim order of the device queues (schedule.hpp): list-schedule the whole batch, all ranks included, with the measured
+  // cost curve of the launch shapes (imprint_cost_us) and pop the strokes of every launch in the order the model started
+  // them. The same simulation picks the launch-shape policy: the batch is planned under the latency shapes and under the
+  // throughput shapes, and the policy with the shorter model makespan runs (FP32 only: the throughput shapes keep the
+  // whole cell state of a stroke in one CTA's shared memory). PB_IMPRINT_POLICY = latency | throughput forces one.
   static const bool kReorder = [] {
     const char* e = std::getenv("PB_IMPRINT_REORDER");
     return e == nullptr || std::atoi(e) != 0;
   }();
-  // us per imprint = kCostBase + kCostPerCell * active cells (scratch/imprint_micro.py on a 16-CTA cluster)
-  static const double kCostBase = [] {
-    const char* e = std::getenv("PB_IMPRINT_COST_BASE");
-    return e ? std::atof(e) : 3.0;
-  }();
-  static const double kCostPerCell = [] {
-    const char* e = std::getenv("PB_IMPRINT_COST_CELL");
-    return e ? std::atof(e) : 0.35e-3;
+  static const int kForcedPolicy = [] {
+    const char* e = std::getenv("PB_IMPRINT_POLICY");
+    if (e == nullptr) return -1;
+    return std::strcmp(e, "throughput") == 0 ? kShapeThroughput : (std::strcmp(e, "latency") == 0 ? kShapeLatency : -1);
   }();
   std::vector<int32_t> claim_pos;  // global stroke -> position in the claim sequence (empty = submission order)
-  if (kReorder && n > 1) {
+  std::vector<int64_t> counts64(n);
+  for (size_t s = 0; s < n; ++s) counts64[s] = hs[s].n;
+  auto simulate = [&](int pol, std::vector<int32_t>& pos) -> double {  // model makespan of the batch under policy `pol`
+    policy = pol;
     std::vector<ClaimSpec> spec(n);
     std::vector<std::vector<int>> slots(static_cast<size_t>(world));
-    std::vector<int64_t> counts64(n);
     for (int r = 0; r < world; ++r) {
-      const auto runs = r == my_rank ? my_runs : split_runs(locals[r]);
+      const auto runs = split_runs(locals[r]);
       for (size_t j = 0; j < runs.size(); ++j) {
         ImprintLaunch L{};
         L.n_bands   = world;
+        L.policy    = pol;
         size_t smem = 0;
         imprint_plan(ctx, run_max_active(locals[r], runs[j]), L, smem);
         const int64_t n_run = static_cast<int64_t>(runs[j].second - runs[j].first);
         slots[r].push_back(static_cast<int>(std::min<int64_t>(imprint_slots(L), n_run)));
         for (size_t k = runs[j].first; k < runs[j].second; ++k) {
           const size_t s = locals[r][k];
-          spec[s]        = ClaimSpec{r, static_cast<int32_t>(j), kCostBase + kCostPerCell * hs[s].g->n_active};
+          spec[s]        = ClaimSpec{r, static_cast<int32_t>(j), imprint_cost_us(hs[s].g->n_active, pol)};
         }
       }
     }
-    for (size_t s = 0; s < n; ++s) counts64[s] = hs[s].n;
-    const std::vector<int32_t> seq = plan_claim_order(plan, counts64, spec, slots, 64, &model_makespan);
-    claim_pos.assign(n, -1);
-    for (size_t q = 0; q < seq.size(); ++q) claim_pos[seq[q]] = static_cast<int32_t>(q);
+    double makespan = 0.0;
+    const std::vector<int32_t> seq = plan_claim_order(plan, counts64, spec, slots, 64, &makespan);
+    pos.assign(n, -1);
+    for (size_t q = 0; q < seq.size(); ++q) pos[seq[q]] = static_cast<int32_t>(q);
     // the device relies on the order being topological; fall back to submission order otherwise
     bool ok = seq.size() == n;
     for (size_t s = 0; s < n && ok; ++s) {
-      ok = claim_pos[s] >= 0;
+      ok = pos[s] >= 0;
       for (int32_t p = plan.seg_off[plan.seg_first[s]]; p < plan.seg_off[plan.seg_first[s + 1]] && ok; ++p)
-        ok = claim_pos[plan.pred_stroke[p]] < claim_pos[s];
+        ok = pos[plan.pred_stroke[p]] < pos[s];
     }
-    if (!ok) claim_pos.clear();
+    if (!ok) pos.clear();
+    return makespan;
+  };
+  const bool may_choose = ctx->precision == PB_F32 && kForcedPolicy < 0;
+  if (kReorder && n > 1) {
+    model_makespan = simulate(kShapeLatency, claim_pos);
+    if (may_choose) {
+      std::vector<int32_t> pos_t;
+      const double mk_t = simulate(kShapeThroughput, pos_t);
+      if (mk_t < model_makespan) {
+        model_makespan = mk_t;
+        claim_pos.swap(pos_t);
+      } else {
+        policy = kShapeLatency;
+      }
+    }
   }
+  if (kForcedPolicy >= 0 && ctx->precision == PB_F32 && policy != kForcedPolicy) {
+    if (kReorder && n > 1)
+      model_makespan = simulate(kForcedPolicy, claim_pos);
+    else
+      policy = kForcedPolicy;
+  }
+  P.policy = policy;
+  const std::vector<std::pair<size_t, size_t>> my_runs = split_runs(mine);
   PB_REQUIRE(static_cast<int64_t>(mine.size()) <= kDistFlagCapacity, "too many strokes in one batch");
 
   const auto t_plan1 = std::chrono::steady_clock::now();
@@ -595,10 +620,10 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
     {  // resident clusters of this run's launch shape (diagnostics)
       ImprintLaunch Lq{};
       Lq.n_bands   = multi ? dist->world : 1;
+      Lq.policy    = policy;
       size_t smemq = 0;
       imprint_plan(ctx, max_active, Lq, smemq);
-      const int cls = imprint_cluster_class(max_active);
-      P.stats[cls == 1 ? 8 : (cls == 16 ? 9 : 10)] = static_cast<double>(imprint_slots(Lq));
+      P.stats[max_active <= 256 ? 8 : (max_active <= 4096 ? 9 : 10)] = static_cast<double>(imprint_slots(Lq));
       P.stats[11] = std::max(P.stats[11], static_cast<double>(Lq.block) * Lq.cluster);
     }
     if (!claim_pos.empty()) {
@@ -662,6 +687,7 @@ void run_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo
     const size_t max_window = RP.max_window;
     ImprintLaunch L{};
     L.n_bands = multi ? dist->world : 1;
+    L.policy  = P.policy;
     size_t smem = 0;
     imprint_plan(ctx, max_active, L, smem);
     L.grid = static_cast<int>(std::min<int64_t>(L.grid, static_cast<int64_t>(n_run) * L.cluster));

@@ -993,27 +993,55 @@ int env_int(const char* name, int fallback) {
 
 }  // namespace
 
-// A stroke is latency bound (a chain of dependent imprints), so it is spread thin: CTAs of 128..512 threads on
-// up to 16 SMs (non-portable cluster size).
-// Launch classes (a run of consecutive strokes of one class shares a launch):
-//   1  : tiny footprints (<= 256 active cells), one CTA per stroke
-//   16 : cluster x 128 threads (<= 4096 cells)
-//   17 : cluster x 256 or 512 threads for the large footprints
-int imprint_cluster_class(int n_active) { return n_active <= 256 ? 1 : (n_active <= 4096 ? 16 : 17); }
+// Launch classes (a run of consecutive strokes of one class shares a launch) and their shapes, per policy:
+//   latency policy      1 : <= 256 active cells, one CTA (128 / 256 threads)
+//                       16: <= 4096 cells, cluster 8 x 256 (as fast as 16 x 128 and twice the resident clusters)
+//                       17: cluster 16 x 256 (<= 8192 cells) or 16 x 512
+//   throughput policy   1 : <= 4096 cells, one CTA of up to 512 threads (r = 30: 8.9 us on ONE SM against 4.0 us on 8)
+//                       8 : <= 8192 cells, cluster 8 x 512
+//                       17: cluster 16 x 512
+int imprint_cluster_class(int n_active, int policy) {
+  if (policy == kShapeThroughput) return n_active <= 4096 ? 1 : (n_active <= 8192 ? 8 : 17);
+  return n_active <= 256 ? 1 : (n_active <= 4096 ? 16 : 17);
+}
+
+double imprint_cost_us(int n_active, int policy) {
+  struct P {
+    double n, us;
+  };
+  static const P lat[] = {{146, 3.2}, {1107, 4.0}, {2461, 5.3}, {3958, 6.8}, {5081, 5.4}, {8025, 6.5}, {15200, 6.7}, {20319, 8.2}, {27507, 12.6}};
+  static const P thr[] = {{146, 3.2}, {1107, 8.9}, {2461, 15.7}, {3958, 31.7}, {5081, 6.6}, {8025, 8.0}, {15200, 6.7}, {20319, 8.2}, {27507, 12.6}};
+  const P* t  = policy == kShapeThroughput ? thr : lat;
+  const int m = 9;
+  const double x = n_active;
+  if (x <= t[0].n) return t[0].us;
+  for (int i = 1; i < m; ++i)
+    if (x <= t[i].n) {
+      // the tables are not continuous where the shape changes (4096 / 8192 cells): no interpolation across a class border
+      if (imprint_cluster_class(static_cast<int>(t[i - 1].n), policy) != imprint_cluster_class(static_cast<int>(t[i].n), policy) &&
+          imprint_cluster_class(n_active, policy) != imprint_cluster_class(static_cast<int>(t[i].n), policy))
+        return t[i - 1].us * x / t[i - 1].n;
+      return t[i - 1].us + (t[i].us - t[i - 1].us) * (x - t[i - 1].n) / (t[i].n - t[i - 1].n);
+    }
+  return t[m - 1].us * x / t[m - 1].n;
+}
 
 int imprint_slots(const ImprintLaunch& L) { return std::max(1, L.grid / std::max(1, L.cluster)); }
 
 void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& smem_bytes) {
-  const int cls = imprint_cluster_class(max_active);
-  // experiment knobs (sweeps in scratch/): cluster size and block size per class
-  const int cluster = cls == 1 ? 1 : std::min(16, std::max(1, env_int(cls == 16 ? "PB_IMPRINT_CLUSTER16" : "PB_IMPRINT_CLUSTER17", 16)));
-  int block = 128;
+  const int cls = imprint_cluster_class(max_active, L.policy);
+  // experiment knobs (scratch/imprint_sweep.py): cluster size and block size per class of the latency policy
+  int cluster = 1, block = 128;
   if (cls == 1) {
-    block = max_active <= 128 ? 128 : 256;
+    block = max_active <= 128 ? 128 : (max_active <= 256 ? 256 : 512);
+  } else if (cls == 8) {
+    cluster = 8, block = 512;
   } else if (cls == 16) {
-    block = env_int("PB_IMPRINT_BLOCK16", 128);
+    cluster = std::min(16, std::max(1, env_int("PB_IMPRINT_CLUSTER16", 8)));
+    block   = env_int("PB_IMPRINT_BLOCK16", 256);
   } else {
-    block = env_int("PB_IMPRINT_BLOCK17", max_active <= 8192 ? 256 : 512);
+    cluster = std::min(16, std::max(1, env_int("PB_IMPRINT_CLUSTER17", 16)));
+    block   = env_int("PB_IMPRINT_BLOCK17", max_active <= 8192 ? 256 : 512);
   }
   block               = std::min(512, std::max(32, block / 32 * 32));
   const size_t es     = ctx->esize();
@@ -1035,7 +1063,9 @@ void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& sme
   }
   L.cta_cells    = cta_cells;
   L.chunk_cells  = chunk;
-  L.ring_threads = std::min(block, std::max(32, env_int("PB_RING_THREADS", 64) / 32 * 32));
+  // the incremental ring pass runs on the last warp of every CTA: where a CTA has more threads than cells, those threads own
+  // no cells and the pass stays off the critical path (r = 30: 3.7 us per imprint with 32 ring threads, 4.9 with 64)
+  L.ring_threads = std::min(block, std::max(32, env_int("PB_RING_THREADS", 32) / 32 * 32));
   L.block        = block;
   L.cluster      = cluster;
   // occupancy queries and attribute changes cost milliseconds: do them once per launch shape

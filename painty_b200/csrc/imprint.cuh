@@ -111,12 +111,21 @@ struct ImprintLaunch {
   int block;               // threads per CTA
   int cluster;             // CTAs per thread-block cluster
   int grid;                // CTAs (multiple of cluster)
+  int policy;              // kShapeLatency / kShapeThroughput (input of imprint_plan)
 };
+
+// Launch-shape policies. A stroke is a chain of dependent imprints, so its speed is a latency; a batch, however, is bound
+// either by its dependency graph (critical path: spread every stroke over many SMs to cut the latency per imprint) or by
+// the number of strokes that can run at once (give every stroke as few SMs as it needs, run many). The host planner
+// simulates the batch under both policies with the measured cost curves and takes the faster one (capi.cu).
+constexpr int kShapeLatency = 0, kShapeThroughput = 1;
+// measured single-stroke latency of the policy's shape, us per imprint (scratch/imprint_sweep.py, brush at 45 degrees)
+double imprint_cost_us(int n_active, int policy);
 
 // Launch shape for a run of strokes whose largest footprint has max_active cells: a stroke is owned by a
 // thread-block cluster of `cluster` CTAs x `block` threads.
-void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& smem_bytes);
-int imprint_cluster_class(int n_active);
+void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& smem_bytes);  // reads L.n_bands, L.policy
+int imprint_cluster_class(int n_active, int policy);
 void imprint_launch(pb_context* ctx, const ImprintLaunch& L, size_t smem_bytes);
 // concurrent strokes of a launch shape (resident clusters), for the host's claim-order model
 int imprint_slots(const ImprintLaunch& L);
