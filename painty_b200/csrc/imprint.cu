@@ -998,10 +998,11 @@ int env_int(const char* name, int fallback) {
 //                       16: <= 4096 cells, cluster 8 x 256 (as fast as 16 x 128 and twice the resident clusters)
 //                       17: cluster 16 x 256 (<= 8192 cells) or 16 x 512
 //   throughput policy   1 : <= 4096 cells, one CTA of up to 512 threads (r = 30: 8.9 us on ONE SM against 4.0 us on 8)
-//                       8 : <= 8192 cells, cluster 8 x 512
-//                       17: cluster 16 x 512
+//                       8 : cluster 8 x 512 (r = 151: 21.8 us on 8 SMs against 12.4 us on 16 — and 16-CTA clusters only
+//                           fit 7 times on the 148 SMs, 8-CTA clusters use all of them)
+// Two classes per policy, so that a pass of similar strokes stays one launch.
 int imprint_cluster_class(int n_active, int policy) {
-  if (policy == kShapeThroughput) return n_active <= 4096 ? 1 : (n_active <= 8192 ? 8 : 17);
+  if (policy == kShapeThroughput) return n_active <= 4096 ? 1 : 8;
   return n_active <= 256 ? 1 : (n_active <= 4096 ? 16 : 17);
 }
 
@@ -1010,7 +1011,7 @@ double imprint_cost_us(int n_active, int policy) {
     double n, us;
   };
   static const P lat[] = {{146, 3.2}, {1107, 4.0}, {2461, 5.3}, {3958, 6.8}, {5081, 5.4}, {8025, 6.5}, {15200, 6.7}, {20319, 8.2}, {27507, 12.6}};
-  static const P thr[] = {{146, 3.2}, {1107, 8.9}, {2461, 15.7}, {3958, 31.7}, {5081, 6.6}, {8025, 8.0}, {15200, 6.7}, {20319, 8.2}, {27507, 12.6}};
+  static const P thr[] = {{146, 3.2}, {1107, 8.9}, {2461, 15.7}, {3958, 31.7}, {5081, 6.6}, {8025, 8.0}, {15200, 15.2}, {20319, 16.6}, {27507, 21.8}};
   const P* t  = policy == kShapeThroughput ? thr : lat;
   const int m = 9;
   const double x = n_active;
