@@ -286,6 +286,14 @@ void ensure_snapshot(pb_fbrush* b, pb_canvas* c) {  // FootprintBrush.hxx:281-28
   b->snap_canvas_version = c->version;
 }
 
+// Granularity of the dependency planner's tile tables in pixels (PB_PLAN_TILE, default 64): regions are rounded outward to
+// tiles, so smaller tiles mean fewer false dependencies between neighbouring strokes and more planning work.
+int plan_tile() {
+  const char* e = std::getenv("PB_PLAN_TILE");
+  const int t   = e ? std::atoi(e) : 64;
+  return std::min(512, std::max(8, t));
+}
+
 struct HostStroke {
   const FootprintGeom* g;
   double radius;
@@ -391,7 +399,7 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
       allowed[s]   = r;
     }
     local_index[s] = counts[executor[s]]++;
-  });
+  }, plan_tile());
   const int my_rank = multi ? dist->rank : 0, world = multi ? dist->world : 1;
   std::vector<std::vector<size_t>> locals(static_cast<size_t>(world));  // per rank: its strokes in submission order
   for (size_t s = 0; s < n; ++s) locals[executor[s]].push_back(s);
@@ -928,7 +936,7 @@ int pb_plan_segments(int rows, int cols, int64_t n, const int64_t* first, const 
   const SegmentPlan plan = plan_segments(
       rows, cols, static_cast<size_t>(n),
       [&](size_t s) { return StrokeSpan{first[s], count[s], (side[s] - 1) / 2, radius[s], single != nullptr && single[s] != 0}; },
-      cx, cy, segment_length, use_snapshot != 0, [](size_t, const Region&, const Region&) {});
+      cx, cy, segment_length, use_snapshot != 0, [](size_t, const Region&, const Region&) {}, plan_tile());
   for (int64_t s = 0; s < n; ++s) {
     seg_first[s] = plan.seg_first[static_cast<size_t>(s)];
     seg_len[s]   = plan.seg_len[static_cast<size_t>(s)];
@@ -954,7 +962,7 @@ int pb_plan_claim_order(int rows, int cols, int64_t n, const int64_t* first, con
   const SegmentPlan plan = plan_segments(
       rows, cols, static_cast<size_t>(n),
       [&](size_t s) { return StrokeSpan{first[s], count[s], (side[s] - 1) / 2, radius[s], single != nullptr && single[s] != 0}; },
-      cx, cy, segment_length, use_snapshot != 0, [](size_t, const Region&, const Region&) {});
+      cx, cy, segment_length, use_snapshot != 0, [](size_t, const Region&, const Region&) {}, plan_tile());
   std::vector<std::vector<int>> sl(static_cast<size_t>(n_pools));
   for (int p = 0, o = 0; p < n_pools; ++p)
     for (int j = 0; j < runs_per_pool[p]; ++j) sl[p].push_back(slots[o++]);
