@@ -328,6 +328,11 @@ struct RunPlan {
   std::vector<int32_t> order;      // queue ticket -> stroke of this run (empty = submission order)
   int max_active    = 1;
   size_t max_window = 0;
+  // multi GPU: a run is executed by two concurrent launches — `views` = the one for the straddling strokes; both carry the
+  // same group number. share = this launch's part of the run's imprints (splits the resident clusters between the two).
+  bool views   = false;
+  int group    = 0;
+  double share = 1.0;
 };
 }  // namespace
 struct pb_batch_plan {
@@ -569,6 +574,7 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
       // half width of the undecided band of the single-precision hit test: 3x the error bound of imprint_geom.hpp
       d.eps      = static_cast<float>(1e-6 * ((h.g->side - 1) / 2) + 2e-5);
       d.win_ox = d.win_cols = 0;
+      d.flag_index = static_cast<int32_t>(run_begin + k);
       const int nseg = plan.seg_first[s + 1] - plan.seg_first[s];
       const size_t win_first = run_windows.size();
       run_windows.resize(win_first + static_cast<size_t>(nseg), DevWindow{{-1, -1}, {0, 0}, {0, 0}});
@@ -640,6 +646,53 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
       std::sort(RP.order.begin(), RP.order.end(),
                 [&](int32_t a, int32_t b2) { return claim_pos[mine[run_begin + a]] < claim_pos[mine[run_begin + b2]]; });
     }
+    RP.group = static_cast<int>(P.runs.size());
+    if (multi) {
+      // Split the run: strokes inside the band -> the launch without the view chain, straddling strokes -> the launch
+      // with it. Each part keeps the run's claim order among its own strokes.
+      auto is_views = [&](size_t k) { return (RP.ds[k].flags & (kStrokeDirect | kStrokeWindows)) != 0; };
+      size_t n_views = 0;
+      double imprints_all = 0.0, imprints_views = 0.0;
+      for (size_t k = 0; k < n_run; ++k) {
+        imprints_all += RP.ds[k].n_imprints;
+        if (is_views(k)) {
+          ++n_views;
+          imprints_views += RP.ds[k].n_imprints;
+        }
+      }
+      if (n_views == n_run) {
+        RP.views = true;
+      } else if (n_views > 0) {
+        auto subset = [&](bool want_views) {
+          RunPlan S;
+          S.begin = RP.begin, S.end = RP.end, S.max_active = RP.max_active, S.group = RP.group, S.views = want_views;
+          S.max_window = want_views ? RP.max_window : 0;
+          S.seg_off.assign(1, 0);
+          std::vector<int32_t> new_index(n_run, -1);
+          for (size_t k = 0; k < n_run; ++k) {
+            if (is_views(k) != want_views) continue;
+            new_index[k]     = static_cast<int32_t>(S.ds.size());
+            DevStroke d      = RP.ds[k];
+            const int nseg   = (k + 1 < n_run ? RP.ds[k + 1].seg_begin : static_cast<int32_t>(RP.seg_off.size()) - 1) - d.seg_begin;
+            const int old_sb = d.seg_begin;
+            d.seg_begin      = static_cast<int32_t>(S.seg_off.size()) - 1;
+            for (int g = 0; g < nseg; ++g) {
+              for (int32_t p = RP.seg_off[old_sb + g]; p < RP.seg_off[old_sb + g + 1]; ++p) S.preds.push_back(RP.preds[p]);
+              S.seg_off.push_back(static_cast<int32_t>(S.preds.size()));
+              S.windows.push_back(RP.windows[static_cast<size_t>(old_sb + g)]);
+            }
+            S.ds.push_back(d);
+          }
+          for (int32_t k : RP.order)
+            if (new_index[static_cast<size_t>(k)] >= 0) S.order.push_back(new_index[static_cast<size_t>(k)]);
+          S.share = (want_views ? imprints_views : imprints_all - imprints_views) / std::max(imprints_all, 1.0);
+          return S;
+        };
+        RunPlan main_part = subset(false), views_part = subset(true);
+        P.runs.back() = std::move(main_part);
+        P.runs.push_back(std::move(views_part));
+      }
+    }
   }
 }
 
@@ -684,20 +737,29 @@ void run_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo
     planes_to_records(ctx, c->pl, b->work_rec, conv.x0, conv.y0, conv.x1, conv.y1);
   }
 
-  for (const RunPlan& RP : P.runs) {
-    const size_t run_begin = RP.begin, n_run = RP.end - RP.begin;
-    const std::vector<DevStroke>& ds = RP.ds;
-    const std::vector<int2>& run_preds = RP.preds;
-    const std::vector<int32_t>& run_seg_off = RP.seg_off;
-    const std::vector<DevWindow>& run_windows = RP.windows;
-    const std::vector<int32_t>& run_order = RP.order;
-    const int max_active = RP.max_active;
-    const size_t max_window = RP.max_window;
+  // device copies of one launch's arrays; they live until the launch (and, for a pair of concurrent launches, the join of
+  // the two streams) has been enqueued — the stream-ordered frees then run behind it
+  struct LaunchBuffers {
+    DevBuf<DevStroke> strokes;
+    DevBuf<int2> preds;
+    DevBuf<int32_t> seg_off, order;
+    DevBuf<char> scratch;
+    DevBuf<unsigned char> windows;
+    DevBuf<DevWindow> win_desc;
+    LaunchBuffers(pb_context* cx_, const RunPlan& RP, size_t scratch_bytes, size_t window_bytes, bool multi_)
+        : strokes(cx_, RP.ds.size()), preds(cx_, RP.preds.size()), seg_off(cx_, RP.seg_off.size()), order(cx_, RP.order.size()),
+          scratch(cx_, scratch_bytes), windows(cx_, window_bytes), win_desc(cx_, multi_ ? RP.windows.size() : 0) {}
+  };
+  // clusters: upper bound of resident clusters this launch may take (0 = all that fit)
+  auto launch_run = [&](const RunPlan& RP, int clusters, cudaStream_t stream) -> std::unique_ptr<LaunchBuffers> {
+    const size_t n_run = RP.ds.size();
     ImprintLaunch L{};
-    L.n_bands = multi ? dist->world : 1;
-    L.policy  = P.policy;
-    size_t smem = 0;
-    imprint_plan(ctx, max_active, L, smem);
+    L.n_bands      = multi ? dist->world : 1;
+    L.policy       = P.policy;
+    L.views_kernel = (multi && RP.views) ? 1 : 0;
+    size_t smem    = 0;
+    imprint_plan(ctx, RP.max_active, L, smem);
+    if (clusters > 0) L.grid = std::min(L.grid, clusters * L.cluster);
     L.grid = static_cast<int>(std::min<int64_t>(L.grid, static_cast<int64_t>(n_run) * L.cluster));
     if (multi) {
       for (int r = 0; r < dist->world; ++r) {
@@ -718,14 +780,13 @@ void run_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo
       L.rows_per_band = std::max(c->pl.rows, 1);
       L.my_band       = 0;
       L.queue         = reinterpret_cast<int*>(d_flags.p + P.n_mine);
-      if (run_begin > 0) PB_CUDA(cudaMemsetAsync(L.queue, 0, sizeof(int), ctx->stream));
+      if (RP.begin > 0) PB_CUDA(cudaMemsetAsync(L.queue, 0, sizeof(int), ctx->stream));
     }
     L.own_canvas   = L.canvas[L.my_band];
     L.own_snapshot = L.snapshot[L.my_band];
     for (int p = 0; p < kLayerPlanes; ++p) L.pick_dense[p] = b->pick.base ? b->pick.plane(p) : nullptr;
-    L.own_dirty = L.dirty[L.my_band];
+    L.own_dirty       = L.dirty[L.my_band];
     L.epoch           = epoch;
-    L.flag_offset     = static_cast<int>(run_begin);
     L.use_snapshot    = b->use_snapshot ? 1 : 0;
     L.rows            = c->rows;
     L.cols            = c->cols;
@@ -736,32 +797,61 @@ void run_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo
     L.capacity        = b->capacity;
     L.n_strokes       = static_cast<int64_t>(n_run);
 
-    DevBuf<DevStroke> d_strokes(ctx, ds.size());
-    DevBuf<int2> d_preds(ctx, run_preds.size());
-    DevBuf<int32_t> d_seg_off(ctx, run_seg_off.size());
-    DevBuf<int32_t> d_order(ctx, run_order.size());
-    d_order.upload(run_order.data(), run_order.size());
-    L.order = run_order.empty() ? nullptr : d_order.p;
-    d_strokes.upload(ds.data(), ds.size());
-    d_preds.upload(run_preds.data(), run_preds.size());
-    d_seg_off.upload(run_seg_off.data(), run_seg_off.size());
-    DevBuf<char> d_scratch(ctx, static_cast<size_t>(L.scratch_stride) * L.grid);
     const size_t n_slots = static_cast<size_t>(imprint_slots(L));
-    DevBuf<unsigned char> d_windows(ctx, 2 * max_window * n_slots);
-    DevBuf<DevWindow> d_win_desc(ctx, multi ? run_windows.size() : 0);
-    if (multi) d_win_desc.upload(run_windows.data(), run_windows.size());
-    L.windows     = multi ? d_win_desc.p : nullptr;
-    L.win_scratch = d_windows.p;
-    L.win_stride  = static_cast<int64_t>(2 * max_window);
-    L.scratch  = d_scratch.p;
-    L.strokes  = d_strokes.p;
-    L.imprints = d_im.p;
-    L.preds    = d_preds.p;
-    L.seg_off  = d_seg_off.p;
-    L.counters = b->d_counters;
-    L.trace    = b->d_trace;
-    imprint_launch(ctx, L, smem);
-    if (b->count_visited) imprint_count_visited(ctx, d_strokes.p, L.n_strokes, d_im.p, c->rows, c->cols, b->d_counters + 1);
+    auto B = std::make_unique<LaunchBuffers>(ctx, RP, static_cast<size_t>(L.scratch_stride) * L.grid, 2 * RP.max_window * n_slots, multi);
+    B->order.upload(RP.order.data(), RP.order.size());
+    B->strokes.upload(RP.ds.data(), RP.ds.size());
+    B->preds.upload(RP.preds.data(), RP.preds.size());
+    B->seg_off.upload(RP.seg_off.data(), RP.seg_off.size());
+    if (multi) B->win_desc.upload(RP.windows.data(), RP.windows.size());
+    L.order       = RP.order.empty() ? nullptr : B->order.p;
+    L.windows     = multi ? B->win_desc.p : nullptr;
+    L.win_scratch = B->windows.p;
+    L.win_stride  = static_cast<int64_t>(2 * RP.max_window);
+    L.scratch     = B->scratch.p;
+    L.strokes     = B->strokes.p;
+    L.imprints    = d_im.p;
+    L.preds       = B->preds.p;
+    L.seg_off     = B->seg_off.p;
+    L.counters    = b->d_counters;
+    L.trace       = b->d_trace;
+    if (stream != nullptr) {  // everything enqueued on the main stream so far (uploads, memsets) precedes the forked launch
+      PB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+      PB_CUDA(cudaStreamWaitEvent(stream, ctx->ev_fork, 0));
+    }
+    imprint_launch(ctx, L, smem, stream);
+    if (b->count_visited) imprint_count_visited(ctx, B->strokes.p, L.n_strokes, d_im.p, c->rows, c->cols, b->d_counters + 1);
+    return B;
+  };
+  for (size_t i = 0; i < P.runs.size(); ++i) {
+    const RunPlan& RP = P.runs[i];
+    const bool paired = multi && i + 1 < P.runs.size() && P.runs[i + 1].group == RP.group;
+    if (!paired) {
+      auto keep = launch_run(RP, 0, nullptr);
+      continue;
+    }
+    // the run's two launches run side by side: the straddling strokes on the second stream with their share of the
+    // resident clusters, the strokes inside the band on the main stream with the rest
+    const RunPlan& VP = P.runs[i + 1];
+    if (ctx->aux_stream == nullptr) {
+      PB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+      PB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      PB_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    ImprintLaunch Lq{};
+    Lq.n_bands      = dist->world;
+    Lq.policy       = P.policy;
+    Lq.views_kernel = 1;
+    size_t smemq    = 0;
+    imprint_plan(ctx, VP.max_active, Lq, smemq);
+    const int total   = imprint_slots(Lq);
+    PB_REQUIRE(total >= 2, "multi-GPU stroke batches need room for two resident thread-block clusters of the launch shape");
+    const int n_views = std::min<int>(std::max(1, static_cast<int>(std::lround(total * VP.share))), std::max(1, total - 1));
+    auto keep_views = launch_run(VP, n_views, ctx->aux_stream);
+    auto keep_main  = launch_run(RP, std::max(1, total - n_views), nullptr);
+    PB_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    ++i;
   }
   if (!multi) records_to_planes(ctx, b->work_rec, c->pl, conv.x0, conv.y0, conv.x1, conv.y1);
   c->version++;
@@ -813,6 +903,9 @@ int pb_context_destroy(pb_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
   }
   PB_API_END

@@ -46,6 +46,9 @@ struct pb_context {
   int device       = 0;
   int precision    = PB_F32;
   cudaStream_t stream = nullptr;
+  // second stream + fork / join events for the straddling strokes of a multi-GPU run (created on first use)
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t launches = 0;
   int sm_count     = 148;
   size_t esize() const { return precision == PB_F64 ? 8 : 4; }

@@ -550,22 +550,24 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // SCR: the per-cell state lives in a per-CTA global scratch area instead of shared memory (footprints beyond ~60 000
 // active cells in FP64 mode); everything else is identical.
-template <typename T, bool CL, int MAXB, bool MULTI, bool SCR>
+// MODE: 0 = single GPU; 1 = multi GPU, strokes inside the executor's band only; 2 = multi GPU incl. straddling strokes
+template <typename T, bool CL, int MAXB, int MODE, bool SCR>
 __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L) {
+  constexpr bool MULTI = MODE != 0;
   // interactions in flight per thread: 16 registers of records each in FP32 mode, 32 in FP64 mode; as many as fit
   // without spilling (512-thread CTAs leave 128 registers per thread)
   constexpr int kInFlight = sizeof(T) == 4 ? (MAXB > 256 ? 3 : 4) : (MAXB > 256 ? 1 : 2);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_stroke;
   __shared__ unsigned long long s_active;
-  __shared__ Band<T> s_view[MULTI ? kMaxBands : 1];
+  __shared__ Band<T> s_view[MODE == 2 ? kMaxBands : 1];
   // Register diet (one CTA of 512 threads leaves 128 registers per thread): everything that is constant over a stroke
   // or an imprint lives in shared memory and is re-read where it is used — the stroke record, the paint constants, and a
   // ring of four imprint records (previous, current, next, and the one being prefetched with cp.async).
   __shared__ DevStroke s_st;
   __shared__ OpCtx<T> s_ctx;
   __shared__ DevImprint s_im[4];
-  const Band<T>* views = MULTI ? s_view : nullptr;
+  const Band<T>* views = MODE == 2 ? s_view : nullptr;
 
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, bd = blockDim.x;
@@ -662,10 +664,10 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
         const long long v = (static_cast<long long>(L.epoch) << 32) | static_cast<unsigned>(done_segments);
         if (MULTI) {
           __threadfence_system();
-          st_release64_sys(L.done[L.my_band] + L.flag_offset + si, v);
+          st_release64_sys(L.done[L.my_band] + st.flag_index, v);
         } else {
           __threadfence();
-          st_release64(L.done[0] + L.flag_offset + si, v);
+          st_release64(L.done[0] + st.flag_index, v);
         }
       }
     };
@@ -906,12 +908,8 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
         __threadfence_system();
       }
     };
-    if constexpr (MULTI) {
-      if (st.flags & (kStrokeDirect | kStrokeWindows)) {
-        imprint_chain(std::true_type{});
-      } else {
-        imprint_chain(std::false_type{});
-      }
+    if constexpr (MODE == 2) {
+      imprint_chain(std::true_type{});  // this variant is only launched for straddling strokes (capi.cu: run_plan)
     } else {
       imprint_chain(std::false_type{});
     }
@@ -969,22 +967,25 @@ __global__ void __launch_bounds__(256) count_visited_kernel(const DevStroke* str
 
 // variants by maximum block size: smaller CTAs get a larger register budget. The scratch variant only exists for the
 // shape very large footprints use (clusters of 512-thread CTAs).
-template <typename T, bool CL, bool MULTI>
+template <typename T, bool CL, int MODE>
 const void* kernel_ptr_b(int block, bool scr) {
   if constexpr (CL) {
-    if (scr) return reinterpret_cast<const void*>(imprint_kernel<T, true, 512, MULTI, true>);
+    if (scr) return reinterpret_cast<const void*>(imprint_kernel<T, true, 512, MODE, true>);
   }
-  if (block <= 256) return reinterpret_cast<const void*>(imprint_kernel<T, CL, 256, MULTI, false>);
-  return reinterpret_cast<const void*>(imprint_kernel<T, CL, 512, MULTI, false>);
+  if (block <= 256) return reinterpret_cast<const void*>(imprint_kernel<T, CL, 256, MODE, false>);
+  return reinterpret_cast<const void*>(imprint_kernel<T, CL, 512, MODE, false>);
 }
 template <typename T>
-const void* kernel_ptr_t(bool cl, int block, bool multi, bool scr) {
-  if (multi) return cl ? kernel_ptr_b<T, true, true>(block, scr) : kernel_ptr_b<T, false, true>(block, scr);
-  return cl ? kernel_ptr_b<T, true, false>(block, scr) : kernel_ptr_b<T, false, false>(block, scr);
+const void* kernel_ptr_t(bool cl, int block, int mode, bool scr) {
+  if (mode == 2) return cl ? kernel_ptr_b<T, true, 2>(block, scr) : kernel_ptr_b<T, false, 2>(block, scr);
+  if (mode == 1) return cl ? kernel_ptr_b<T, true, 1>(block, scr) : kernel_ptr_b<T, false, 1>(block, scr);
+  return cl ? kernel_ptr_b<T, true, 0>(block, scr) : kernel_ptr_b<T, false, 0>(block, scr);
 }
-const void* kernel_ptr(int precision, bool cl, int block, bool multi, bool scr) {
-  return precision == PB_F64 ? kernel_ptr_t<double>(cl, block, multi, scr) : kernel_ptr_t<float>(cl, block, multi, scr);
+// mode: 0 single GPU, 1 multi GPU without / 2 with the band-view chain
+const void* kernel_ptr(int precision, bool cl, int block, int mode, bool scr) {
+  return precision == PB_F64 ? kernel_ptr_t<double>(cl, block, mode, scr) : kernel_ptr_t<float>(cl, block, mode, scr);
 }
+int launch_mode(const ImprintLaunch& L) { return L.n_bands > 1 ? (L.views_kernel ? 2 : 1) : 0; }
 
 int env_int(const char* name, int fallback) {
   const char* e = std::getenv(name);
@@ -1073,15 +1074,15 @@ void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& sme
   static std::mutex cache_mutex;  // contexts of different devices may plan from different host threads
   std::lock_guard<std::mutex> lock(cache_mutex);
   static std::map<std::tuple<int, int, int, int, size_t>, int> cache;
-  const bool multi = L.n_bands > 1;
-  const auto key   = std::make_tuple(ctx->device, ctx->precision * 2 + (multi ? 1 : 0), cluster, block, smem_bytes);
+  const int mode = launch_mode(L);
+  const auto key = std::make_tuple(ctx->device, ctx->precision * 4 + mode, cluster, block, smem_bytes);
   auto it        = cache.find(key);
   if (it != cache.end()) {
     L.grid = it->second;
     return;
   }
   PB_REQUIRE(L.cells_in_smem || (cluster > 1 && block == 512), "footprint too large for this launch shape");
-  const void* fn = kernel_ptr(ctx->precision, cluster > 1, block, multi, !L.cells_in_smem);
+  const void* fn = kernel_ptr(ctx->precision, cluster > 1, block, mode, !L.cells_in_smem);
   PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget)));
   if (cluster > 8) PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   if (cluster == 1) {
@@ -1109,14 +1110,14 @@ void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& sme
   cache[key] = L.grid;
 }
 
-void imprint_launch(pb_context* ctx, const ImprintLaunch& L, size_t smem_bytes) {
+void imprint_launch(pb_context* ctx, const ImprintLaunch& L, size_t smem_bytes, cudaStream_t stream) {
   if (L.n_strokes <= 0) return;
-  const void* fn = kernel_ptr(ctx->precision, L.cluster > 1, L.block, L.n_bands > 1, !L.cells_in_smem);
+  const void* fn = kernel_ptr(ctx->precision, L.cluster > 1, L.block, launch_mode(L), !L.cells_in_smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim            = dim3(static_cast<unsigned>(L.grid));
   cfg.blockDim           = dim3(static_cast<unsigned>(L.block));
   cfg.dynamicSmemBytes   = smem_bytes;
-  cfg.stream             = ctx->stream;
+  cfg.stream             = stream ? stream : ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id               = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(L.cluster);

@@ -47,7 +47,8 @@ struct alignas(16) DevStroke {
   int32_t flags;      // kStroke*
   float eps;          // half width of the undecided band of the single-precision hit test (imprint_geom.hpp)
   int32_t win_ox, win_cols;  // staging windows: canvas columns [win_ox, win_ox + win_cols), multiples of 4
-  int32_t pad[2];            // 128 bytes: the kernel copies the record into shared memory in 16-byte pieces
+  int32_t flag_index;        // progress word of this stroke in the executor's flag array (its number among the rank's strokes)
+  int32_t pad;               // 128 bytes: the kernel copies the record into shared memory in 16-byte pieces
 };
 static_assert(sizeof(DevStroke) == 128, "DevStroke layout");
 
@@ -92,7 +93,11 @@ struct ImprintLaunch {
   const DevWindow* windows;      // per segment (multi GPU, strokes with kStrokeWindows); may be null otherwise
   long long* done[kMaxBands];    // per-rank progress words ([my_band] is local): (epoch << 32) | segments completed
   int epoch;
-  int flag_offset;               // flag index of this launch's stroke 0 (strokes of earlier launches come first)
+  // Multi GPU: a run of strokes is split over TWO concurrent launches — the strokes that stay inside the executor's band
+  // (kernel variant without the band-view chain: exactly the single-GPU code plus system-scope progress words) and the
+  // straddling strokes (variant with the view chain, on a second stream). Compiled into one kernel, the view chain's
+  // register pressure slowed EVERY stroke by 40-50 % (r = 151: 20.6 instead of 13.8 us per imprint). views_kernel selects.
+  int views_kernel;
   int* queue;                    // single counter (zeroed): tickets
   const int32_t* order;          // ticket -> stroke of this launch (host-planned claim order); nullptr = identity
   unsigned long long* counters;  // [0] active stroke-pixels
@@ -126,7 +131,7 @@ double imprint_cost_us(int n_active, int policy);
 // thread-block cluster of `cluster` CTAs x `block` threads.
 void imprint_plan(pb_context* ctx, int max_active, ImprintLaunch& L, size_t& smem_bytes);  // reads L.n_bands, L.policy
 int imprint_cluster_class(int n_active, int policy);
-void imprint_launch(pb_context* ctx, const ImprintLaunch& L, size_t smem_bytes);
+void imprint_launch(pb_context* ctx, const ImprintLaunch& L, size_t smem_bytes, cudaStream_t stream = nullptr);  // nullptr: ctx->stream
 // concurrent strokes of a launch shape (resident clusters), for the host's claim-order model
 int imprint_slots(const ImprintLaunch& L);
 
