@@ -30,6 +30,8 @@ import argparse
 import json
 import math
 import os
+
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # persistent kernels on several streams / GPUs: no load-time syncs
 import subprocess
 import sys
 import threading

@@ -7,6 +7,9 @@ There is no CPU fallback: importing works anywhere (so that symbol checks can ru
 creating a Context without a B200 raises PaintyError.
 """
 import ctypes as C
+import os as _os
+
+_os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # see pb_context_create: no load-time syncs behind persistent kernels
 import os
 
 import numpy as np

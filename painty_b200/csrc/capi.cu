@@ -750,14 +750,26 @@ void run_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo
         : strokes(cx_, RP.ds.size()), preds(cx_, RP.preds.size()), seg_off(cx_, RP.seg_off.size()), order(cx_, RP.order.size()),
           scratch(cx_, scratch_bytes), windows(cx_, window_bytes), win_desc(cx_, multi_ ? RP.windows.size() : 0) {}
   };
-  // clusters: upper bound of resident clusters this launch may take (0 = all that fit)
-  auto launch_run = [&](const RunPlan& RP, int clusters, cudaStream_t stream) -> std::unique_ptr<LaunchBuffers> {
-    const size_t n_run = RP.ds.size();
+  struct Prepared {
     ImprintLaunch L{};
+    size_t smem = 0;
+    std::unique_ptr<LaunchBuffers> B;
+  };
+  // Everything of a launch except the launch itself (uploads on the main stream). clusters: upper bound of resident clusters
+  // the launch may take (0 = all that fit).
+  auto prepare_run = [&](const RunPlan& RP, int clusters) -> Prepared {
+    Prepared out;
+    const size_t n_run = RP.ds.size();
+    ImprintLaunch& L = out.L;
     L.n_bands      = multi ? dist->world : 1;
     L.policy       = P.policy;
     L.views_kernel = (multi && RP.views) ? 1 : 0;
-    size_t smem    = 0;
+    static const unsigned long long kWatchdogNs = [] {
+      const char* e = std::getenv("PB_IMPRINT_WATCHDOG_S");
+      return static_cast<unsigned long long>((e ? std::atof(e) : 60.0) * 1e9);
+    }();
+    L.watchdog_ns  = kWatchdogNs;
+    size_t& smem   = out.smem;
     imprint_plan(ctx, RP.max_active, L, smem);
     if (clusters > 0) L.grid = std::min(L.grid, clusters * L.cluster);
     L.grid = static_cast<int>(std::min<int64_t>(L.grid, static_cast<int64_t>(n_run) * L.cluster));
@@ -815,19 +827,19 @@ void run_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo
     L.seg_off     = B->seg_off.p;
     L.counters    = b->d_counters;
     L.trace       = b->d_trace;
-    if (stream != nullptr) {  // everything enqueued on the main stream so far (uploads, memsets) precedes the forked launch
-      PB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
-      PB_CUDA(cudaStreamWaitEvent(stream, ctx->ev_fork, 0));
-    }
-    imprint_launch(ctx, L, smem, stream);
-    if (b->count_visited) imprint_count_visited(ctx, B->strokes.p, L.n_strokes, d_im.p, c->rows, c->cols, b->d_counters + 1);
-    return B;
+    out.B         = std::move(B);
+    return out;
+  };
+  auto count_visited = [&](const Prepared& pr) {
+    if (b->count_visited) imprint_count_visited(ctx, pr.B->strokes.p, pr.L.n_strokes, d_im.p, c->rows, c->cols, b->d_counters + 1);
   };
   for (size_t i = 0; i < P.runs.size(); ++i) {
     const RunPlan& RP = P.runs[i];
     const bool paired = multi && i + 1 < P.runs.size() && P.runs[i + 1].group == RP.group;
     if (!paired) {
-      auto keep = launch_run(RP, 0, nullptr);
+      const Prepared pr = prepare_run(RP, 0);
+      imprint_launch(ctx, pr.L, pr.smem, nullptr);
+      count_visited(pr);
       continue;
     }
     // the run's two launches run side by side: the straddling strokes on the second stream with their share of the
@@ -847,10 +859,18 @@ void run_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo
     const int total   = imprint_slots(Lq);
     PB_REQUIRE(total >= 2, "multi-GPU stroke batches need room for two resident thread-block clusters of the launch shape");
     const int n_views = std::min<int>(std::max(1, static_cast<int>(std::lround(total * VP.share))), std::max(1, total - 1));
-    auto keep_views = launch_run(VP, n_views, ctx->aux_stream);
-    auto keep_main  = launch_run(RP, std::max(1, total - n_views), nullptr);
+    // The two kernels wait for each other's strokes: nothing that can block the host (a first-use module load, a
+    // synchronous copy) may come between their launches — prepare both, then launch back to back.
+    const Prepared pv = prepare_run(VP, n_views);
+    const Prepared pm = prepare_run(RP, std::max(1, total - n_views));
+    PB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));  // uploads and memsets of both launches precede the forked one
+    PB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    imprint_launch(ctx, pv.L, pv.smem, ctx->aux_stream);
+    imprint_launch(ctx, pm.L, pm.smem, nullptr);
     PB_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    count_visited(pv);
+    count_visited(pm);
     ++i;
   }
   if (!multi) records_to_planes(ctx, b->work_rec, c->pl, conv.x0, conv.y0, conv.x1, conv.y1);
@@ -879,6 +899,10 @@ int pb_version(void) { return 100; }
 // ---- context -------------------------------------------------------------------------------------
 int pb_context_create(int device, int precision, pb_context** out) {
   PB_API_BEGIN
+  // Persistent kernels wait for each other across streams and GPUs; a lazily loaded kernel module would be loaded at its
+  // first launch or attribute query, which synchronises the context — behind kernels that may be waiting for exactly that
+  // launch. Load everything up front (no effect once the CUDA runtime of this process is initialised).
+  setenv("CUDA_MODULE_LOADING", "EAGER", 0);
   PB_REQUIRE(out != nullptr, "pb_context_create: out is null");
   PB_REQUIRE(precision == PB_F32 || precision == PB_F64, "precision must be PB_F32 or PB_F64");
   int count = 0;

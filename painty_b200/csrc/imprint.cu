@@ -33,6 +33,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -647,12 +648,37 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
         for (int p = pb0 + tid; p < pb1; p += bd) {
           const int2 pr        = L.preds[p];
           const long long want = (static_cast<long long>(L.epoch) << 32) | static_cast<unsigned>(pr.y);
+          // Watchdog: a wait that lasts longer than L.watchdog_ns (default 60 s, PB_IMPRINT_WATCHDOG_S; 0 = off) cannot be a
+          // legitimate dependency: report it and stop the kernel instead of hanging the device.
+          unsigned polls = 0;
+          unsigned long long t0 = 0;
+          auto stuck = [&](long long have) {
+            if (L.watchdog_ns == 0 || (++polls & 1023u) != 0u) return false;
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            if (now - t0 < L.watchdog_ns) return false;
+            printf("painty_b200 imprint watchdog: band %d stroke %lld (flag %d, segment %d, kernel mode %d) waits for band %d flag %d: "
+                   "wants %llx, sees %llx\n",
+                   L.my_band, static_cast<long long>(si), st.flag_index, k, MODE, MULTI ? (pr.x >> 27) : 0, MULTI ? (pr.x & 0x7ffffff) : pr.x,
+                   static_cast<unsigned long long>(want), static_cast<unsigned long long>(have));
+            __trap();
+            return true;
+          };
           if (MULTI) {  // the predecessor may run on another GPU: poll its progress word through NVLink
             const long long* flag = L.done[pr.x >> 27] + (pr.x & 0x7ffffff);
-            while (ld_acquire64_sys(flag) < want) __nanosleep(256);
+            long long have;
+            while ((have = ld_acquire64_sys(flag)) < want) {
+              if (stuck(have)) break;
+              __nanosleep(256);
+            }
           } else {
             const long long* flag = L.done[0] + pr.x;
-            while (ld_acquire64(flag) < want) __nanosleep(64);
+            long long have;
+            while ((have = ld_acquire64(flag)) < want) {
+              if (stuck(have)) break;
+              __nanosleep(64);
+            }
           }
         }
       }

@@ -98,6 +98,7 @@ struct ImprintLaunch {
   // straddling strokes (variant with the view chain, on a second stream). Compiled into one kernel, the view chain's
   // register pressure slowed EVERY stroke by 40-50 % (r = 151: 20.6 instead of 13.8 us per imprint). views_kernel selects.
   int views_kernel;
+  unsigned long long watchdog_ns;  // longest legitimate dataflow wait (0 = no watchdog), see seg_wait
   int* queue;                    // single counter (zeroed): tickets
   const int32_t* order;          // ticket -> stroke of this launch (host-planned claim order); nullptr = identity
   unsigned long long* counters;  // [0] active stroke-pixels
