@@ -448,6 +448,7 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
   std::vector<int32_t> claim_pos;  // global stroke -> position in the claim sequence (empty = submission order)
   std::vector<int64_t> counts64(n);
   for (size_t s = 0; s < n; ++s) counts64[s] = hs[s].n;
+  constexpr double kViewsCost = 1.75;
   auto simulate = [&](int pol, std::vector<int32_t>& pos) -> double {  // model makespan of the batch under policy `pol`
     policy = pol;
     std::vector<ClaimSpec> spec(n);
@@ -464,7 +465,9 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
         slots[r].push_back(static_cast<int>(std::min<int64_t>(imprint_slots(L), n_run)));
         for (size_t k = runs[j].first; k < runs[j].second; ++k) {
           const size_t s = locals[r][k];
-          spec[s]        = ClaimSpec{r, static_cast<int32_t>(j), imprint_cost_us(hs[s].g->n_active, pol)};
+          // straddling strokes run in the kernel variant with the band-view chain: ~1.75x the latency per imprint
+          // (scratch/dist_micro.py: r = 151 along a band boundary 23.2 us against 12.4 us inside the band)
+          spec[s] = ClaimSpec{r, static_cast<int32_t>(j), imprint_cost_us(hs[s].g->n_active, pol) * ((multi && remote[s]) ? kViewsCost : 1.0)};
         }
       }
     }
@@ -685,7 +688,9 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
           }
           for (int32_t k : RP.order)
             if (new_index[static_cast<size_t>(k)] >= 0) S.order.push_back(new_index[static_cast<size_t>(k)]);
-          S.share = (want_views ? imprints_views : imprints_all - imprints_views) / std::max(imprints_all, 1.0);
+          // share of the run's work: imprints weighted with the view chain's cost factor
+          const double w_views = 1.75 * imprints_views, w_main = imprints_all - imprints_views;
+          S.share = (want_views ? w_views : w_main) / std::max(w_views + w_main, 1.0);
           return S;
         };
         RunPlan main_part = subset(false), views_part = subset(true);
