@@ -580,47 +580,27 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
       d.flag_index = static_cast<int32_t>(run_begin + k);
       const int nseg = plan.seg_first[s + 1] - plan.seg_first[s];
       const size_t win_first = run_windows.size();
-      run_windows.resize(win_first + static_cast<size_t>(nseg), DevWindow{{-1, -1}, {0, 0}, {0, 0}});
+      run_windows.resize(win_first + static_cast<size_t>(nseg), DevWindow{0, 0, 0, 0});
       if (multi && remote[s]) {
-        // Per dataflow segment, the part of the segment's region in a neighbour's band is staged in a local window
-        // (<= 2 neighbours, bounded size); anything larger falls back to direct peer accesses with system-scope fences.
-        const Region& r = allowed[s];
-        const int rpb = dist->rows_per_band;
-        const int ox = r.x0 & ~3, wc = ((r.x1 - ox + 1) + 3) & ~3;
+        // Per dataflow segment, the segment's whole region (own rows and neighbour rows) is staged in a local window.
         const int half = (h.g->side - 1) / 2;
         size_t bytes = 0;
-        bool ok = std::getenv("PB_DIST_DIRECT") == nullptr;  // env: force the direct path (tests)
-        for (int k2 = 0; k2 < nseg && ok; ++k2) {
+        for (int k2 = 0; k2 < nseg; ++k2) {
           Region sbox, sall;
           const int64_t len = plan.seg_len[s];
           imprint_regions(h.first + k2 * len, std::min<int64_t>(len, h.n - k2 * len), half, h.radius, cx, cy, c->rows, c->cols, sbox,
                           sall);
-          if (sall.y1 < sall.y0) continue;
           DevWindow& w = run_windows[win_first + static_cast<size_t>(k2)];
-          int nw = 0;
-          for (int bnd = sall.y0 / rpb; bnd <= sall.y1 / rpb && ok; ++bnd) {
-            if (bnd == dist->rank) continue;
-            if (nw == 2) {
-              ok = false;
-              break;
-            }
-            const int g0 = std::max(sall.y0, bnd * rpb), g1 = std::min(sall.y1, std::min((bnd + 1) * rpb, c->rows) - 1);
-            w.band[nw] = bnd;
-            w.row0[nw] = g0 - bnd * rpb;
-            w.rows[nw] = g1 - g0 + 1;
-            bytes = std::max(bytes, static_cast<size_t>(w.rows[nw]) * wc * (2 * kRecord * ctx->esize() + 2) + 64);
-            ++nw;
-          }
+          if (sall.y1 < sall.y0 || sall.x1 < sall.x0) continue;  // nothing on the canvas: an empty window
+          w.x0   = sall.x0 & ~3;
+          w.cols = ((sall.x1 - w.x0 + 1) + 3) & ~3;
+          w.y0   = sall.y0;
+          w.rows = sall.y1 - sall.y0 + 1;
+          bytes  = std::max(bytes, static_cast<size_t>(w.rows) * w.cols * (2 * kRecord * ctx->esize() + 2) + 64);
         }
-        if (ok && bytes <= (size_t(192) << 20)) {
-          d.win_ox   = ox;
-          d.win_cols = wc;
-          d.flags |= kStrokeWindows;
-          max_window = std::max(max_window, (bytes + 255) / 256 * 256);
-        } else {
-          for (int k2 = 0; k2 < nseg; ++k2) run_windows[win_first + static_cast<size_t>(k2)] = DevWindow{{-1, -1}, {0, 0}, {0, 0}};
-          d.flags |= kStrokeDirect;
-        }
+        PB_REQUIRE(bytes <= (size_t(2) << 30), "footprint too large for a multi-GPU staging window");
+        d.flags |= kStrokeWindows;
+        max_window = std::max(max_window, (bytes + 255) / 256 * 256);
       }
       max_active = std::max(max_active, d.n_active);
       d.seg_begin = static_cast<int32_t>(run_seg_off.size()) - 1;
@@ -653,7 +633,7 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
     if (multi) {
       // Split the run: strokes inside the band -> the launch without the view chain, straddling strokes -> the launch
       // with it. Each part keeps the run's claim order among its own strokes.
-      auto is_views = [&](size_t k) { return (RP.ds[k].flags & (kStrokeDirect | kStrokeWindows)) != 0; };
+      auto is_views = [&](size_t k) { return (RP.ds[k].flags & kStrokeWindows) != 0; };
       size_t n_views = 0;
       double imprints_all = 0.0, imprints_views = 0.0;
       for (size_t k = 0; k < n_run; ++k) {
@@ -815,7 +795,7 @@ void run_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo
     L.n_strokes       = static_cast<int64_t>(n_run);
 
     const size_t n_slots = static_cast<size_t>(imprint_slots(L));
-    auto B = std::make_unique<LaunchBuffers>(ctx, RP, static_cast<size_t>(L.scratch_stride) * L.grid, 2 * RP.max_window * n_slots, multi);
+    auto B = std::make_unique<LaunchBuffers>(ctx, RP, static_cast<size_t>(L.scratch_stride) * L.grid, RP.max_window * n_slots, multi);
     B->order.upload(RP.order.data(), RP.order.size());
     B->strokes.upload(RP.ds.data(), RP.ds.size());
     B->preds.upload(RP.preds.data(), RP.preds.size());
@@ -824,7 +804,7 @@ void run_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo
     L.order       = RP.order.empty() ? nullptr : B->order.p;
     L.windows     = multi ? B->win_desc.p : nullptr;
     L.win_scratch = B->windows.p;
-    L.win_stride  = static_cast<int64_t>(2 * RP.max_window);
+    L.win_stride  = static_cast<int64_t>(RP.max_window);
     L.scratch     = B->scratch.p;
     L.strokes     = B->strokes.p;
     L.imprints    = d_im.p;

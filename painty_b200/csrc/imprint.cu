@@ -357,11 +357,10 @@ __device__ __forceinline__ void ring_scan(T* own_can, T* own_src, unsigned char*
         ring_list_item(rl, t, row[q], x0, j);
         int lrow = row[q] - X.store_first, pitch = X.pitch;
         const unsigned char* dbase = own_dirty;
-        if (VIEWS) {
-          const int band = ring_band_of(X, row[q]);
-          lrow           = row[q] - band * X.rows_per_band;
-          pitch          = views[band].pitch;
-          dbase          = views[band].dirty;
+        if (VIEWS) {  // the segment's window: indexed with global rows
+          lrow  = row[q];
+          pitch = views[0].pitch;
+          dbase = views[0].dirty;
         }
         w[q]    = ((lrow * pitch + x0) >> 2) + j;
         word[q] = ld_word<L1C>(reinterpret_cast<const unsigned*>(dbase) + w[q]);
@@ -374,9 +373,8 @@ __device__ __forceinline__ void ring_scan(T* own_can, T* own_src, unsigned char*
       if (word[q] == 0u) continue;
       int lrow = row[q] - X.store_first, pitch = X.pitch;
       if (VIEWS) {
-        const int band = ring_band_of(X, row[q]);
-        lrow           = row[q] - band * X.rows_per_band;
-        pitch          = views[band].pitch;
+        lrow  = row[q];
+        pitch = views[0].pitch;
       }
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
@@ -401,10 +399,7 @@ __device__ __forceinline__ void ring_scan(T* own_can, T* own_src, unsigned char*
           }
           f[k]         = 4 * wq + (bit & 3);
           const T* can = own_can;
-          if (VIEWS) {
-            bnd[k] = ring_band_of(X, rq);
-            can    = views[bnd[k]].can;
-          }
+          if (VIEWS) can = views[0].can;
           rec[k] = ld_rec<L1C>(can + static_cast<int64_t>(f[k]) * kRecord);
         }
       }
@@ -415,9 +410,9 @@ __device__ __forceinline__ void ring_scan(T* own_can, T* own_src, unsigned char*
           unsigned char* dirty   = own_dirty;
           unsigned char* touched = nullptr;
           if (VIEWS) {
-            src     = views[bnd[k]].src;
-            dirty   = views[bnd[k]].dirty;
-            touched = views[bnd[k]].touched;
+            src     = views[0].src;
+            dirty   = views[0].dirty;
+            touched = views[0].touched;
           }
           st_rec<L1C>(src + static_cast<int64_t>(f[k]) * kRecord, rec[k]);
           st_byte<L1C>(dirty + f[k], static_cast<unsigned char>(0));
@@ -429,17 +424,22 @@ __device__ __forceinline__ void ring_scan(T* own_can, T* own_src, unsigned char*
 }
 
 // ---- multi-GPU staging windows ------------------------------------------------------------------------------------
-// Layout of one window in the stroke slot's scratch: canvas records | snapshot records (npx records each) | dirty
-// bytes | touched bytes, npx = rows * cols (cols a multiple of 4).
+// A straddling stroke works on a LOCAL copy of its current dataflow segment's whole region (the union of the allowed
+// boxes of the segment's imprints, rows of the executor's own band and of its neighbours alike): one window per stroke
+// slot, laid out as canvas records | snapshot records (npx records each) | dirty bytes | touched bytes, npx = rows * cols
+// (cols a multiple of 4). Inside the segment every pixel access goes to the window through ONE view with a uniform pitch
+// — the same index arithmetic and the same code as a stroke inside the band, no per-pixel band selection. The window is
+// filled when the segment starts (own rows from local HBM, neighbour rows over NVLink) and the pixels the segment
+// touched are written back when it ends.
 template <typename T>
 struct Window {
   T* can;
   T* src;
   unsigned char *dirty, *touched;
-  int band, row0, rows, ox, cols;
-  __device__ __forceinline__ Window(const ImprintLaunch& L, const DevStroke& st, const DevWindow& dw, int slot, int w) {
-    band = dw.band[w], row0 = dw.row0[w], rows = dw.rows[w], ox = st.win_ox, cols = st.win_cols;
-    unsigned char* base = L.win_scratch + static_cast<int64_t>(slot) * L.win_stride + static_cast<int64_t>(w) * (L.win_stride / 2);
+  int x0, y0, rows, cols;
+  __device__ __forceinline__ Window(const ImprintLaunch& L, const DevWindow& dw, int slot) {
+    x0 = dw.x0, y0 = dw.y0, rows = dw.rows, cols = dw.cols;
+    unsigned char* base = L.win_scratch + static_cast<int64_t>(slot) * L.win_stride;
     const int64_t npx   = static_cast<int64_t>(rows) * cols;
     can     = reinterpret_cast<T*>(base);
     src     = can + npx * kRecord;
@@ -448,96 +448,83 @@ struct Window {
   }
 };
 
-// Build the per-band views of a segment and pull its windows from the neighbours' HBM (whole records over NVLink).
+// Build the view of a segment's window (virtual base pointers: index = global row * window cols + column) and fill it.
 template <typename T>
-__device__ __forceinline__ void stage_in(const ImprintLaunch& L, const DevStroke& st, const DevWindow& dw, Band<T>* views, int slot,
-                                         int sgt, int gstride, int tid) {
-  const bool windows = (st.flags & kStrokeWindows) != 0;
-  if (tid < L.n_bands) {
-    Band<T> v(L, tid);
-    if (windows) {
-      for (int w = 0; w < 2; ++w) {
-        if (dw.band[w] != tid) continue;
-        const Window<T> W(L, st, dw, slot, w);
-        const int64_t off = static_cast<int64_t>(W.row0) * W.cols + W.ox;  // virtual base: index = lrow * cols + px
-        v.can     = W.can - off * kRecord;
-        v.src     = W.src - off * kRecord;
-        v.dirty   = W.dirty - off;
-        v.touched = W.touched - off;
-        v.pitch   = W.cols;
-      }
-    }
-    views[tid] = v;
+__device__ __forceinline__ void stage_in(const ImprintLaunch& L, const DevWindow& dw, Band<T>* view, int slot, int sgt, int gstride,
+                                         int tid) {
+  const Window<T> W(L, dw, slot);
+  if (tid == 0) {
+    const int64_t off = static_cast<int64_t>(W.y0) * W.cols + W.x0;
+    Band<T> v;
+    v.can     = W.can - off * kRecord;
+    v.src     = W.src - off * kRecord;
+    v.dirty   = W.dirty - off;
+    v.touched = W.touched - off;
+    v.pitch   = W.cols;
+    *view     = v;
   }
-  if (!windows) return;
-  for (int w = 0; w < 2; ++w) {
-    if (dw.band[w] < 0) continue;
-    const Window<T> W(L, st, dw, slot, w);
-    const int npx = W.rows * W.cols;
-    // two pixels per thread and iteration: the six NVLink loads of a pair are in flight together
+  const int npx = W.rows * W.cols;
+  // two pixels per thread and iteration: the six loads of a pair are in flight together
 #pragma unroll 1
-    for (int i0 = sgt; i0 < npx; i0 += 2 * gstride) {
-      Rec<T> a[2], b[2];
-      unsigned char dflag[2];
-      int idx[2];
+  for (int i0 = sgt; i0 < npx; i0 += 2 * gstride) {
+    Rec<T> a[2], b[2];
+    unsigned char dflag[2];
+    int idx[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int i = i0 + u * gstride;
-        idx[u]      = -1;
-        dflag[u]    = 0;
-        if (i >= npx) continue;
-        const int lr = i / W.cols, c = i - lr * W.cols, px = W.ox + c;
-        idx[u] = i;
-        if (px >= L.cols) {
-          idx[u] = -2 - i;  // outside the canvas: only the flags are initialised
-          continue;
-        }
-        const int64_t gi = static_cast<int64_t>(W.row0 + lr) * L.cols + px;
-        a[u]     = ld_rec(static_cast<const T*>(L.canvas[W.band]) + gi * kRecord);
-        b[u]     = ld_rec(static_cast<const T*>(L.snapshot[W.band]) + gi * kRecord);
-        dflag[u] = __ldcg(L.dirty[W.band] + gi);
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + u * gstride;
+      idx[u]      = -1;
+      dflag[u]    = 0;
+      if (i >= npx) continue;
+      const int lr = i / W.cols, c = i - lr * W.cols, px = W.x0 + c, gy = W.y0 + lr;
+      idx[u] = i;
+      if (px >= L.cols || gy >= L.rows) {
+        idx[u] = -2 - i;  // outside the canvas (column padding): only the flags are initialised
+        continue;
       }
+      const int band   = gy / L.rows_per_band;
+      const int64_t gi = static_cast<int64_t>(gy - band * L.rows_per_band) * L.cols + px;
+      a[u]     = ld_rec(static_cast<const T*>(L.canvas[band]) + gi * kRecord);
+      b[u]     = ld_rec(static_cast<const T*>(L.snapshot[band]) + gi * kRecord);
+      dflag[u] = __ldcg(L.dirty[band] + gi);
+    }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (idx[u] == -1) continue;
-        const int i = idx[u] >= 0 ? idx[u] : -2 - idx[u];
-        __stcg(W.touched + i, static_cast<unsigned char>(0));
-        __stcg(W.dirty + i, dflag[u]);
-        if (idx[u] >= 0) {
-          st_rec(W.can + static_cast<int64_t>(i) * kRecord, a[u]);
-          st_rec(W.src + static_cast<int64_t>(i) * kRecord, b[u]);
-        }
+    for (int u = 0; u < 2; ++u) {
+      if (idx[u] == -1) continue;
+      const int i = idx[u] >= 0 ? idx[u] : -2 - idx[u];
+      __stcg(W.touched + i, static_cast<unsigned char>(0));
+      __stcg(W.dirty + i, dflag[u]);
+      if (idx[u] >= 0) {
+        st_rec(W.can + static_cast<int64_t>(i) * kRecord, a[u]);
+        st_rec(W.src + static_cast<int64_t>(i) * kRecord, b[u]);
       }
     }
   }
 }
 
-// Push back only what this segment changed: untouched pixels may meanwhile have been refreshed by a commuting stroke's
+// Write back only what this segment changed: untouched pixels may meanwhile have been refreshed by a commuting stroke's
 // snapshot ring on their owner (an idempotent copy this window must not undo).
 template <typename T>
-__device__ __forceinline__ void stage_out(const ImprintLaunch& L, const DevStroke& st, const DevWindow& dw, int slot, int sgt,
-                                          int gstride) {
-  for (int w = 0; w < 2; ++w) {
-    if (dw.band[w] < 0) continue;
-    const Window<T> W(L, st, dw, slot, w);
-    const int nwords = W.rows * W.cols / 4;  // the touched map is scanned 4 pixels at a time
-    const int cpr    = W.cols / 4;
+__device__ __forceinline__ void stage_out(const ImprintLaunch& L, const DevWindow& dw, int slot, int sgt, int gstride) {
+  const Window<T> W(L, dw, slot);
+  const int nwords = W.rows * W.cols / 4;  // the touched map is scanned 4 pixels at a time
+  const int cpr    = W.cols / 4;
 #pragma unroll 1
-    for (int i = sgt; i < nwords; i += gstride) {
-      const unsigned t = __ldcg(reinterpret_cast<const unsigned*>(W.touched) + i);
-      if (t == 0u) continue;
-      const int lr = i / cpr, c = (i - lr * cpr) * 4;
+  for (int i = sgt; i < nwords; i += gstride) {
+    const unsigned t = __ldcg(reinterpret_cast<const unsigned*>(W.touched) + i);
+    if (t == 0u) continue;
+    const int lr = i / cpr, c = (i - lr * cpr) * 4, gy = W.y0 + lr;
+    const int band = gy / L.rows_per_band;
 #pragma unroll 1
-      for (int b = 0; b < 4; ++b) {
-        if (((t >> (8 * b)) & 0xffu) == 0u) continue;
-        const int wi = lr * W.cols + c + b, px = W.ox + c + b;
-        const int64_t gi = static_cast<int64_t>(W.row0 + lr) * L.cols + px;
-        const Rec<T> va = ld_rec(W.can + static_cast<int64_t>(wi) * kRecord);
-        const Rec<T> vb = ld_rec(W.src + static_cast<int64_t>(wi) * kRecord);
-        st_rec(static_cast<T*>(L.canvas[W.band]) + gi * kRecord, va);
-        st_rec(static_cast<T*>(L.snapshot[W.band]) + gi * kRecord, vb);
-        __stcg(L.dirty[W.band] + gi, __ldcg(W.dirty + wi));
-      }
+    for (int b = 0; b < 4; ++b) {
+      if (((t >> (8 * b)) & 0xffu) == 0u) continue;
+      const int wi = lr * W.cols + c + b, px = W.x0 + c + b;
+      const int64_t gi = static_cast<int64_t>(gy - band * L.rows_per_band) * L.cols + px;
+      const Rec<T> va = ld_rec(W.can + static_cast<int64_t>(wi) * kRecord);
+      const Rec<T> vb = ld_rec(W.src + static_cast<int64_t>(wi) * kRecord);
+      st_rec(static_cast<T*>(L.canvas[band]) + gi * kRecord, va);
+      st_rec(static_cast<T*>(L.snapshot[band]) + gi * kRecord, vb);
+      __stcg(L.dirty[band] + gi, __ldcg(W.dirty + wi));
     }
   }
 }
@@ -561,7 +548,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_stroke;
   __shared__ unsigned long long s_active;
-  __shared__ Band<T> s_view[MODE == 2 ? kMaxBands : 1];
+  __shared__ Band<T> s_view[1];  // MODE 2: the view of the current segment's staging window
   // Register diet (one CTA of 512 threads leaves 128 registers per thread): everything that is constant over a stroke
   // or an imprint lives in shared memory and is re-read where it is used — the stroke record, the paint constants, and a
   // ring of four imprint records (previous, current, next, and the one being prefetched with cp.async).
@@ -574,9 +561,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
   const int tid = threadIdx.x, bd = blockDim.x;
   const int csize   = CL ? static_cast<int>(cluster.num_blocks()) : 1;
   const int crank   = CL ? static_cast<int>(cluster.block_rank()) : 0;
-  bool remote   = false;  // current stroke touches rows of another GPU directly: barriers need system-scope fences
   auto sync_all = [&]() {
-    if (MULTI && remote) __threadfence_system();
     if (CL) {
       cluster.sync();
     } else {
@@ -585,7 +570,6 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
   };
   // the same barrier in two halves: arrive (release: this thread's stores) ... independent work ... wait (acquire)
   auto sync_arrive = [&]() {
-    if (MULTI && remote) __threadfence_system();
     if (CL) asm volatile("barrier.cluster.arrive.release;" ::: "memory");
   };
   auto sync_wait = [&]() {
@@ -713,7 +697,6 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
         s_ctx.paintS[k] = static_cast<T>(st.paintS[k]);
       }
     }
-    remote = MULTI && (st.flags & kStrokeDirect) != 0;
     const bool two_phase = (st.flags & kStrokeTwoPhase) != 0;
     const int wr = (st.side - 1) / 2;  // == hr (square footprint), FootprintBrush.hxx:75-78
     // The compacted cell list is cut into csize contiguous chunks (neighbouring cells -> neighbouring lanes ->
@@ -754,8 +737,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
       constexpr bool VIEWS = decltype(views_tag)::value;
       constexpr bool L1C   = !CL && !VIEWS;  // one CTA, own band: L1-cached pixel accesses (see ld_rec)
       if (st.n_imprints <= 0) return;
-      const DevWindow* wins = (VIEWS && (st.flags & kStrokeWindows)) ? L.windows + st.seg_begin : nullptr;
-      const DevWindow no_window{{-1, -1}, {0, 0}, {0, 0}};
+      const DevWindow* wins = VIEWS ? L.windows + st.seg_begin : nullptr;  // one staging window per dataflow segment
 
       // Interactions (cell, pixel) of `chunk` of this thread's cells for imprint ii, border phase ph (-1 = all).
       auto build_list = [&](int ii, int chunk, int ph) -> int {
@@ -785,10 +767,9 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
               const int py = h.py[j], px = h.px[j];
               int band = 0, lrow = py - row_lo, pitch = L.cols;
               bool ok = true;
-              if (VIEWS) {
-                band  = band_of(L, py);  // the row's owner GPU
-                lrow  = py - band * L.rows_per_band;
-                pitch = views[band].pitch;
+              if (VIEWS) {  // the segment's window is indexed with global rows
+                lrow  = py;
+                pitch = views[0].pitch;
               } else if (py < row_lo || py > row_hi) {
                 ok = false;  // band canvas without peers: rows outside the stored window are not ours
               }
@@ -840,7 +821,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
       };
 
       if (VIEWS) {
-        stage_in<T>(L, st, wins ? wins[0] : no_window, s_view, slot_id(), scan_id(), scan_stride(), tid);
+        stage_in<T>(L, wins[0], s_view, slot_id(), scan_id(), scan_stride(), tid);
         sync_all();
       }
       // The chain is a flat loop over UNITS (imprint ii, border phase ph, cell chunk): process the unit's list, build
@@ -861,15 +842,15 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
           if (ii == seg_next) {
             ++seg_k;
             seg_next += st.seg_len;
-            if (wins) {  // push the pixels the finished segment touched back into their owners' HBM
-              stage_out<T>(L, st, wins[seg_k - 1], slot_id(), scan_id(), scan_stride());
+            if (wins) {  // write the pixels the finished segment touched back into their owners' HBM
+              stage_out<T>(L, wins[seg_k - 1], slot_id(), scan_id(), scan_stride());
               __threadfence_system();
               sync_all();
             }
             seg_publish(seg_k);
             if (seg_wait(seg_k)) need_full = true;
             if (wins) {
-              stage_in<T>(L, st, wins[seg_k], s_view, slot_id(), scan_id(), scan_stride(), tid);
+              stage_in<T>(L, wins[seg_k], s_view, slot_id(), scan_id(), scan_stride(), tid);
               sync_all();
               n_list    = build_list(ii, 0, ph);  // the views (window pitch) may have changed
               need_full = true;
@@ -930,7 +911,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
         if (done) break;
       }
       if (wins) {
-        stage_out<T>(L, st, wins[seg_k], slot_id(), scan_id(), scan_stride());
+        stage_out<T>(L, wins[seg_k], slot_id(), scan_id(), scan_stride());
         __threadfence_system();
       }
     };

@@ -28,8 +28,7 @@ constexpr int kStrokeDone = 0x7fffffff;  // progress value of a finished stroke
 // DevStroke::flags
 constexpr int kStrokeLoadPick  = 1;   // load the pickup state from the brush's dense map (continue without dip)
 constexpr int kStrokeStorePick = 2;   // store it back after the stroke
-constexpr int kStrokeDirect    = 4;   // rows of another GPU are accessed directly through NVLink (system-scope fences)
-constexpr int kStrokeWindows   = 8;   // they are staged in local windows, one set per dataflow segment
+constexpr int kStrokeWindows   = 8;   // straddling stroke (multi GPU): every dataflow segment works on a local staging window
 constexpr int kStrokeTwoPhase  = 16;  // footprint is not compact: ring pass and main pass are separated by a barrier,
                                       // every ring pass scans the whole ring, hits are decided in f64 only
 
@@ -46,18 +45,19 @@ struct alignas(16) DevStroke {
   int32_t seg_len;    // imprints per dataflow segment (>= 1)
   int32_t flags;      // kStroke*
   float eps;          // half width of the undecided band of the single-precision hit test (imprint_geom.hpp)
-  int32_t win_ox, win_cols;  // staging windows: canvas columns [win_ox, win_ox + win_cols), multiples of 4
+  int32_t win_ox, win_cols;  // unused
   int32_t flag_index;        // progress word of this stroke in the executor's flag array (its number among the rank's strokes)
   int32_t pad;               // 128 bytes: the kernel copies the record into shared memory in 16-byte pieces
 };
 static_assert(sizeof(DevStroke) == 128, "DevStroke layout");
 
-// Multi-GPU staging windows of one dataflow segment: the part of the segment's region that lies in a neighbour's band is
-// pulled into local scratch when the segment starts and the touched pixels are pushed back when it ends (one bulk NVLink
-// transfer each way instead of remote round trips on every imprint). Window w covers band-local rows
-// [row0, row0 + rows) of band[w]; band[w] < 0 = unused.
+// Multi-GPU staging window of one dataflow segment of a straddling stroke: the segment's whole region (union of the
+// allowed boxes of its imprints, clipped to the canvas; x0 and cols multiples of 4) — rows of the executor's own band and
+// of its neighbours alike — is copied into local scratch when the segment starts and the touched pixels are written back
+// when it ends (one bulk transfer each way instead of NVLink round trips on every imprint, and one uniform view for the
+// imprint chain).
 struct DevWindow {
-  int32_t band[2], row0[2], rows[2];
+  int32_t x0, y0, cols, rows;
 };
 
 struct ImprintLaunch {
@@ -105,7 +105,7 @@ struct ImprintLaunch {
   // diagnostics (pb_fbrush_enable_trace): SM cycle stamps of the first kTraceImprints imprints of stroke 0 of the launch,
   // taken by the first and the last thread of the cluster's rank-0 CTA: [imprint][thread][kTraceStamps]; nullptr = off
   unsigned long long* trace;
-  unsigned char* win_scratch;    // staging windows, win_stride bytes per stroke slot (two halves, one per window)
+  unsigned char* win_scratch;    // staging windows, win_stride bytes per stroke slot
   int64_t win_stride;
   // per-CTA cell state in global memory for footprints that do not fit shared memory
   void* scratch;
