@@ -1,5 +1,5 @@
 """Per-imprint latency inside the multi-GPU kernel: one stroke that stays in rank 0's band, and one that runs along the band
-boundary (half of its footprint in rank 1's band: staging windows per segment, or direct peer access with PB_DIST_DIRECT=1).
+boundary (half of its footprint in rank 1's band: one staging window per dataflow segment).
 torchrun --nproc-per-node 2 scratch/dist_micro.py [R1,R2,..] [N_IMPRINTS]   (2 GPUs)"""
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, '.')
@@ -19,6 +19,8 @@ for r in radii:
     br.register_radius(assets.snap_to_safe_radius(r))
 dc.attach(br)
 lib = api.lib()
+if os.environ.get("PB_TRACE"):
+    api._chk(lib.pb_fbrush_enable_trace(br.h, 1))
 for r in radii:
     r = assets.snap_to_safe_radius(r)
     for name, y0 in (("inside band 0", 1000.0), ("along the boundary", 2150.0)):
@@ -38,6 +40,15 @@ for r in radii:
             api._chk(lib.pb_fbrush_dist_end(br.h, dc.canvas.h))
             if rep and rank == 0: best = min(best, e0.elapsed_time(e1))
         if rank == 0:
-            print("r=%5.1f %-20s %7.2f ms  %6.2f us/imprint%s" % (r, name, best, best * 1e3 / n, "  (direct peer access)" if os.environ.get("PB_DIST_DIRECT") else ""), flush=True)
+            print("r=%5.1f %-20s %7.2f ms  %6.2f us/imprint%s" % (r, name, best, best * 1e3 / n, ""), flush=True)
+        if os.environ.get("PB_TRACE") and rank == 0:  # cycle stamps of the last repetition's stroke (thread 0)
+            import ctypes as C
+            out = np.zeros((256, 2, 8), dtype=np.uint64)
+            api._chk(lib.pb_fbrush_read_trace(br.h, out.ctypes.data_as(C.c_void_p)))
+            t = out[:min(n, 256), 0, :5].astype(np.int64)
+            per = np.diff(t[:, 0])
+            seg = [i for i in range(1, len(per)) if (i + 1) % 64 == 0]
+            print("   cycles per imprint: median %d; imprints that start a segment (incl. staging): %s; first interval (ring) there: %s" % (
+                np.median(per), [int(per[i]) for i in seg], [int(t[i + 1, 1] - t[i + 1, 0]) for i in seg]), flush=True)
 dc.close()
 dist.destroy_process_group()
