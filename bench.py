@@ -465,7 +465,7 @@ def main():
                      "compose_ms_in_step": cmp_in_step_ms, "compose_ms_back_to_back": cmp_b2b_ms,
                      # NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one 4K launch from the committed
                      # ncu --set full capture (profiles/r01_compose_f32_raw.csv); null where the launch has another size
-                     "traffic": 401643264 if world == 1 else None, "traffic_source": "ncu constant (profiles/r01_compose_f32_raw.csv)",
+                     "traffic": 404830464 if world == 1 else None, "traffic_source": "ncu constant (profiles/r02_compose_f32_raw.csv)",
                      "algorithmic_bytes_per_launch": COMPOSE_BYTES_PER_PX * n_px, "frac_of_8TBs_nominal": achieved / 8000.0},
     }
     # the step's dominant kernel is the imprint chain: a dependency chain of imprints whose working set lives in L2, bound by

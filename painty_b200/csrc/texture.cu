@@ -63,29 +63,37 @@ struct Edge {
 __device__ __forceinline__ void mvc(const double2* __restrict__ poly, const double2* __restrict__ uv, int n, double x,
                                     double y, double& ou, double& ov) {
   const double Eps = 2.220446049250313e-16 * 100.0;
-  auto edge = [&](int i, double2& si, double2& si1) {
+  // r_i = |p_i - x| is needed by edge i - 1 (as r_{i+1}) and by edge i: it is computed once and carried over (the same
+  // expression on the same operands, so the value is the one the reference recomputes)
+  auto dist = [&](int i) {
+    const double2 p = poly[i];
+    const double dx = p.x - x, dy = p.y - y;
+    return sqrt(dx * dx + dy * dy);
+  };
+  auto edge = [&](int i, double r_i, double2& si, double2& si1) {
     const double2 p = poly[i], q = poly[i == n - 1 ? 0 : i + 1];
     si  = make_double2(p.x - x, p.y - y);
     si1 = make_double2(q.x - x, q.y - y);
     Edge e;
-    e.r = sqrt(si.x * si.x + si.y * si.y);
+    e.r = r_i;
     e.A = (si.x * si1.y - si1.x * si.y) / 2.0;
     e.D = si.x * si1.x + si.y * si1.y;
     return e;
   };
   double2 s0, s1;
-  Edge prev = edge(n - 1, s0, s1);  // A_{i-1}, r_{i-1}, D_{i-1} for i = 0
-  const double r_first = sqrt((poly[0].x - x) * (poly[0].x - x) + (poly[0].y - y) * (poly[0].y - y));
+  const double r_first = dist(0);
+  Edge prev = edge(n - 1, dist(n - 1), s0, s1);  // A_{i-1}, r_{i-1}, D_{i-1} for i = 0
   double fu = 0.0, fv = 0.0, W = 0.0;
+  double r_cur = r_first;
   for (int i = 0; i < n; ++i) {
-    const Edge cur = edge(i, s0, s1);
+    const Edge cur = edge(i, r_cur, s0, s1);
+    const double ri1 = (i == n - 1) ? r_first : sqrt(s1.x * s1.x + s1.y * s1.y);  // r_{i+1}
     if (fabs(cur.r - 0.0) < Eps) {  // :102-104
       ou = uv[i].x;
       ov = uv[i].y;
       return;
     }
     if (fabs(cur.A - 0.0) < Eps && cur.D < 0.0) {  // :114-119
-      const double ri1 = sqrt(s1.x * s1.x + s1.y * s1.y);
       const double2 f1 = uv[i == n - 1 ? 0 : i + 1];
       const double sc  = 1.0 / (cur.r + ri1);
       ou = (ri1 * uv[i].x + cur.r * f1.x) * sc;
@@ -94,14 +102,12 @@ __device__ __forceinline__ void mvc(const double2* __restrict__ poly, const doub
     }
     double w = 0.0;
     if (prev.A != 0.0) w = w + (prev.r - prev.D / cur.r) / prev.A;
-    if (cur.A != 0.0) {
-      const double ri1 = (i == n - 1) ? r_first : sqrt(s1.x * s1.x + s1.y * s1.y);
-      w                = w + (ri1 - cur.D / cur.r) / cur.A;
-    }
+    if (cur.A != 0.0) w = w + (ri1 - cur.D / cur.r) / cur.A;
     fu = fu + w * uv[i].x;
     fv = fv + w * uv[i].y;
     W  = W + w;
-    prev = cur;
+    prev  = cur;
+    r_cur = ri1;
   }
   if (!(fabs(W - 0.0) < Eps)) {
     const double sc = 1.0 / W;
