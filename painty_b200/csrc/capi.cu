@@ -846,21 +846,8 @@ void run_plan(pb_fbrush* b, pb_canvas* c, const pb_batch_plan& P, const DistInfo
     const int n_views = std::min<int>(std::max(1, static_cast<int>(std::lround(total * VP.share))), std::max(1, total - 1));
     // The two kernels wait for each other's strokes: nothing that can block the host (a first-use module load, a
     // synchronous copy) may come between their launches — prepare both, then launch back to back.
-    Prepared pv = prepare_run(VP, n_views);
+    const Prepared pv = prepare_run(VP, n_views);
     const Prepared pm = prepare_run(RP, std::max(1, total - n_views));
-    // Work stealing, one way: the straddlers' launch (it contains both chains) continues with in-band strokes of the run
-    // once its own queue is empty — same claim order, shared ticket counter. Only for batches the planner found to be
-    // bound by the number of concurrent strokes (throughput policy): in-band strokes run ~1.5x slower in that kernel, which
-    // a batch bound by its critical path cannot afford (4K weak-scaling bench at N = 2: 4.97 s per step with stealing,
-    // 4.50 s without).
-    if (P.policy == kShapeThroughput) {
-      pv.L.strokes2   = pm.L.strokes;
-      pv.L.n_strokes2 = pm.L.n_strokes;
-      pv.L.preds2     = pm.L.preds;
-      pv.L.seg_off2   = pm.L.seg_off;
-      pv.L.order2     = pm.L.order;
-      pv.L.queue2     = pm.L.queue;
-    }
     PB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));  // uploads and memsets of both launches precede the forked one
     PB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
     imprint_launch(ctx, pv.L, pv.smem, ctx->aux_stream);

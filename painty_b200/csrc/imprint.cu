@@ -611,25 +611,13 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
     sync_all();
     if (crank == 0 && tid == 0) {
       const long long ticket = atomicAdd(L.queue, 1);
-      long long s = -1;  // -1: no work left; bit 40 set: a stroke of the concurrent in-band launch (set 2)
-      if (ticket < L.n_strokes) {
-        s = L.order != nullptr ? static_cast<long long>(L.order[ticket]) : ticket;
-      } else if (MODE == 2 && L.n_strokes2 > 0) {
-        const long long t2 = atomicAdd(L.queue2, 1);
-        if (t2 < L.n_strokes2) s = (L.order2 != nullptr ? static_cast<long long>(L.order2[t2]) : t2) | (1ll << 40);
-      }
-      s_stroke = s;
+      s_stroke = (ticket < L.n_strokes && L.order != nullptr) ? static_cast<long long>(L.order[ticket]) : ticket;
     }
     sync_all();
-    const long long popped = CL ? *cluster.map_shared_rank(&s_stroke, 0) : s_stroke;
-    if (popped < 0) break;
-    const bool set2   = MODE == 2 && (popped >> 40) != 0;
-    const int64_t si  = popped & ((1ll << 40) - 1);
-    const DevStroke* const strokes = set2 ? L.strokes2 : L.strokes;
-    const int2* const preds        = set2 ? L.preds2 : L.preds;
-    const int32_t* const seg_off   = set2 ? L.seg_off2 : L.seg_off;
+    const int64_t si = CL ? *cluster.map_shared_rank(&s_stroke, 0) : s_stroke;
+    if (si >= L.n_strokes) break;
     static_assert(sizeof(DevStroke) == 128, "DevStroke is copied in eight 16-byte pieces");
-    if (tid < 8) cp_async16(reinterpret_cast<char*>(&s_st) + 16 * tid, reinterpret_cast<const char*>(strokes + si) + 16 * tid);
+    if (tid < 8) cp_async16(reinterpret_cast<char*>(&s_st) + 16 * tid, reinterpret_cast<const char*>(L.strokes + si) + 16 * tid);
     if (tid < 8) cp_async_wait_all();
     __syncthreads();
     const DevStroke& st = s_st;
@@ -638,11 +626,11 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
     // stroke has finished the segments whose region meets segment k's (host-built lists of (stroke, segments
     // needed)); strokes publish their progress at segment boundaries. Returns whether there was anything to wait for.
     auto seg_wait = [&](int k) -> bool {
-      const int pb0 = seg_off[st.seg_begin + k], pb1 = seg_off[st.seg_begin + k + 1];
+      const int pb0 = L.seg_off[st.seg_begin + k], pb1 = L.seg_off[st.seg_begin + k + 1];
       if (pb1 == pb0) return false;
       if (crank == 0) {
         for (int p = pb0 + tid; p < pb1; p += bd) {
-          const int2 pr        = preds[p];
+          const int2 pr        = L.preds[p];
           const long long want = (static_cast<long long>(L.epoch) << 32) | static_cast<unsigned>(pr.y);
           // Watchdog: a wait that lasts longer than L.watchdog_ns (default 60 s, PB_IMPRINT_WATCHDOG_S; 0 = off) cannot be a
           // legitimate dependency: report it and stop the kernel instead of hanging the device.
@@ -840,7 +828,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
       // the list of the next unit (geometry only, so the one that starts the next imprint is built before the barrier),
       // and synchronise whenever the next unit starts a new phase or imprint. One build site, one process site.
       const int chunks = max((my_cells + L.chunk_cells - 1) / L.chunk_cells, 1);
-      const bool tracing = L.trace != nullptr && si == 0 && !set2 && crank == 0 && (tid == 0 || tid == bd - 1);
+      const bool tracing = L.trace != nullptr && si == 0 && crank == 0 && (tid == 0 || tid == bd - 1);
       auto stamp = [&](int i, int slot) {
         if (tracing && i < kTraceImprints) L.trace[(i * 2 + (tid != 0 ? 1 : 0)) * kTraceStamps + slot] = clock64();
       };
@@ -927,12 +915,8 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
         __threadfence_system();
       }
     };
-    if constexpr (MODE == 2) {  // the launch for straddling strokes; it also takes in-band strokes when it runs dry
-      if (st.flags & kStrokeWindows) {
-        imprint_chain(std::true_type{});
-      } else {
-        imprint_chain(std::false_type{});
-      }
+    if constexpr (MODE == 2) {
+      imprint_chain(std::true_type{});  // this variant is only launched for straddling strokes (capi.cu: run_plan)
     } else {
       imprint_chain(std::false_type{});
     }

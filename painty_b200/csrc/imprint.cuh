@@ -98,15 +98,6 @@ struct ImprintLaunch {
   // straddling strokes (variant with the view chain, on a second stream). Compiled into one kernel, the view chain's
   // register pressure slowed EVERY stroke by 40-50 % (r = 151: 20.6 instead of 13.8 us per imprint). views_kernel selects.
   int views_kernel;
-  // The launch for the straddling strokes may also take strokes of the concurrent in-band launch once its own queue is
-  // empty (it contains both chains): the in-band launch's stroke records, wait lists, claim order and — shared — ticket
-  // counter. Its clusters therefore never idle while the other launch still has unclaimed strokes. Null / 0 otherwise.
-  const DevStroke* strokes2;
-  int64_t n_strokes2;
-  const int2* preds2;
-  const int32_t* seg_off2;
-  const int32_t* order2;
-  int* queue2;
   unsigned long long watchdog_ns;  // longest legitimate dataflow wait (0 = no watchdog), see seg_wait
   int* queue;                    // single counter (zeroed): tickets
   const int32_t* order;          // ticket -> stroke of this launch (host-planned claim order); nullptr = identity
