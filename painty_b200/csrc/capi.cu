@@ -635,12 +635,13 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
       // with it. Each part keeps the run's claim order among its own strokes.
       auto is_views = [&](size_t k) { return (RP.ds[k].flags & kStrokeWindows) != 0; };
       size_t n_views = 0;
-      double imprints_all = 0.0, imprints_views = 0.0;
+      double imprints_all = 0.0, imprints_views = 0.0;  // work = imprints x modelled latency of the footprint
       for (size_t k = 0; k < n_run; ++k) {
-        imprints_all += RP.ds[k].n_imprints;
+        const double w = RP.ds[k].n_imprints * imprint_cost_us(RP.ds[k].n_active, policy);
+        imprints_all += w;
         if (is_views(k)) {
           ++n_views;
-          imprints_views += RP.ds[k].n_imprints;
+          imprints_views += w;
         }
       }
       if (n_views == n_run) {
