@@ -576,29 +576,36 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
       if (!h.g->compact) d.flags |= kStrokeTwoPhase;
       // half width of the undecided band of the single-precision hit test: 3x the error bound of imprint_geom.hpp
       d.eps      = static_cast<float>(1e-6 * ((h.g->side - 1) / 2) + 2e-5);
-      d.win_ox = d.win_cols = 0;
       d.flag_index = static_cast<int32_t>(run_begin + k);
       const int nseg = plan.seg_first[s + 1] - plan.seg_first[s];
       const size_t win_first = run_windows.size();
       run_windows.resize(win_first + static_cast<size_t>(nseg), DevWindow{0, 0, 0, 0});
+      d.win_x0 = d.win_y0 = d.win_cols = d.win_rows = 0;
       if (multi && remote[s]) {
-        // Per dataflow segment, the segment's whole region (own rows and neighbour rows) is staged in a local window.
-        const int half = (h.g->side - 1) / 2;
-        size_t bytes = 0;
+        // The stroke's staging window mirrors its whole region (own rows and neighbour rows); per dataflow segment the
+        // kernel brings the segment's region inside it up to date (imprint.cuh: DevWindow).
+        const Region& r = allowed[s];
+        const int half  = (h.g->side - 1) / 2;
+        if (r.x1 >= r.x0 && r.y1 >= r.y0) {
+          d.win_x0   = r.x0 & ~3;
+          d.win_cols = ((r.x1 - d.win_x0 + 1) + 3) & ~3;
+          d.win_y0   = r.y0;
+          d.win_rows = r.y1 - r.y0 + 1;
+        }
         for (int k2 = 0; k2 < nseg; ++k2) {
           Region sbox, sall;
           const int64_t len = plan.seg_len[s];
           imprint_regions(h.first + k2 * len, std::min<int64_t>(len, h.n - k2 * len), half, h.radius, cx, cy, c->rows, c->cols, sbox,
                           sall);
           DevWindow& w = run_windows[win_first + static_cast<size_t>(k2)];
-          if (sall.y1 < sall.y0 || sall.x1 < sall.x0) continue;  // nothing on the canvas: an empty window
+          if (sall.y1 < sall.y0 || sall.x1 < sall.x0) continue;  // nothing on the canvas: an empty rectangle
           w.x0   = sall.x0 & ~3;
           w.cols = ((sall.x1 - w.x0 + 1) + 3) & ~3;
           w.y0   = sall.y0;
           w.rows = sall.y1 - sall.y0 + 1;
-          bytes  = std::max(bytes, static_cast<size_t>(w.rows) * w.cols * (2 * kRecord * ctx->esize() + 2) + 64);
         }
-        PB_REQUIRE(bytes <= (size_t(2) << 30), "footprint too large for a multi-GPU staging window");
+        const size_t bytes = static_cast<size_t>(d.win_rows) * d.win_cols * (2 * kRecord * ctx->esize() + 2) + 64;
+        PB_REQUIRE(bytes <= (size_t(2) << 30), "stroke too large for a multi-GPU staging window");
         d.flags |= kStrokeWindows;
         max_window = std::max(max_window, (bytes + 255) / 256 * 256);
       }

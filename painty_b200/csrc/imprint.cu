@@ -436,9 +436,9 @@ struct Window {
   T* can;
   T* src;
   unsigned char *dirty, *touched;
-  int x0, y0, rows, cols;
-  __device__ __forceinline__ Window(const ImprintLaunch& L, const DevWindow& dw, int slot) {
-    x0 = dw.x0, y0 = dw.y0, rows = dw.rows, cols = dw.cols;
+  int x0, y0, rows, cols;  // the stroke's frame
+  __device__ __forceinline__ Window(const ImprintLaunch& L, const DevStroke& st, int slot) {
+    x0 = st.win_x0, y0 = st.win_y0, rows = st.win_rows, cols = st.win_cols;
     unsigned char* base = L.win_scratch + static_cast<int64_t>(slot) * L.win_stride;
     const int64_t npx   = static_cast<int64_t>(rows) * cols;
     can     = reinterpret_cast<T*>(base);
@@ -448,40 +448,44 @@ struct Window {
   }
 };
 
-// Build the view of a segment's window (virtual base pointers: index = global row * window cols + column) and fill it.
+// The view of a stroke's window: virtual base pointers, index = global row * window cols + column.
 template <typename T>
-__device__ __forceinline__ void stage_in(const ImprintLaunch& L, const DevWindow& dw, Band<T>* view, int slot, int sgt, int gstride,
-                                         int tid) {
-  const Window<T> W(L, dw, slot);
-  if (tid == 0) {
-    const int64_t off = static_cast<int64_t>(W.y0) * W.cols + W.x0;
-    Band<T> v;
-    v.can     = W.can - off * kRecord;
-    v.src     = W.src - off * kRecord;
-    v.dirty   = W.dirty - off;
-    v.touched = W.touched - off;
-    v.pitch   = W.cols;
-    *view     = v;
-  }
-  const int npx = W.rows * W.cols;
+__device__ __forceinline__ void stage_view(const ImprintLaunch& L, const DevStroke& st, Band<T>* view, int slot) {
+  const Window<T> W(L, st, slot);
+  const int64_t off = static_cast<int64_t>(W.y0) * W.cols + W.x0;
+  Band<T> v;
+  v.can     = W.can - off * kRecord;
+  v.src     = W.src - off * kRecord;
+  v.dirty   = W.dirty - off;
+  v.touched = W.touched - off;
+  v.pitch   = W.cols;
+  *view     = v;
+}
+
+// Pull one rectangle (canvas coordinates, inside the frame) from the bands' HBM into the window; touched flags off.
+template <typename T>
+__device__ __forceinline__ void stage_pull(const ImprintLaunch& L, const Window<T>& W, const Rect& r, int sgt, int gstride) {
+  const int rc = r.x1 - r.x0 + 1, rr = r.y1 - r.y0 + 1;
+  if (rc <= 0 || rr <= 0) return;
+  const int npx = rr * rc;
   // two pixels per thread and iteration: the six loads of a pair are in flight together
 #pragma unroll 1
   for (int i0 = sgt; i0 < npx; i0 += 2 * gstride) {
     Rec<T> a[2], b[2];
     unsigned char dflag[2];
-    int idx[2];
+    int wi[2];
+    bool on[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int i = i0 + u * gstride;
-      idx[u]      = -1;
+      wi[u]       = -1;
       dflag[u]    = 0;
+      on[u]       = false;
       if (i >= npx) continue;
-      const int lr = i / W.cols, c = i - lr * W.cols, px = W.x0 + c, gy = W.y0 + lr;
-      idx[u] = i;
-      if (px >= L.cols || gy >= L.rows) {
-        idx[u] = -2 - i;  // outside the canvas (column padding): only the flags are initialised
-        continue;
-      }
+      const int lr = i / rc, c = i - lr * rc, px = r.x0 + c, gy = r.y0 + lr;
+      wi[u] = (gy - W.y0) * W.cols + (px - W.x0);
+      if (px >= L.cols || gy >= L.rows) continue;  // column padding outside the canvas: only the flags are initialised
+      on[u]            = true;
       const int band   = gy / L.rows_per_band;
       const int64_t gi = static_cast<int64_t>(gy - band * L.rows_per_band) * L.cols + px;
       a[u]     = ld_rec(static_cast<const T*>(L.canvas[band]) + gi * kRecord);
@@ -490,35 +494,58 @@ __device__ __forceinline__ void stage_in(const ImprintLaunch& L, const DevWindow
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      if (idx[u] == -1) continue;
-      const int i = idx[u] >= 0 ? idx[u] : -2 - idx[u];
-      __stcg(W.touched + i, static_cast<unsigned char>(0));
-      __stcg(W.dirty + i, dflag[u]);
-      if (idx[u] >= 0) {
-        st_rec(W.can + static_cast<int64_t>(i) * kRecord, a[u]);
-        st_rec(W.src + static_cast<int64_t>(i) * kRecord, b[u]);
+      if (wi[u] < 0) continue;
+      __stcg(W.touched + wi[u], static_cast<unsigned char>(0));
+      __stcg(W.dirty + wi[u], dflag[u]);
+      if (on[u]) {
+        st_rec(W.can + static_cast<int64_t>(wi[u]) * kRecord, a[u]);
+        st_rec(W.src + static_cast<int64_t>(wi[u]) * kRecord, b[u]);
       }
     }
   }
 }
 
-// Write back only what this segment changed: untouched pixels may meanwhile have been refreshed by a commuting stroke's
-// snapshot ring on their owner (an idempotent copy this window must not undo).
+// Bring the window up to date for a segment: its whole region (`full`: first segment, or other strokes may have written
+// into the region since the previous segment), or only what was not in the previous segment's region.
 template <typename T>
-__device__ __forceinline__ void stage_out(const ImprintLaunch& L, const DevWindow& dw, int slot, int sgt, int gstride) {
-  const Window<T> W(L, dw, slot);
-  const int nwords = W.rows * W.cols / 4;  // the touched map is scanned 4 pixels at a time
-  const int cpr    = W.cols / 4;
+__device__ __forceinline__ void stage_in(const ImprintLaunch& L, const DevStroke& st, const DevWindow& dw, const DevWindow* prev,
+                                         bool full, int slot, int sgt, int gstride) {
+  if (dw.cols <= 0 || dw.rows <= 0) return;
+  const Window<T> W(L, st, slot);
+  const Rect cur{dw.x0, dw.y0, dw.x0 + dw.cols - 1, dw.y0 + dw.rows - 1};
+  if (full || prev == nullptr || prev->cols <= 0 || prev->rows <= 0) {
+    stage_pull<T>(L, W, cur, sgt, gstride);
+    return;
+  }
+  const Rect old{prev->x0, prev->y0, prev->x0 + prev->cols - 1, prev->y0 + prev->rows - 1};
+  RingGeom clip;  // rect_difference clips to an "allowed" box: the current region itself
+  clip.ax0 = cur.x0, clip.ay0 = cur.y0, clip.ax1 = cur.x1, clip.ay1 = cur.y1;
+  clip.tlx = clip.tly = clip.brx = clip.bry = 0;
+  rect_difference(cur, old, clip, [&](const Rect& r) { stage_pull<T>(L, W, r, sgt, gstride); });
+}
+
+// Write back what this segment changed, and only that: untouched pixels may meanwhile have been refreshed by a commuting
+// stroke's snapshot ring on their owner (an idempotent copy this window must not undo). The touched flags are cleared, so
+// a pixel is written back once per segment that touches it.
+template <typename T>
+__device__ __forceinline__ void stage_out(const ImprintLaunch& L, const DevStroke& st, const DevWindow& dw, int slot, int sgt,
+                                          int gstride) {
+  if (dw.cols <= 0 || dw.rows <= 0) return;
+  const Window<T> W(L, st, slot);
+  const int cpr    = dw.cols / 4;  // the touched map is scanned 4 pixels at a time (x0, cols and the frame are 4-aligned)
+  const int nwords = dw.rows * cpr;
 #pragma unroll 1
   for (int i = sgt; i < nwords; i += gstride) {
-    const unsigned t = __ldcg(reinterpret_cast<const unsigned*>(W.touched) + i);
+    const int lr = i / cpr, c = (i - lr * cpr) * 4, gy = dw.y0 + lr;
+    const int wbase = (gy - W.y0) * W.cols + (dw.x0 + c - W.x0);
+    const unsigned t = __ldcg(reinterpret_cast<const unsigned*>(W.touched + wbase));
     if (t == 0u) continue;
-    const int lr = i / cpr, c = (i - lr * cpr) * 4, gy = W.y0 + lr;
+    __stcg(reinterpret_cast<unsigned*>(W.touched + wbase), 0u);
     const int band = gy / L.rows_per_band;
 #pragma unroll 1
     for (int b = 0; b < 4; ++b) {
       if (((t >> (8 * b)) & 0xffu) == 0u) continue;
-      const int wi = lr * W.cols + c + b, px = W.x0 + c + b;
+      const int wi = wbase + b, px = dw.x0 + c + b;
       const int64_t gi = static_cast<int64_t>(gy - band * L.rows_per_band) * L.cols + px;
       const Rec<T> va = ld_rec(W.can + static_cast<int64_t>(wi) * kRecord);
       const Rec<T> vb = ld_rec(W.src + static_cast<int64_t>(wi) * kRecord);
@@ -616,9 +643,9 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
     sync_all();
     const int64_t si = CL ? *cluster.map_shared_rank(&s_stroke, 0) : s_stroke;
     if (si >= L.n_strokes) break;
-    static_assert(sizeof(DevStroke) == 128, "DevStroke is copied in eight 16-byte pieces");
-    if (tid < 8) cp_async16(reinterpret_cast<char*>(&s_st) + 16 * tid, reinterpret_cast<const char*>(L.strokes + si) + 16 * tid);
-    if (tid < 8) cp_async_wait_all();
+    static_assert(sizeof(DevStroke) == 144, "DevStroke is copied in nine 16-byte pieces");
+    if (tid < 9) cp_async16(reinterpret_cast<char*>(&s_st) + 16 * tid, reinterpret_cast<const char*>(L.strokes + si) + 16 * tid);
+    if (tid < 9) cp_async_wait_all();
     __syncthreads();
     const DevStroke& st = s_st;
 
@@ -821,7 +848,8 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
       };
 
       if (VIEWS) {
-        stage_in<T>(L, wins[0], s_view, slot_id(), scan_id(), scan_stride(), tid);
+        if (tid == 0) stage_view<T>(L, st, s_view, slot_id());
+        stage_in<T>(L, st, wins[0], nullptr, true, slot_id(), scan_id(), scan_stride());
         sync_all();
       }
       // The chain is a flat loop over UNITS (imprint ii, border phase ph, cell chunk): process the unit's list, build
@@ -843,17 +871,17 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
             ++seg_k;
             seg_next += st.seg_len;
             if (wins) {  // write the pixels the finished segment touched back into their owners' HBM
-              stage_out<T>(L, wins[seg_k - 1], slot_id(), scan_id(), scan_stride());
+              stage_out<T>(L, st, wins[seg_k - 1], slot_id(), scan_id(), scan_stride());
               __threadfence_system();
               sync_all();
             }
             seg_publish(seg_k);
-            if (seg_wait(seg_k)) need_full = true;
-            if (wins) {
-              stage_in<T>(L, wins[seg_k], s_view, slot_id(), scan_id(), scan_stride(), tid);
+            const bool waited = seg_wait(seg_k);
+            if (waited) need_full = true;
+            if (wins) {  // after a wait other strokes may have written into the region: pull all of it again
+              stage_in<T>(L, st, wins[seg_k], wins + (seg_k - 1), waited, slot_id(), scan_id(), scan_stride());
               sync_all();
-              n_list    = build_list(ii, 0, ph);  // the views (window pitch) may have changed
-              need_full = true;
+              need_full = true;  // newly pulled pixels bring their own dirty flags
             }
           }
           // imprint record ii + 2 -> ring slot (ii + 2) & 3 (nobody reads that slot during this imprint); completed
@@ -911,7 +939,7 @@ __global__ void __launch_bounds__(MAXB, 1) imprint_kernel(const ImprintLaunch L)
         if (done) break;
       }
       if (wins) {
-        stage_out<T>(L, wins[seg_k], slot_id(), scan_id(), scan_stride());
+        stage_out<T>(L, st, wins[seg_k], slot_id(), scan_id(), scan_stride());
         __threadfence_system();
       }
     };

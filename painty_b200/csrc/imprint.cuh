@@ -45,17 +45,21 @@ struct alignas(16) DevStroke {
   int32_t seg_len;    // imprints per dataflow segment (>= 1)
   int32_t flags;      // kStroke*
   float eps;          // half width of the undecided band of the single-precision hit test (imprint_geom.hpp)
-  int32_t win_ox, win_cols;  // unused
   int32_t flag_index;        // progress word of this stroke in the executor's flag array (its number among the rank's strokes)
-  int32_t pad;               // 128 bytes: the kernel copies the record into shared memory in 16-byte pieces
+  // straddling strokes (multi GPU): the frame of the stroke's staging window = its whole region on the canvas
+  // (x0 and cols multiples of 4); the segments' rectangles (DevWindow) lie inside it
+  int32_t win_x0, win_y0, win_cols, win_rows;
+  int32_t pad[3];            // 144 bytes: the kernel copies the record into shared memory in 16-byte pieces
 };
-static_assert(sizeof(DevStroke) == 128, "DevStroke layout");
+static_assert(sizeof(DevStroke) == 144, "DevStroke layout");
 
-// Multi-GPU staging window of one dataflow segment of a straddling stroke: the segment's whole region (union of the
-// allowed boxes of its imprints, clipped to the canvas; x0 and cols multiples of 4) — rows of the executor's own band and
-// of its neighbours alike — is copied into local scratch when the segment starts and the touched pixels are written back
-// when it ends (one bulk transfer each way instead of NVLink round trips on every imprint, and one uniform view for the
-// imprint chain).
+// Multi-GPU staging of a straddling stroke. The stroke owns a local WINDOW that mirrors its whole region of the canvas
+// (DevStroke::win_*: rows of the executor's own band and of its neighbours alike) and gives the imprint chain one uniform
+// view. Per dataflow segment (DevWindow = the segment's region: union of the allowed boxes of its imprints, clipped to
+// the canvas, x0 and cols multiples of 4) the window is brought up to date when the segment starts and the touched pixels
+// are written back when it ends. Bringing up to date = pulling the whole segment region after a wait on other strokes
+// (they may have written into it), otherwise only the part that was not in the previous segment's region — consecutive
+// segments overlap by ~90 %, and without an intervening writer the window is the truth for everything it already holds.
 struct DevWindow {
   int32_t x0, y0, cols, rows;
 };
