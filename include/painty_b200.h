@@ -312,7 +312,10 @@ int pb_fbrush_dist_storage(pb_fbrush* b, pb_canvas* c, void** canvas_records, vo
  *   pb_fbrush_dist_begin (planes -> records, synchronises the stream)  ->  process-group barrier  ->
  *   pb_fbrush_stroke_batch_dist, any number of times                  ->  context sync + process-group barrier  ->
  *   pb_fbrush_dist_end (records -> planes).
- * pb_fbrush_stroke_batch_dist has the contract of pb_fbrush_stroke_batch; every rank passes the SAME global stroke list. */
+ * pb_fbrush_stroke_batch_dist has the contract of pb_fbrush_stroke_batch; every rank passes the SAME global stroke list.
+ * Brush state after the call: radius and paint are those of the last stroke on every rank; the pickup map of the last stroke
+ * is only written back on the rank that executed it — continue with a dip (as every stroke of a batch does) before relying
+ * on it. */
 int pb_fbrush_dist_begin(pb_fbrush* b, pb_canvas* c);
 int pb_fbrush_dist_end(pb_fbrush* b, pb_canvas* c);
 int pb_fbrush_stroke_batch_dist(pb_fbrush* b, pb_canvas* c, const pb_dist_desc* dist, int64_t n_strokes, const pb_stroke* strokes,
