@@ -377,7 +377,7 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
   const size_t n = hs.size();
   static const int kSegmentLength = [] {
     const char* e = std::getenv("PB_IMPRINT_SEGMENT");  // imprints per dataflow segment; 0 = whole strokes
-    return e ? std::max(0, std::atoi(e)) : 64;  // measured 16 / 32 / 64: 8.13 / 8.14 / 8.11 s, whole strokes 9.78 s
+    return e ? std::max(0, std::atoi(e)) : 64;  // 4K bench step, round 2: 16 / 32 / 64 / 128 -> 3.26 / 3.11 / 3.09 / 3.18 s
   }();
   std::vector<int32_t> executor(n, 0), local_index(n, -1);
   std::vector<int32_t> counts(kMaxBands, 0);
