@@ -527,6 +527,19 @@ def main():
                                       "checksum_sha256_KSV": h.hexdigest()[:16],
                                       "what": "every %d-th stroke of the workload rendered on %d GPUs vs on one GPU (rank 0)" % (k, world)}
             del br1, full
+        if rank == 0 and not args.no_cpu:  # the other ranks wait in the barrier below
+            # the same CPU leg as at N = 1, on ONE band's stroke list (every band holds a copy of it): the per-GPU workload on a host core
+            try:  # never leave the other ranks in the barrier because of the reporting leg
+                tile_strokes = build_workload(args.strokes, rows=ROWS, tiles=1)[0]
+                info = cpu_sample(tile_strokes, ROWS, COLS)
+                t = info["t_imprint"] + info["t_compose_full"] * info["n_sample"] / len(tile_strokes)
+                line["cpu_baseline"] = {"value": info["visited"] / t, "unit": "stroke-pixels/s", "cores": 1, "kind": info["kind"],
+                                        "sample": "%d of the %d strokes of one band (%d visited cells, %.1f s imprint single-threaded as "
+                                                  "in the reference); one band's compose %.2f s on %d threads, prorated" % (
+                                                      info["n_sample"], len(tile_strokes), info["visited"], info["t_imprint"],
+                                                      info["t_compose_full"], info["threads"])}
+            except Exception as exc:
+                line["cpu_baseline"] = {"unavailable": str(exc)}
         dist.barrier()
 
     if rank == 0 and not args.no_cpu and world == 1:
