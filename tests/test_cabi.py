@@ -465,21 +465,36 @@ def test_hit_finder_matches_the_forward_mapping(built_lib):
     assert decided > 50 * max(deferred, 1) or deferred < 0.03 * decided  # the fast path decides almost everything
 
 
-def _emulate_queues(n, seg_first, seg_off, ps, pn, order, pool, run, slots, rng):
-    """Discrete-event emulation of the device protocol: per pool and launch, `slots` clusters pop strokes strictly in
-    claim order and block on (stroke, segments needed) waits; segment durations are random. Returns the number of
-    strokes that finished (== n unless the protocol deadlocks)."""
+def _emulate_queues(n, seg_first, seg_off, ps, pn, order, pool, run, slots, rng, sub=None, sub_share=0.25):
+    """Discrete-event emulation of the device protocol: per pool (GPU) the launches (runs) follow each other; within a
+    launch `slots` clusters pop strokes strictly in claim order and block on (stroke, segments needed) waits; segment
+    durations are random. With `sub` (0/1 per stroke) every run is TWO concurrent launches on its pool — sub-queue 1 (the
+    straddlers' launch) gets max(1, sub_share * slots) of the run's clusters, sub-queue 0 the rest — and the next run starts
+    when both have drained (the stream join of the library). Returns the number of strokes that finished (== n unless the
+    protocol deadlocks)."""
     import heapq
 
     nseg = np.diff(seg_first)
+    subs = np.zeros(n, np.int32) if sub is None else np.asarray(sub, np.int32)
+    n_sub = 1 if sub is None else 2
     queues = {}
     for s in order:
-        queues.setdefault((int(pool[s]), int(run[s])), []).append(int(s))
+        queues.setdefault((int(pool[s]), int(run[s]), int(subs[s])), []).append(int(s))
     progress = np.zeros(n, dtype=np.int64)
     cur_run = {p: 0 for p in range(len(slots))}
     head = {k: 0 for k in queues}
     left = {k: len(v) for k, v in queues.items()}
-    state = {p: [None] * max(slots[p][0], 1) if slots[p] else [] for p in range(len(slots))}
+
+    def fresh(p):
+        if cur_run[p] >= len(slots[p]):
+            return [[] for _ in range(n_sub)]
+        total = max(slots[p][cur_run[p]], 1)
+        if n_sub == 1:
+            return [[None] * total]
+        views = max(1, int(sub_share * total))
+        return [[None] * max(total - views, 1), [None] * views]
+
+    state = {p: fresh(p) for p in range(len(slots))}
     events, now, done = [], 0.0, 0
 
     def ready(s, k):
@@ -487,39 +502,40 @@ def _emulate_queues(n, seg_first, seg_off, ps, pn, order, pool, run, slots, rng)
         return all(progress[ps[i]] >= pn[i] for i in range(seg_off[g], seg_off[g + 1]))
 
     def advance(p):
-        nonlocal now
-        while cur_run[p] < len(slots[p]) and left.get((p, cur_run[p]), 0) == 0:
+        while cur_run[p] < len(slots[p]) and all(left.get((p, cur_run[p], q), 0) == 0 for q in range(n_sub)):
             cur_run[p] += 1
-            if cur_run[p] < len(slots[p]):
-                state[p] = [None] * max(slots[p][cur_run[p]], 1)
+            state[p] = fresh(p)
         if cur_run[p] >= len(slots[p]):
             return
-        key = (p, cur_run[p])
-        for i in range(len(state[p])):
-            st = state[p][i]
-            if st is None and head[key] < len(queues[key]):
-                st = state[p][i] = [queues[key][head[key]], 0, False]
-                head[key] += 1
-            if st is not None and not st[2] and ready(st[0], st[1]):
-                st[2] = True
-                heapq.heappush(events, (now + float(rng.uniform(0.2, 3.0)), p, i))
+        for q in range(n_sub):
+            key = (p, cur_run[p], q)
+            if key not in queues:
+                continue
+            for i in range(len(state[p][q])):
+                st = state[p][q][i]
+                if st is None and head[key] < len(queues[key]):
+                    st = state[p][q][i] = [queues[key][head[key]], 0, False]
+                    head[key] += 1
+                if st is not None and not st[2] and ready(st[0], st[1]):
+                    st[2] = True
+                    heapq.heappush(events, (now + float(rng.uniform(0.2, 3.0)), p, q, i))
 
     for p in range(len(slots)):
         advance(p)
     while events:
-        now, p, i = heapq.heappop(events)
-        s, k, _ = state[p][i]
+        now, p, q, i = heapq.heappop(events)
+        s, k, _ = state[p][q][i]
         k += 1
         if k >= nseg[s]:
             progress[s] = 1 << 40
-            state[p][i] = None
-            left[(p, cur_run[p])] -= 1
+            state[p][q][i] = None
+            left[(p, cur_run[p], q)] -= 1
             done += 1
         else:
             progress[s] = k
-            state[p][i] = [s, k, False]
-        for q in range(len(slots)):
-            advance(q)
+            state[p][q][i] = [s, k, False]
+        for r in range(len(slots)):
+            advance(r)
     return done
 
 
@@ -570,6 +586,56 @@ def test_claim_order_protocol_never_deadlocks_on_eight_gpus(built_lib):
         assert _emulate_queues(n, seg_first, seg_off, ps, pn, order, pool, run, slots, np.random.default_rng(trial)) == n
     # the check has teeth: reversing the queues makes later strokes wait for strokes stuck behind them
     assert _emulate_queues(n, seg_first, seg_off, ps, pn, order[::-1], pool, run[::-1] * 0, [[2]] * world, np.random.default_rng(0)) < n
+
+
+def test_paired_launches_drain_in_claim_order(built_lib):
+    """The multi-GPU protocol as it runs today: straddling strokes are segmented like the rest and run in their OWN launch,
+    concurrent with the launch of the in-band strokes of the same run (two in-order queues per GPU and run, clusters split
+    between them, the next run starts when both have drained). Both launches pop in the order of one global claim sequence;
+    the queues must drain under arbitrary timing and for any split of the clusters. Pure host code."""
+    from painty_b200 import api, assets
+
+    rng = np.random.default_rng(5)
+    world, rpb, cols = 4, 320, 640
+    rows = world * rpb
+    n = 900
+    first, count, side, radius, cx, cy = [], [], [], [], [], []
+    for i in range(n):
+        m = int(rng.integers(1, 300))
+        r = float(rng.choice([6.0, 14.0, 30.0, 45.0]))
+        x, y, a = rng.uniform(0, cols), rng.uniform(0, rows), rng.uniform(0, 2 * np.pi)
+        first.append(len(cx)); count.append(m); radius.append(r); side.append(assets.footprint_geometry(r)[3])
+        for _ in range(m):
+            cx.append(x); cy.append(y)
+            a += rng.normal(0, 0.06); x += np.cos(a); y += np.sin(a)
+    cya = np.asarray(cy)
+    pool, straddles = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    for s in range(n):
+        a, m = first[s], count[s]
+        pool[s] = min(min(max(int(cya[a]), 0), rows - 1) // rpb, world - 1)
+        mm = (side[s] - 1) // 2 + radius[s] + 2.0
+        lo = max(0, int(np.floor(cya[a:a + m].min() - mm)))
+        hi = min(rows - 1, int(np.ceil(cya[a:a + m].max() + mm)))
+        straddles[s] = lo < pool[s] * rpb or hi > min((pool[s] + 1) * rpb, rows) - 1
+    assert 0.05 < straddles.mean() < 0.9
+    run, slots, last = np.zeros(n, np.int32), [[] for _ in range(world)], [None] * world
+    for s in range(n):
+        cls = 0 if radius[s] < 35 else 1
+        if last[pool[s]] != cls:
+            slots[pool[s]].append(15 if cls == 0 else 7)
+            last[pool[s]] = cls
+        run[s] = len(slots[pool[s]]) - 1
+    cost = 5.2 + 0.002 * np.asarray(side, dtype=np.float64) ** 2
+    order = api.plan_claim_order(rows, cols, first, count, side, radius, cx, cy, pool, run, cost, slots, 32, True)
+    assert sorted(order) == list(range(n))
+    seg_first, seg_len, seg_off, ps, pn = api.plan_segments(rows, cols, first, count, side, radius, cx, cy, 32, True)
+    assert any(seg_first[s + 1] - seg_first[s] > 1 for s in range(n) if straddles[s])  # straddlers are segmented too
+    for trial, share in enumerate((0.15, 0.3, 0.6)):
+        assert _emulate_queues(n, seg_first, seg_off, ps, pn, order, pool, run, slots, np.random.default_rng(trial), sub=straddles,
+                               sub_share=share) == n
+    # teeth: popping the queues back to front strands later strokes behind earlier ones
+    assert _emulate_queues(n, seg_first, seg_off, ps, pn, order[::-1], pool, run * 0, [[4]] * world, np.random.default_rng(0),
+                           sub=straddles) < n
 
 
 def _dictionary_restatement(tex):
