@@ -10,6 +10,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -521,11 +522,29 @@ void plan_imprints(pb_fbrush* b, pb_canvas* c, const std::vector<HostStroke>& hs
     im.resize(total);
     size_t o = 0;
     for (size_t k = 0; k < mine.size(); ++k) {
-      const HostStroke& h = hs[mine[k]];
-      local_first[k]      = static_cast<int64_t>(o);
-      const int wr        = (h.g->side - 1) / 2;
-      for (int64_t i = h.first; i < h.first + h.n; ++i, ++o) im[o] = make_imprint(cx[i], cy[i], theta[i], wr);  // :95-96
+      local_first[k] = static_cast<int64_t>(o);
+      o += static_cast<size_t>(hs[mine[k]].n);
     }
+    // cos / sin of every imprint in f64 with the host's libm (the reference's values): independent per imprint, so the
+    // strokes are dealt out to a few host threads (PB_HOST_THREADS, default min(cores, 8)); same results for any count
+    static const unsigned kHostThreads = [] {
+      const char* e = std::getenv("PB_HOST_THREADS");
+      const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+      return e ? static_cast<unsigned>(std::max(1, std::atoi(e))) : std::min(hw, 8u);
+    }();
+    const unsigned n_threads = total < (1u << 16) ? 1u : kHostThreads;
+    auto work = [&](unsigned t) {
+      for (size_t k = t; k < mine.size(); k += n_threads) {
+        const HostStroke& h = hs[mine[k]];
+        const int wr        = (h.g->side - 1) / 2;
+        DevImprint* out     = im.data() + local_first[k];
+        for (int64_t i = 0; i < h.n; ++i) out[i] = make_imprint(cx[h.first + i], cy[h.first + i], theta[h.first + i], wr);  // :95-96
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
   }
   const auto t_prep1 = std::chrono::steady_clock::now();
   {
